@@ -1,0 +1,159 @@
+"""CPU tests: pin the oracle.  (1) public constants / known answers, (2) C oracle == Python big-int restatement."""
+import numpy as np
+import pytest
+from oracle import pyref, oracle as orc
+from util import *
+
+P, R = pyref.P, pyref.R
+
+
+def test_public_constants():
+    # alt_bn128 / BN254 parameters (EIP-196) and halo2curves constants quoted in SURVEY.md §8(c)
+    assert P == 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    assert R == 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert (R - 1) % (1 << 28) == 0 and (R - 1) % (1 << 29) != 0
+    assert pyref.ROOT_OF_UNITY == 0x03DDB9F5166D18B798865EA93DD31F743215CF6DD39329C8D34F1ED960C37C9C
+    assert pow(pyref.ROOT_OF_UNITY, 1 << 28, R) == 1 and pow(pyref.ROOT_OF_UNITY, 1 << 27, R) == R - 1
+    assert pow(pyref.ZETA, 3, R) == 1 and pyref.ZETA != 1
+    assert pyref.ZETA == pow(pow(7, (R - 1) // 3, R), 2, R)
+    assert pyref.MONT_R % P == 0x0E0A77C19A07DF2F666EA36F7879462C0A78EB28F5C70B3DD35D438DC58F0D9D
+    assert pyref.MONT_R % R == 0x0E0A77C19A07DF2F666EA36F7879462E36FC76959F60CD29AC96341C4FFFFFFB
+    assert pyref.is_on_curve(pyref.G1)
+
+
+def test_eip196_doubling_vector():
+    # 2*(1,2) on alt_bn128, the EIP-196 ecAdd known answer
+    two_g = pyref.g1_add(pyref.G1, pyref.G1)
+    assert two_g == (
+        0x030644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD3,
+        0x15ED738C0E0A7C92E7845F96B2AE9C0A68A6A449E3538FC7FF3EBF7A5A18A2C4,
+    )
+    g = affine_to_limbs([pyref.G1])[0]
+    out = orc.g1_scalar_mul(mont([2], R)[0], g)
+    assert jac_limbs_to_affine(out) == two_g
+    # group order: r*G = identity, (r-1)*G = -G
+    assert pyref.g1_mul(R - 1, pyref.G1) == pyref.g1_neg(pyref.G1)
+    out = orc.g1_scalar_mul(mont([R - 1], R)[0], g)
+    assert jac_limbs_to_affine(out) == pyref.g1_neg(pyref.G1)
+
+
+@pytest.mark.parametrize("which,m", [(orc.FQ, P), (orc.FR, R)])
+def test_field_ops_vs_python(which, m):
+    rng = np.random.default_rng(1)
+    edge = [0, 1, 2, m - 1, m - 2, (1 << 64) - 1, 1 << 64, (1 << 128) - 1, (1 << 253), m >> 1]
+    a = edge + rand_ints(rng, 200, m)
+    b = list(reversed(edge)) + rand_ints(rng, 200, m)
+    A, B = mont(a, m), mont(b, m)
+    assert unmont(orc.f_mul(which, A, B), m) == [x * y % m for x, y in zip(a, b)]
+    assert unmont(orc.f_add(which, A, B), m) == [(x + y) % m for x, y in zip(a, b)]
+    assert unmont(orc.f_sub(which, A, B), m) == [(x - y) % m for x, y in zip(a, b)]
+    assert unmont(orc.f_inv(which, A), m) == [pow(x, -1, m) if x else 0 for x in a]
+    assert limbs_to_ints(orc.from_mont(which, A)) == a
+    assert limbs_to_ints(orc.to_mont(which, ints_to_limbs(a))) == limbs_to_ints(A)
+
+
+def test_msm_naive_and_pippenger_vs_python():
+    rng = np.random.default_rng(2)
+    n = 40
+    pts = progression_points(n, a0=5, delta=3)
+    pts[7] = None  # identity base (halo2-ecc/src/ecc/pippenger.rs:216-218 edge)
+    pts[9] = pts[8]  # repeated base
+    sc = rand_ints(rng, n, R)
+    sc[0], sc[1], sc[2] = 0, 1, R - 1  # halo2-ecc/src/secp256k1/tests/mod.rs:87-109 edge scalars
+    want = pyref.msm_naive(sc, pts)
+    S, B = mont(sc, R), affine_to_limbs(pts)
+    assert jac_limbs_to_affine(orc.msm_naive(S, B)) == want
+    for t in (1, 3, 8):
+        assert jac_limbs_to_affine(orc.msm_pippenger(S, B, t)) == want
+
+
+def test_msm_sums_to_infinity():
+    # halo2-ecc/src/bn254/tests/msm_sum_infinity.rs:16-69: P, P with scalars s, -s
+    pts = [pyref.g1_mul(11, pyref.G1)] * 2
+    S, B = mont([5, R - 5], R), affine_to_limbs(pts)
+    for out in (orc.msm_naive(S, B), orc.msm_pippenger(S, B, 2)):
+        assert jac_limbs_to_affine(out) is None
+        assert limbs_to_ints(out.reshape(3, 4))[2] == 0
+
+
+def test_msm_pippenger_closed_form_large():
+    # bases a_i*G, a_i = a0 + i*delta  =>  MSM == (sum s_i a_i mod r) * G   
+    rng = np.random.default_rng(3)
+    n = 3000
+    pts = progression_points(n, a0=123456789, delta=987654321)
+    sc = witness_like_ints(rng, n // 2) + rand_ints(rng, n - n // 2, R)
+    k = sum(s * (123456789 + i * 987654321) for i, s in enumerate(sc)) % R
+    want = pyref.g1_mul(k, pyref.G1)
+    assert jac_limbs_to_affine(orc.msm_pippenger(mont(sc, R), affine_to_limbs(pts))) == want
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 5, 8])
+def test_ntt_vs_dft(k):
+    rng = np.random.default_rng(10 + k)
+    n = 1 << k
+    a = rand_ints(rng, n, R)
+    w = pyref.omega_for(k)
+    assert unmont(orc.omega(k), R) == [w]
+    want = pyref.dft(a, w) if k <= 5 else pyref.ntt(a, w)
+    assert unmont(orc.ntt(mont(a, R), k, mont([w], R)[0]), R) == want
+    assert unmont(orc.coeff_to_lagrange(mont(a, R), k), R) == want
+    assert unmont(orc.lagrange_to_coeff(mont(want, R), k), R) == a
+
+
+def test_coset_extended_round_trip_and_definition():
+    rng = np.random.default_rng(20)
+    k, ext_k = 4, 6
+    a = rand_ints(rng, 1 << k, R)
+    ext = pyref.coeff_to_extended(a, k, ext_k)
+    # definition: evaluations of a(X) on the coset zeta * <extended_omega>
+    we = pyref.omega_for(ext_k)
+    for i in (0, 1, 17, 63):
+        x = pyref.ZETA * pow(we, i, R) % R
+        assert ext[i] == sum(c * pow(x, j, R) for j, c in enumerate(a)) % R
+    got = orc.coeff_to_extended(mont(a, R), ext_k)
+    assert unmont(got, R) == ext
+    back = orc.extended_to_coeff(got, ext_k)
+    assert unmont(back, R) == a + [0] * ((1 << ext_k) - (1 << k))
+    assert pyref.extended_to_coeff(ext, k, ext_k, 3) == a + [0] * (3 * (1 << k) - (1 << k))
+
+
+def test_assign_witnesses_vs_python_walk():
+    rng = np.random.default_rng(30)
+    k, ncols, min_rows = 6, 4, 9
+    max_rows = (1 << k) - min_rows
+    # threads with random lengths and a basic-gate-like selector pattern (q every 4th cell of a gate)
+    threads, sels = [], []
+    total = 0
+    while total < 3 * max_rows + 17:
+        ln = int(rng.integers(0, 40))
+        threads.append([int(v) for v in rng.integers(1, 1 << 62, size=ln)])
+        sels.append([(j % 4 == 0) and (j + 3 < ln) for j in range(ln)])
+        total += ln
+    bps = pyref.break_points_for(sels, max_rows)
+    assert len(bps) == 3
+    want = pyref.assign_witnesses(threads, bps, ncols, 1 << k)
+    flat = [v for t in threads for v in t]
+    rc, cols = orc.assign_witnesses(ints_to_limbs(flat), np.array(bps, dtype=np.uint64), k, ncols)
+    assert rc == 0
+    for c in range(ncols):
+        assert limbs_to_ints(cols[c]) == want[c]
+    # closed form of SURVEY.md Appendix A.2
+    s = 0
+    for c, b in enumerate(bps):
+        assert want[c][: b + 1] == flat[s : s + b + 1]
+        s += b
+    assert want[len(bps)][: len(flat) - s] == flat[s:]
+    # too few columns -> Rust would panic (index out of bounds, single_phase.rs:304)
+    rc, _ = orc.assign_witnesses(ints_to_limbs(flat), np.array(bps, dtype=np.uint64), k, 3)
+    assert rc == -1
+    with pytest.raises(IndexError):
+        pyref.assign_witnesses(threads, bps, 3, 1 << k)
+
+
+def test_assign_lookups_vs_python():
+    vals = list(range(1, 30))
+    want = pyref.assign_lookups(vals, 3, 16)
+    rc, cols = orc.assign_lookups(ints_to_limbs(vals), 4, 3)
+    assert rc == 0
+    for c in range(3):
+        assert limbs_to_ints(cols[c]) == want[c]
