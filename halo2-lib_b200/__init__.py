@@ -1,0 +1,16 @@
+"""halo2-lib_b200 — host-side mirror (Python, for tests / bench plumbing) of the prover interfaces that the
+B200 back end implements behind the C ABI of include/h2b200.h.  The C++ mirror for a compiled host is
+include/h2b200.hpp; the Rust binding a maintainer adds is shown in INTEGRATION.md."""
+from ._capi import lib, LIB_PATH, SIGNATURES, header_symbols  # noqa: F401
+from .host import (  # noqa: F401
+    H2BError,
+    LayoutError,
+    Context,
+    ParamsKZG,
+    EvaluationDomain,
+    best_multiexp,
+    best_fft,
+    assign_witnesses,
+    assign_lookups,
+    omega,
+)

@@ -1,0 +1,83 @@
+"""ctypes binding of libh2b200.so — exactly the symbols include/h2b200.h declares.
+
+There is no fallback: if the shared library is missing the import fails, and if no CUDA device is present
+`Context()` raises (h2b_ctx_create returns H2B_ERR_CUDA)."""
+from __future__ import annotations
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libh2b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "h2b200.h")
+
+H2B_OK, H2B_ERR_ARG, H2B_ERR_CUDA, H2B_ERR_OOM, H2B_ERR_LAYOUT = 0, -1, -2, -3, -4
+BASIS_MONOMIAL, BASIS_LAGRANGE = 0, 1
+
+_vp, _sz, _u32, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
+_u64p = C.POINTER(C.c_uint64)
+
+# name -> (restype, argtypes)
+SIGNATURES = {
+    "h2b_version": (C.c_char_p, []),
+    "h2b_ctx_create": (_int, [_int, C.POINTER(_vp)]),
+    "h2b_ctx_destroy": (None, [_vp]),
+    "h2b_ctx_set_stream": (_int, [_vp, _vp]),
+    "h2b_ctx_synchronize": (_int, [_vp]),
+    "h2b_last_error": (C.c_char_p, [_vp]),
+    "h2b_kernel_launches": (C.c_uint64, [_vp]),
+    "h2b_srs_upload": (_int, [_vp, _vp, _vp, _u32, _sz, _sz, C.POINTER(_vp)]),
+    "h2b_srs_upload_dev": (_int, [_vp, _vp, _vp, _u32, _sz, _sz, C.POINTER(_vp)]),
+    "h2b_srs_destroy": (None, [_vp, _vp]),
+    "h2b_msm_g1": (_int, [_vp, _vp, _int, _vp, _sz, _vp]),
+    "h2b_msm_g1_batch": (_int, [_vp, _vp, _int, C.POINTER(_vp), _sz, _sz, _vp]),
+    "h2b_msm_g1_bases": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_msm_g1_dev": (_int, [_vp, _vp, _int, _vp, _sz, _vp]),
+    "h2b_msm_g1_bases_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_g1_sum": (_int, [_vp, _vp, _sz, _vp]),
+    "h2b_g1_sum_dev": (_int, [_vp, _vp, _sz, _vp]),
+    "h2b_g1_normalize": (_int, [_vp, _vp, _sz]),
+    "h2b_g1_fixed_base_mul": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_g1_fixed_base_mul_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_ntt_fr": (_int, [_vp, _vp, _u32, _vp, _int]),
+    "h2b_ntt_fr_dev": (_int, [_vp, _vp, _u32, _vp, _int]),
+    "h2b_domain_omega": (_int, [_u32, _vp]),
+    "h2b_lagrange_to_coeff": (_int, [_vp, _vp, _u32]),
+    "h2b_coeff_to_lagrange": (_int, [_vp, _vp, _u32]),
+    "h2b_lagrange_to_coeff_dev": (_int, [_vp, _vp, _u32]),
+    "h2b_coeff_to_lagrange_dev": (_int, [_vp, _vp, _u32]),
+    "h2b_coeff_to_extended": (_int, [_vp, _vp, _sz, _u32, _vp]),
+    "h2b_coeff_to_extended_dev": (_int, [_vp, _vp, _sz, _u32, _vp]),
+    "h2b_extended_to_coeff": (_int, [_vp, _vp, _u32]),
+    "h2b_extended_to_coeff_dev": (_int, [_vp, _vp, _u32]),
+    "h2b_assign_columns": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _sz, _vp]),
+    "h2b_assign_columns_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _sz, _vp]),
+    "h2b_assign_lookups": (_int, [_vp, _vp, _sz, _u32, _sz, _vp]),
+    "h2b_assign_lookups_dev": (_int, [_vp, _vp, _sz, _u32, _sz, _vp]),
+    "h2b_eval_rational": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_eval_rational_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_test_field_op": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp]),
+}
+
+
+def header_symbols() -> list[str]:
+    """Function names declared in include/h2b200.h (used by the CPU test that every symbol is exported)."""
+    txt = open(HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(h2b_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load()

@@ -1,0 +1,447 @@
+// capi.cu — the extern "C" surface declared in include/h2b200.h: context, SRS handles, staging of host buffers.
+// No exception leaves this file: every entry point maps failures to a status code + h2b_last_error().
+#include <cstring>
+
+#include "h2b_internal.cuh"
+
+namespace h2b {
+void msm_run_adhoc(h2b_ctx* ctx, const void* d_bases, size_t n, const void* d_scalars, void* d_out);
+static std::string g_create_error;
+static std::mutex g_create_mu;
+}  // namespace h2b
+
+using namespace h2b;
+
+void* h2b_ctx::get(int slot, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    Buf& b = ws[slot];
+    if (b.cap >= bytes) return b.p;
+    if (b.p) {
+        H2B_CUDA(cudaDeviceSynchronize());
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 8;
+    cap = (cap + 255) & ~(size_t)255;
+    H2B_CUDA(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return b.p;
+}
+void* h2b_ctx::get_pinned(int slot, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    Buf& b = pinned[slot];
+    if (b.cap >= bytes) return b.p;
+    if (b.p) {
+        H2B_CUDA(cudaDeviceSynchronize());
+        cudaFreeHost(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    H2B_CUDA(cudaMallocHost(&b.p, bytes));
+    b.cap = bytes;
+    return b.p;
+}
+
+// Runs `body` under the context lock with the context's device current; translates every failure.
+template <class Fn>
+static int guarded(h2b_ctx* ctx, Fn&& body) {
+    if (!ctx) return H2B_ERR_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        H2B_CUDA(cudaSetDevice(ctx->device));
+        body();
+        return H2B_OK;
+    } catch (const StatusError& e) {
+        ctx->err = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        ctx->err = "host allocation failed";
+        return H2B_ERR_OOM;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return H2B_ERR_CUDA;
+    } catch (...) {
+        ctx->err = "unknown failure";
+        return H2B_ERR_CUDA;
+    }
+}
+
+extern "C" {
+
+const char* h2b_version(void) { return "h2b200 0.1.0 (sm_100a)"; }
+
+int h2b_ctx_create(int device, h2b_ctx** out) {
+    if (!out) return H2B_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(g_create_mu);
+    h2b_ctx* ctx = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw StatusError{H2B_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0")};
+        if (device < 0 || device >= ndev) throw StatusError{H2B_ERR_ARG, "device index out of range"};
+        H2B_CUDA(cudaSetDevice(device));
+        ctx = new h2b_ctx();
+        ctx->device = device;
+        H2B_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : ctx->ev) H2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->stream = ctx->own_stream;
+        cudaDeviceProp prop;
+        H2B_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        *out = ctx;
+        return H2B_OK;
+    } catch (const StatusError& e) {
+        g_create_error = e.msg;
+        delete ctx;
+        return e.code;
+    } catch (...) {
+        g_create_error = "unknown failure in h2b_ctx_create";
+        delete ctx;
+        return H2B_ERR_CUDA;
+    }
+}
+
+void h2b_ctx_destroy(h2b_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ntt_free_plans(ctx);
+    for (auto& b : ctx->ws)
+        if (b.p) cudaFree(b.p);
+    for (auto& b : ctx->pinned)
+        if (b.p) cudaFreeHost(b.p);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int h2b_ctx_set_stream(h2b_ctx* ctx, void* cuda_stream) {
+    return guarded(ctx, [&] { ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream; });
+}
+int h2b_ctx_synchronize(h2b_ctx* ctx) {
+    return guarded(ctx, [&] { H2B_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+const char* h2b_last_error(const h2b_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint64_t h2b_kernel_launches(const h2b_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ SRS
+static void srs_build(h2b_ctx* ctx, const void* d_g, const void* d_gl, uint32_t k, size_t begin, size_t count, h2b_srs** out) {
+    H2B_REQUIRE(out, "srs: null output handle");
+    H2B_REQUIRE(k <= 27, "srs: k out of range");
+    H2B_REQUIRE(count >= 1 && begin + count <= ((size_t)1 << k), "srs: shard [begin, begin+count) outside the 2^k bases");
+    H2B_REQUIRE(d_g || d_gl, "srs: both base arrays are null");
+    h2b_srs* s = new h2b_srs();
+    s->k = k;
+    s->begin = begin;
+    s->count = count;
+    s->c = msm_choose_c_fixed(count);
+    s->W = (255 + s->c - 1) / s->c;
+    try {
+        const void* src[2] = {d_g, d_gl};
+        for (int b = 0; b < 2; b++) {
+            if (!src[b]) continue;
+            H2B_CUDA(cudaMalloc(&s->table[b], (size_t)s->W * count * 64));
+            msm_build_table(ctx, src[b], count, s->c, s->W, s->table[b]);
+        }
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        for (auto& t : s->table)
+            if (t) cudaFree(t);
+        delete s;
+        throw;
+    }
+    *out = s;
+}
+
+int h2b_srs_upload(h2b_ctx* ctx, const uint64_t* g, const uint64_t* g_lagrange, uint32_t k, size_t begin, size_t count,
+                   h2b_srs** out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(k <= 27 && count >= 1 && begin + count <= ((size_t)1 << k), "srs: bad shard");
+        const uint64_t* host[2] = {g, g_lagrange};
+        void* dev[2] = {nullptr, nullptr};
+        int slot[2] = {WS_BASES, WS_MISC2};
+        for (int b = 0; b < 2; b++) {
+            if (!host[b]) continue;
+            dev[b] = ctx->get(slot[b], count * 64);
+            H2B_CUDA(cudaMemcpyAsync(dev[b], host[b] + 8 * begin, count * 64, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        srs_build(ctx, dev[0], dev[1], k, begin, count, out);
+    });
+}
+int h2b_srs_upload_dev(h2b_ctx* ctx, const void* d_g, const void* d_g_lagrange, uint32_t k, size_t begin, size_t count,
+                       h2b_srs** out) {
+    return guarded(ctx, [&] { srs_build(ctx, d_g, d_g_lagrange, k, begin, count, out); });
+}
+void h2b_srs_destroy(h2b_ctx* ctx, h2b_srs* srs) {
+    if (!srs) return;
+    if (ctx) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+    }
+    for (auto& t : srs->table)
+        if (t) cudaFree(t);
+    delete srs;
+}
+
+// ------------------------------------------------------------------------------------------------ MSM
+static const void* srs_table(const h2b_srs* srs, int basis, size_t n) {
+    H2B_REQUIRE(srs, "msm: null SRS handle");
+    H2B_REQUIRE(basis == H2B_BASIS_MONOMIAL || basis == H2B_BASIS_LAGRANGE, "msm: basis must be 0 (monomial) or 1 (lagrange)");
+    H2B_REQUIRE(srs->table[basis], "msm: this basis was not uploaded");
+    H2B_REQUIRE(n == srs->count, "msm: scalar count must equal the SRS shard size");
+    return srs->table[basis];
+}
+
+int h2b_msm_g1_dev(h2b_ctx* ctx, const h2b_srs* srs, int basis, const void* d_scalars, size_t n, void* d_out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_scalars && d_out, "msm: null pointer");
+        const void* t = srs_table(srs, basis, n);
+        msm_run(ctx, t, n, srs->c, srs->W, srs->W, d_scalars, d_out);
+    });
+}
+int h2b_msm_g1_bases_dev(h2b_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_bases && d_scalars && d_out && n >= 1, "msm: null pointer or n == 0");
+        msm_run_adhoc(ctx, d_bases, n, d_scalars, d_out);
+    });
+}
+int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* const* scalars, size_t m, size_t n,
+                     uint64_t* out_xyz) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(scalars && out_xyz, "msm: null pointer");
+        const void* t = srs_table(srs, basis, n);
+        if (m == 0) return;
+        void* stage[2] = {ctx->get(WS_SCALARS, n * 32), ctx->get(WS_SCALARS2, n * 32)};
+        void* d_out = ctx->get(WS_OUT, m * 96);
+        cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+        // ev[0..1]: staging buffer b filled; ev[2..3]: staging buffer b consumed
+        for (size_t j = 0; j < m; j++) {
+            int b = (int)(j & 1);
+            H2B_REQUIRE(scalars[j], "msm: null scalar column");
+            if (j >= 2) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2 + b], 0));
+            else if (j == 0) {  // order the first upload after whatever the compute stream was doing with the buffers
+                H2B_CUDA(cudaEventRecord(ctx->ev[2], ks));
+                H2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2], 0));
+            }
+            H2B_CUDA(cudaMemcpyAsync(stage[b], scalars[j], n * 32, cudaMemcpyHostToDevice, cs));
+            H2B_CUDA(cudaEventRecord(ctx->ev[b], cs));
+            H2B_CUDA(cudaStreamWaitEvent(ks, ctx->ev[b], 0));
+            msm_run(ctx, t, n, srs->c, srs->W, srs->W, stage[b], (char*)d_out + 96 * j);
+            H2B_CUDA(cudaEventRecord(ctx->ev[2 + b], ks));
+        }
+        H2B_CUDA(cudaMemcpyAsync(out_xyz, d_out, m * 96, cudaMemcpyDeviceToHost, ks));
+        H2B_CUDA(cudaStreamSynchronize(ks));
+    });
+}
+int h2b_msm_g1(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
+    const uint64_t* cols[1] = {scalars};
+    if (!scalars) return guarded(ctx, [&] { H2B_REQUIRE(false, "msm: null pointer"); });
+    return h2b_msm_g1_batch(ctx, srs, basis, cols, 1, n, out_xyz);
+}
+int h2b_msm_g1_bases(h2b_ctx* ctx, const uint64_t* bases, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(bases && scalars && out_xyz && n >= 1, "msm: null pointer or n == 0");
+        void* d_b = ctx->get(WS_BASES, n * 64);
+        void* d_s = ctx->get(WS_SCALARS, n * 32);
+        void* d_o = ctx->get(WS_OUT, 96);
+        H2B_CUDA(cudaMemcpyAsync(d_b, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+        H2B_CUDA(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        msm_run_adhoc(ctx, d_b, n, d_s, d_o);
+        H2B_CUDA(cudaMemcpyAsync(out_xyz, d_o, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_g1_sum_dev(h2b_ctx* ctx, const void* d_points_xyz, size_t m, void* d_out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_points_xyz && d_out, "g1_sum: null pointer");
+        g1_sum_run(ctx, d_points_xyz, m, d_out);
+    });
+}
+int h2b_g1_sum(h2b_ctx* ctx, const uint64_t* points_xyz, size_t m, uint64_t out_xyz[12]) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(points_xyz && out_xyz, "g1_sum: null pointer");
+        void* d_p = ctx->get(WS_MISC, m * 96 + 96);
+        void* d_o = (char*)d_p + m * 96;
+        H2B_CUDA(cudaMemcpyAsync(d_p, points_xyz, m * 96, cudaMemcpyHostToDevice, ctx->stream));
+        g1_sum_run(ctx, d_p, m, d_o);
+        H2B_CUDA(cudaMemcpyAsync(out_xyz, d_o, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_g1_normalize(h2b_ctx* ctx, uint64_t* points_xyz, size_t m) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(points_xyz, "g1_normalize: null pointer");
+        if (m == 0) return;
+        void* d_p = ctx->get(WS_MISC, m * 96);
+        H2B_CUDA(cudaMemcpyAsync(d_p, points_xyz, m * 96, cudaMemcpyHostToDevice, ctx->stream));
+        g1_normalize_run(ctx, d_p, m);
+        H2B_CUDA(cudaMemcpyAsync(points_xyz, d_p, m * 96, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_g1_fixed_base_mul_dev(h2b_ctx* ctx, const uint64_t base_xy[8], const void* d_scalars, size_t n, void* d_out_xy) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(base_xy && d_scalars && d_out_xy, "fixed_base_mul: null pointer");
+        g1_fixed_base_mul_run(ctx, base_xy, d_scalars, n, d_out_xy);
+    });
+}
+int h2b_g1_fixed_base_mul(h2b_ctx* ctx, const uint64_t base_xy[8], const uint64_t* scalars, size_t n, uint64_t* out_xy) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(base_xy && scalars && out_xy, "fixed_base_mul: null pointer");
+        if (n == 0) return;
+        void* d_s = ctx->get(WS_SCALARS, n * 32);
+        void* d_o = ctx->get(WS_BASES, n * 64);
+        H2B_CUDA(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        g1_fixed_base_mul_run(ctx, base_xy, d_s, n, d_o);
+        H2B_CUDA(cudaMemcpyAsync(out_xy, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ NTT
+int h2b_domain_omega(uint32_t k, uint64_t omega_out[4]) {
+    if (!omega_out || k > 28) return H2B_ERR_ARG;
+    domain_omega(k, omega_out, false);
+    return H2B_OK;
+}
+// mode: 0 plain (omega given), 1 lagrange_to_coeff, 2 coeff_to_lagrange, 3 extended_to_coeff
+static void ntt_inplace_dev(h2b_ctx* ctx, void* d_a, uint32_t log_n, const uint64_t* omega, int scale, int mode) {
+    H2B_REQUIRE(d_a, "ntt: null pointer");
+    H2B_REQUIRE(log_n <= 28, "ntt: log_n exceeds the two-adicity of Fr (28)");
+    uint64_t w[4];
+    int coset = 0;
+    if (mode == 0) { H2B_REQUIRE(omega, "ntt: null omega"); memcpy(w, omega, 32); }
+    else if (mode == 2) domain_omega(log_n, w, false);
+    else { domain_omega(log_n, w, true); scale = 1; if (mode == 3) coset = 2; }
+    ntt_run(ctx, d_a, (size_t)1 << log_n, d_a, log_n, w, scale, coset);
+}
+static void ntt_inplace_host(h2b_ctx* ctx, uint64_t* a, uint32_t log_n, const uint64_t* omega, int scale, int mode) {
+    H2B_REQUIRE(a, "ntt: null pointer");
+    H2B_REQUIRE(log_n <= 28, "ntt: log_n exceeds the two-adicity of Fr (28)");
+    size_t bytes = ((size_t)1 << log_n) * 32;
+    void* d = ctx->get(WS_NTT_A, bytes);
+    H2B_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ntt_inplace_dev(ctx, d, log_n, omega, scale, mode);
+    H2B_CUDA(cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+int h2b_ntt_fr(h2b_ctx* ctx, uint64_t* a, uint32_t log_n, const uint64_t omega[4], int scale_by_n_inv) {
+    return guarded(ctx, [&] { ntt_inplace_host(ctx, a, log_n, omega, scale_by_n_inv, 0); });
+}
+int h2b_ntt_fr_dev(h2b_ctx* ctx, void* d_a, uint32_t log_n, const uint64_t omega[4], int scale_by_n_inv) {
+    return guarded(ctx, [&] { ntt_inplace_dev(ctx, d_a, log_n, omega, scale_by_n_inv, 0); });
+}
+int h2b_lagrange_to_coeff(h2b_ctx* ctx, uint64_t* a, uint32_t k) { return guarded(ctx, [&] { ntt_inplace_host(ctx, a, k, nullptr, 1, 1); }); }
+int h2b_coeff_to_lagrange(h2b_ctx* ctx, uint64_t* a, uint32_t k) { return guarded(ctx, [&] { ntt_inplace_host(ctx, a, k, nullptr, 0, 2); }); }
+int h2b_lagrange_to_coeff_dev(h2b_ctx* ctx, void* d_a, uint32_t k) { return guarded(ctx, [&] { ntt_inplace_dev(ctx, d_a, k, nullptr, 1, 1); }); }
+int h2b_coeff_to_lagrange_dev(h2b_ctx* ctx, void* d_a, uint32_t k) { return guarded(ctx, [&] { ntt_inplace_dev(ctx, d_a, k, nullptr, 0, 2); }); }
+int h2b_extended_to_coeff(h2b_ctx* ctx, uint64_t* a, uint32_t ext_k) { return guarded(ctx, [&] { ntt_inplace_host(ctx, a, ext_k, nullptr, 1, 3); }); }
+int h2b_extended_to_coeff_dev(h2b_ctx* ctx, void* d_a, uint32_t ext_k) { return guarded(ctx, [&] { ntt_inplace_dev(ctx, d_a, ext_k, nullptr, 1, 3); }); }
+
+int h2b_coeff_to_extended_dev(h2b_ctx* ctx, const void* d_coeffs, size_t n_coeffs, uint32_t ext_k, void* d_out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_coeffs && d_out, "coeff_to_extended: null pointer");
+        H2B_REQUIRE(ext_k <= 28 && n_coeffs <= ((size_t)1 << ext_k), "coeff_to_extended: sizes out of range");
+        uint64_t w[4];
+        domain_omega(ext_k, w, false);
+        ntt_run(ctx, d_coeffs, n_coeffs, d_out, ext_k, w, 0, 1);
+    });
+}
+int h2b_coeff_to_extended(h2b_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, uint32_t ext_k, uint64_t* out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(coeffs && out, "coeff_to_extended: null pointer");
+        H2B_REQUIRE(ext_k <= 28 && n_coeffs <= ((size_t)1 << ext_k), "coeff_to_extended: sizes out of range");
+        size_t bytes = ((size_t)1 << ext_k) * 32;
+        void* d = ctx->get(WS_NTT_A, bytes);
+        H2B_CUDA(cudaMemcpyAsync(d, coeffs, n_coeffs * 32, cudaMemcpyHostToDevice, ctx->stream));
+        uint64_t w[4];
+        domain_omega(ext_k, w, false);
+        ntt_run(ctx, d, n_coeffs, d, ext_k, w, 0, 1);
+        H2B_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ assignment
+int h2b_assign_columns_dev(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64_t* break_points, size_t nbp, uint32_t k,
+                           size_t ncols, void* d_cols) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((d_vcol || N == 0) && (d_cols || ncols == 0) && (break_points || nbp == 0), "assign: null pointer");
+        assign_columns_run(ctx, d_vcol, N, break_points, nbp, k, ncols, d_cols);
+    });
+}
+int h2b_assign_columns(h2b_ctx* ctx, const uint64_t* vcol, size_t N, const uint64_t* break_points, size_t nbp, uint32_t k,
+                       size_t ncols, uint64_t* cols) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((vcol || N == 0) && (cols || ncols == 0) && (break_points || nbp == 0), "assign: null pointer");
+        H2B_REQUIRE(k <= 28, "assign: k out of range");
+        size_t out_bytes = (ncols << k) * 32;
+        void* d_in = ctx->get(WS_ASSIGN_IN, N * 32);
+        void* d_out = ctx->get(WS_ASSIGN_OUT, out_bytes);
+        if (N) H2B_CUDA(cudaMemcpyAsync(d_in, vcol, N * 32, cudaMemcpyHostToDevice, ctx->stream));
+        assign_columns_run(ctx, d_in, N, break_points, nbp, k, ncols, d_out);
+        if (out_bytes) H2B_CUDA(cudaMemcpyAsync(cols, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_assign_lookups_dev(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((d_vals || N == 0) && (d_cols || L == 0), "assign: null pointer");
+        assign_lookups_run(ctx, d_vals, N, k, L, d_cols);
+    });
+}
+int h2b_assign_lookups(h2b_ctx* ctx, const uint64_t* vals, size_t N, uint32_t k, size_t L, uint64_t* cols) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((vals || N == 0) && (cols || L == 0), "assign: null pointer");
+        H2B_REQUIRE(k <= 28, "assign: k out of range");
+        size_t out_bytes = (L << k) * 32;
+        void* d_in = ctx->get(WS_ASSIGN_IN, N * 32);
+        void* d_out = ctx->get(WS_ASSIGN_OUT, out_bytes);
+        if (N) H2B_CUDA(cudaMemcpyAsync(d_in, vals, N * 32, cudaMemcpyHostToDevice, ctx->stream));
+        assign_lookups_run(ctx, d_in, N, k, L, d_out);
+        if (out_bytes) H2B_CUDA(cudaMemcpyAsync(cols, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_eval_rational_dev(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((d_num && d_den && d_out) || n == 0, "eval_rational: null pointer");
+        eval_rational_run(ctx, d_num, d_den, n, d_out);
+    });
+}
+int h2b_eval_rational(h2b_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((num && den && out) || n == 0, "eval_rational: null pointer");
+        if (n == 0) return;
+        char* d = (char*)ctx->get(WS_ASSIGN_IN, 3 * n * 32);
+        H2B_CUDA(cudaMemcpyAsync(d, num, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        H2B_CUDA(cudaMemcpyAsync(d + n * 32, den, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        eval_rational_run(ctx, d, d + n * 32, n, d + 2 * n * 32);
+        H2B_CUDA(cudaMemcpyAsync(out, d + 2 * n * 32, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ test hook
+int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(a && out && (b || op > 2) && (field == 0 || field == 1) && op >= 0 && op <= 5, "field_op: bad argument");
+        if (n == 0) return;
+        char* d = (char*)ctx->get(WS_ASSIGN_IN, 3 * n * 32);
+        H2B_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        if (b) H2B_CUDA(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        field_op_run(ctx, field, op, d, d + n * 32, n, d + 2 * n * 32);
+        H2B_CUDA(cudaMemcpyAsync(out, d + 2 * n * 32, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// h2b_internal.cuh — context, workspace and launch helpers shared by the translation units of libh2b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <array>
+
+#include "../../include/h2b200.h"
+
+namespace h2b {
+
+struct StatusError {
+    int code;
+    std::string msg;
+};
+
+#define H2B_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw h2b::StatusError{_e == cudaErrorMemoryAllocation ? H2B_ERR_OOM : H2B_ERR_CUDA,    \
+                                   std::string(#expr) + ": " + cudaGetErrorString(_e)};             \
+    } while (0)
+#define H2B_REQUIRE(cond, msg)                                                   \
+    do {                                                                         \
+        if (!(cond)) throw h2b::StatusError{H2B_ERR_ARG, std::string(msg)};      \
+    } while (0)
+
+// grow-only device workspace slots (freed with the context)
+enum WsSlot {
+    WS_SCALARS = 0,   // staged scalars of host-pointer MSM calls (two of them for double buffering)
+    WS_SCALARS2,
+    WS_KEYS_A,
+    WS_KEYS_B,
+    WS_VALS_A,
+    WS_VALS_B,
+    WS_SORT_TMP,
+    WS_OFFSETS,
+    WS_BUCKETS,
+    WS_PARTIALS,
+    WS_BIGLIST,
+    WS_REDUCE_A,
+    WS_REDUCE_B,
+    WS_POOL,
+    WS_POOL2,
+    WS_OUT,
+    WS_BASES,         // ad-hoc bases staging
+    WS_NTT_A,
+    WS_NTT_B,
+    WS_ASSIGN_IN,
+    WS_ASSIGN_OUT,
+    WS_MISC,
+    WS_MISC2,
+    WS_COUNT
+};
+
+struct NttPlan;
+
+}  // namespace h2b
+
+struct h2b_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int sm_count = 148;
+    mutable std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    struct Buf {
+        void* p = nullptr;
+        size_t cap = 0;
+    };
+    Buf ws[h2b::WS_COUNT];
+    Buf pinned[2];
+    std::map<std::array<uint64_t, 5>, h2b::NttPlan*> ntt_plans;
+
+    // grow-only; growing synchronises the device first (a kernel may still read the old block)
+    void* get(int slot, size_t bytes);
+    void* get_pinned(int slot, size_t bytes);
+};
+
+struct h2b_srs {
+    uint32_t k = 0;
+    size_t begin = 0, count = 0;
+    int c = 0, W = 0;
+    void* table[2] = {nullptr, nullptr};  // [basis] -> W x count affine points: table[w*count + i] = 2^(c*w) * P_i
+};
+
+namespace h2b {
+
+#define H2B_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+    do {                                                                         \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        (ctx)->launches++;                                                       \
+        H2B_CUDA(cudaGetLastError());                                            \
+    } while (0)
+
+static inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+static inline int ceil_log2(size_t n) {
+    int l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return l;
+}
+
+// ---- msm.cu
+int msm_choose_c_fixed(size_t n);
+void msm_build_table(h2b_ctx* ctx, const void* d_bases, size_t count, int c, int W, void* d_table);
+// table mode: q = W (one bucket set), table = W x n affine; ad-hoc mode: q = 1, table = n affine
+void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out);
+void g1_sum_run(h2b_ctx* ctx, const void* d_points, size_t m, void* d_out);
+void g1_normalize_run(h2b_ctx* ctx, void* d_points, size_t m);
+void g1_fixed_base_mul_run(h2b_ctx* ctx, const uint64_t base_xy[8], const void* d_scalars, size_t n, void* d_out);
+void field_op_run(h2b_ctx* ctx, int field, int op, const void* a, const void* b, size_t n, void* out);
+// ---- ntt.cu
+// in-place forward transform with arbitrary root; flags: see ntt.cu
+void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_t log_n, const uint64_t omega[4],
+             int inverse_scale, int coset_mode);
+void ntt_free_plans(h2b_ctx* ctx);
+void domain_omega(uint32_t k, uint64_t out[4], bool inverse);
+// ---- assign.cu
+void assign_columns_run(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64_t* break_points, size_t nbp,
+                        uint32_t k, size_t ncols, void* d_cols);
+void assign_lookups_run(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols);
+void eval_rational_run(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
+
+}  // namespace h2b

@@ -1,0 +1,250 @@
+"""Python mirror of the reference-facing prover interface for the hot path (names and argument meaning follow
+halo2-axiom 0.5.3 / halo2curves-axiom 0.7.3 as used by halo2-lib):
+
+    best_multiexp(coeffs, bases) -> G1                    halo2curves msm::best_multiexp
+    ParamsKZG.commit / commit_lagrange                    poly::kzg::commitment::ParamsKZG
+    best_fft(a, omega, log_n)                             arithmetic::best_fft
+    EvaluationDomain(j, k).lagrange_to_coeff / coeff_to_extended / extended_to_coeff
+    assign_witnesses(threads, break_points, ...)          halo2-base/src/gates/flex_gate/threads/single_phase.rs:273-312
+    assign_lookups(values, ...)                           halo2-base/src/virtual_region/lookups.rs:130-155
+
+Arrays are numpy uint64 in the `[u64;4]` little-endian Montgomery layout.  Everything computes on the GPU
+through libh2b200.so; nothing here does field arithmetic on the CPU."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from ._capi import lib, H2B_OK, H2B_ERR_LAYOUT, BASIS_MONOMIAL, BASIS_LAGRANGE
+
+
+class H2BError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"h2b200 error {code}: {msg}")
+        self.code = code
+
+
+class LayoutError(H2BError):
+    """Where the Rust code panics (out of columns / rows)."""
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    assert isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "need contiguous uint64 ndarray"
+    return C.c_void_p(a.ctypes.data)
+
+
+def _u64(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, cols)
+
+
+class Context:
+    """One per process / GPU (h2b_ctx)."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib.h2b_ctx_create(device, C.byref(h))
+        if rc != H2B_OK:
+            raise H2BError(rc, lib.h2b_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int):
+        if rc != H2B_OK:
+            msg = lib.h2b_last_error(self.h).decode()
+            raise (LayoutError if rc == H2B_ERR_LAYOUT else H2BError)(rc, msg)
+
+    def set_stream(self, cuda_stream: int | None):
+        self.check(lib.h2b_ctx_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self.check(lib.h2b_ctx_synchronize(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib.h2b_kernel_launches(self.h))
+
+    def close(self):
+        if self.h:
+            lib.h2b_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- small group helpers
+    def g1_sum(self, points_xyz) -> np.ndarray:
+        p = _u64(points_xyz, 12)
+        out = np.empty(12, dtype=np.uint64)
+        self.check(lib.h2b_g1_sum(self.h, _ptr(p), len(p), _ptr(out)))
+        return out
+
+    def g1_normalize(self, points_xyz) -> np.ndarray:
+        p = _u64(points_xyz, 12).copy()
+        self.check(lib.h2b_g1_normalize(self.h, _ptr(p), len(p)))
+        return p
+
+    def g1_fixed_base_mul(self, base_xy, scalars) -> np.ndarray:
+        b = _u64(base_xy, 8)
+        s = _u64(scalars, 4)
+        out = np.empty((len(s), 8), dtype=np.uint64)
+        self.check(lib.h2b_g1_fixed_base_mul(self.h, _ptr(b), _ptr(s), len(s), _ptr(out)))
+        return out
+
+    def field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
+        a = _u64(a, 4)
+        bb = _u64(b, 4) if b is not None else None
+        out = np.empty_like(a)
+        self.check(lib.h2b_test_field_op(self.h, field, op, _ptr(a), _ptr(bb), len(a), _ptr(out)))
+        return out
+
+    def eval_rational(self, num, den) -> np.ndarray:
+        a, b = _u64(num, 4), _u64(den, 4)
+        out = np.empty_like(a)
+        self.check(lib.h2b_eval_rational(self.h, _ptr(a), _ptr(b), len(a), _ptr(out)))
+        return out
+
+
+def omega(k: int) -> np.ndarray:
+    out = np.empty(4, dtype=np.uint64)
+    rc = lib.h2b_domain_omega(k, _ptr(out))
+    if rc != H2B_OK:
+        raise H2BError(rc, "k out of range")
+    return out
+
+
+def best_multiexp(ctx: Context, coeffs, bases) -> np.ndarray:
+    """halo2curves `best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1`: ad-hoc bases, Jacobian result."""
+    s, b = _u64(coeffs, 4), _u64(bases, 8)
+    assert len(s) == len(b), "best_multiexp: coeffs.len() != bases.len()"  # Rust: assert_eq!
+    out = np.empty(12, dtype=np.uint64)
+    ctx.check(lib.h2b_msm_g1_bases(ctx.h, _ptr(b), _ptr(s), len(s), _ptr(out)))
+    return out
+
+
+def best_fft(ctx: Context, a, omega_m, log_n: int) -> np.ndarray:
+    """halo2 `best_fft(a, omega, log_n)`; returns the transformed copy (Rust mutates in place)."""
+    a = _u64(a, 4).copy()
+    assert len(a) == 1 << log_n
+    w = _u64(omega_m, 4)
+    ctx.check(lib.h2b_ntt_fr(ctx.h, _ptr(a), log_n, _ptr(w), 0))
+    return a
+
+
+class ParamsKZG:
+    """The base arrays of `ParamsKZG<Bn256>` (g, g_lagrange) resident on the GPU, sharded [begin, begin+count)."""
+
+    def __init__(self, ctx: Context, k: int, g=None, g_lagrange=None, begin: int = 0, count: int | None = None,
+                 device_ptrs: bool = False):
+        self.ctx, self.k, self.n = ctx, k, 1 << k
+        self.begin = begin
+        self.count = (self.n - begin) if count is None else count
+        h = C.c_void_p()
+        if device_ptrs:
+            rc = lib.h2b_srs_upload_dev(ctx.h, C.c_void_p(g or 0), C.c_void_p(g_lagrange or 0), k, begin, self.count, C.byref(h))
+        else:
+            gg = _u64(g, 8) if g is not None else None
+            gl = _u64(g_lagrange, 8) if g_lagrange is not None else None
+            for arr in (gg, gl):
+                assert arr is None or len(arr) == self.n, "SRS arrays must hold all 2^k bases (the shard is cut inside)"
+            rc = lib.h2b_srs_upload(ctx.h, _ptr(gg), _ptr(gl), k, begin, self.count, C.byref(h))
+        ctx.check(rc)
+        self.h = h
+
+    def _commit(self, basis: int, poly) -> np.ndarray:
+        s = _u64(poly, 4)
+        out = np.empty(12, dtype=np.uint64)
+        self.ctx.check(lib.h2b_msm_g1(self.ctx.h, self.h, basis, _ptr(s), len(s), _ptr(out)))
+        return out
+
+    def commit(self, poly) -> np.ndarray:
+        """ParamsKZG::commit(poly: coefficient form) -> G1 (monomial basis `g`)."""
+        return self._commit(BASIS_MONOMIAL, poly)
+
+    def commit_lagrange(self, poly) -> np.ndarray:
+        """ParamsKZG::commit_lagrange(poly: Lagrange form) -> G1 (basis `g_lagrange`)."""
+        return self._commit(BASIS_LAGRANGE, poly)
+
+    def commit_batch(self, basis: int, polys) -> np.ndarray:
+        cols = [_u64(p, 4) for p in polys]
+        m = len(cols)
+        out = np.empty((m, 12), dtype=np.uint64)
+        ptrs = (C.c_void_p * m)(*[c.ctypes.data for c in cols])
+        self.ctx.check(lib.h2b_msm_g1_batch(self.ctx.h, self.h, basis, ptrs, m, len(cols[0]) if m else 0, _ptr(out)))
+        return out
+
+    def commit_dev(self, basis: int, d_scalars: int, n: int, d_out: int):
+        self.ctx.check(lib.h2b_msm_g1_dev(self.ctx.h, self.h, basis, C.c_void_p(d_scalars), n, C.c_void_p(d_out)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.h2b_srs_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EvaluationDomain:
+    """halo2 `EvaluationDomain::new(j, k)`: j = cs.degree(); quotient_poly_degree = j - 1;
+    extended_k = k + ceil(log2(j - 1))."""
+
+    def __init__(self, ctx: Context, j: int, k: int):
+        self.ctx, self.k, self.n = ctx, k, 1 << k
+        self.quotient_poly_degree = j - 1
+        ek = k
+        while (1 << ek) < self.n * self.quotient_poly_degree:
+            ek += 1
+        self.extended_k = ek
+
+    def lagrange_to_coeff(self, a) -> np.ndarray:
+        a = _u64(a, 4).copy()
+        assert len(a) == self.n
+        self.ctx.check(lib.h2b_lagrange_to_coeff(self.ctx.h, _ptr(a), self.k))
+        return a
+
+    def coeff_to_lagrange(self, a) -> np.ndarray:
+        a = _u64(a, 4).copy()
+        assert len(a) == self.n
+        self.ctx.check(lib.h2b_coeff_to_lagrange(self.ctx.h, _ptr(a), self.k))
+        return a
+
+    def coeff_to_extended(self, a) -> np.ndarray:
+        a = _u64(a, 4)
+        assert len(a) == self.n
+        out = np.empty((1 << self.extended_k, 4), dtype=np.uint64)
+        self.ctx.check(lib.h2b_coeff_to_extended(self.ctx.h, _ptr(a), len(a), self.extended_k, _ptr(out)))
+        return out
+
+    def extended_to_coeff(self, a) -> np.ndarray:
+        a = _u64(a, 4).copy()
+        assert len(a) == 1 << self.extended_k
+        self.ctx.check(lib.h2b_extended_to_coeff(self.ctx.h, _ptr(a), self.extended_k))
+        return a[: self.n * self.quotient_poly_degree]  # `a.values.truncate(n * quotient_poly_degree)`
+
+
+def assign_witnesses(ctx: Context, threads, break_points, k: int, ncols: int) -> np.ndarray:
+    """`assign_witnesses(threads, basic_gates, region, break_points)`: threads = list of (len_i x 4) limb arrays
+    (ctx.advice of each Context, Trivial payloads); returns ncols x 2^k x 4.  Raises LayoutError where Rust panics."""
+    parts = [_u64(t, 4) for t in threads if len(t)]
+    vcol = np.concatenate(parts) if parts else np.zeros((0, 4), dtype=np.uint64)
+    bp = np.ascontiguousarray(break_points, dtype=np.uint64).reshape(-1)
+    cols = np.empty((ncols, 1 << k, 4), dtype=np.uint64)
+    ctx.check(lib.h2b_assign_columns(ctx.h, _ptr(vcol) if len(vcol) else None, len(vcol), _ptr(bp) if len(bp) else None,
+                                     len(bp), k, ncols, _ptr(cols) if ncols else None))
+    return cols
+
+
+def assign_lookups(ctx: Context, values, k: int, L: int) -> np.ndarray:
+    v = _u64(values, 4)
+    cols = np.empty((L, 1 << k, 4), dtype=np.uint64)
+    ctx.check(lib.h2b_assign_lookups(ctx.h, _ptr(v) if len(v) else None, len(v), k, L, _ptr(cols) if L else None))
+    return cols

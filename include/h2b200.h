@@ -1,0 +1,147 @@
+/* h2b200.h — C ABI of libh2b200: the sm_100a back end for the create_proof hot path of halo2-lib
+ * (multi-scalar multiplication over BN254 G1, NTT over BN254 Fr, column-wise witness assignment).
+ *
+ * This is the surface a `halo2_proofs`-compatible Rust crate binds with `extern "C"` in place of the rayon
+ * CPU code; halo2-lib selects that crate through its own plug point, the `cuda` feature alias
+ *     halo2-base/src/lib.rs:25-28   (#[cfg(feature = "cuda")] pub use halo2_proofs_axiom_gpu as halo2_proofs;)
+ * so GateInstructions / RangeInstructions / FpChip / EccChip circuits and the keygen_pk / create_proof
+ * entry points (sole call site halo2-base/src/utils/testing.rs:40-48) are untouched.  INTEGRATION.md shows
+ * the Rust-side binding.
+ *
+ * Conventions
+ *  - Field element  = uint64_t[4], little-endian limbs, Montgomery form (R = 2^256): the `[u64;4]` contract
+ *    of halo2-base/src/utils/mod.rs:332-377 and the in-memory layout of halo2curves bn256::{Fr,Fq}.
+ *  - G1Affine       = x||y (8 limbs), identity = (0,0).   G1 (Jacobian) = x||y||z (12 limbs), identity z = 0.
+ *  - Every function returns an int status: 0 = OK, negative = error class below; the message is available
+ *    from h2b_last_error().  No C++ exception and no abort crosses this boundary (Rust `panic = unwind`,
+ *    reference Cargo.toml:31; unwinding through extern "C" is UB).
+ *  - Host-pointer entry points own no caller memory: buffers are read/written during the call only.
+ *    `_dev` entry points take device pointers (same layouts) and enqueue on the context's stream without
+ *    synchronising; the caller owns those allocations (e.g. torch tensors) and the synchronisation.
+ *  - A context is bound to ONE device (one process per GPU); calls on one context are serialised by an
+ *    internal mutex, so the library is re-entrant from rayon worker threads
+ *    (halo2-base/src/gates/flex_gate/threads/parallelize.rs:8-29 runs user code on many threads).
+ *  - There is no CPU fallback: without a CUDA device h2b_ctx_create fails with H2B_ERR_CUDA.
+ */
+#ifndef H2B200_H
+#define H2B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2B_OK 0
+#define H2B_ERR_ARG (-1)   /* bad argument (null pointer, size mismatch, k out of range) */
+#define H2B_ERR_CUDA (-2)  /* CUDA runtime error (message carries cudaGetErrorString) */
+#define H2B_ERR_OOM (-3)   /* device or host allocation failed */
+#define H2B_ERR_LAYOUT (-4) /* witness layout error: where the Rust code panics (out of columns / rows) */
+
+typedef struct h2b_ctx h2b_ctx;
+typedef struct h2b_srs h2b_srs;
+
+#define H2B_BASIS_MONOMIAL 0 /* ParamsKZG::g          -> ParamsKZG::commit          */
+#define H2B_BASIS_LAGRANGE 1 /* ParamsKZG::g_lagrange -> ParamsKZG::commit_lagrange */
+
+/* ---- context -------------------------------------------------------------------------------------- */
+int h2b_ctx_create(int device, h2b_ctx** out);
+void h2b_ctx_destroy(h2b_ctx* ctx);
+/* Use a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) for all work; NULL = the
+ * context's own stream. */
+int h2b_ctx_set_stream(h2b_ctx* ctx, void* cuda_stream);
+int h2b_ctx_synchronize(h2b_ctx* ctx);
+/* Last error message of this context (or of the failed h2b_ctx_create when ctx == NULL). */
+const char* h2b_last_error(const h2b_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
+uint64_t h2b_kernel_launches(const h2b_ctx* ctx);
+const char* h2b_version(void);
+
+/* ---- SRS: replaces the base arrays of ParamsKZG<Bn256> (halo2-base/src/utils/mod.rs:401-443) ------- */
+/* Uploads this device's shard [begin, begin+count) of the 2^k monomial bases `g` and Lagrange bases
+ * `g_lagrange` (each 2^k x 8 limbs on the host; either may be NULL) and builds the per-window multiples
+ * 2^(c*w) * P_i the fixed-base MSM consumes.  Single GPU: begin = 0, count = 2^k. */
+int h2b_srs_upload(h2b_ctx* ctx, const uint64_t* g, const uint64_t* g_lagrange, uint32_t k, size_t begin,
+                   size_t count, h2b_srs** out);
+/* Same, bases already on the device (count x 8 limbs each, the shard only). */
+int h2b_srs_upload_dev(h2b_ctx* ctx, const void* d_g, const void* d_g_lagrange, uint32_t k, size_t begin,
+                       size_t count, h2b_srs** out);
+void h2b_srs_destroy(h2b_ctx* ctx, h2b_srs* srs);
+
+/* ---- MSM: replaces halo2curves-axiom 0.7.3 msm::best_multiexp(coeffs, bases) -> G1, as reached from
+ *      ParamsKZG::commit / commit_lagrange inside create_proof ------------- */
+/* out = sum_{i in shard} scalars[i] * basis[i].  `scalars` holds the `n` scalars of THIS shard
+ * (n == count of the SRS).  Result: a valid Jacobian representative (not normalised), like best_multiexp. */
+int h2b_msm_g1(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* scalars, size_t n,
+               uint64_t out_xyz[12]);
+/* m commitments with the same basis (all advice columns of a phase, the h(X) pieces, ...): scalars[j] points
+ * at n scalars; out = m x 12 limbs.  Uploads are double-buffered against the kernels. */
+int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* const* scalars, size_t m,
+                     size_t n, uint64_t* out_xyz);
+/* Ad-hoc bases (n x 8 limbs on the host), no precomputation. */
+int h2b_msm_g1_bases(h2b_ctx* ctx, const uint64_t* bases, const uint64_t* scalars, size_t n,
+                     uint64_t out_xyz[12]);
+/* Device-resident variants: d_scalars = n x 4 limbs, d_out = 12 limbs, all on the device; asynchronous. */
+int h2b_msm_g1_dev(h2b_ctx* ctx, const h2b_srs* srs, int basis, const void* d_scalars, size_t n, void* d_out);
+int h2b_msm_g1_bases_dev(h2b_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, void* d_out);
+/* out = sum of m Jacobian points (host, m x 12 limbs): combines the per-GPU partial sums after the
+ * all-gather (EC addition is not an NCCL reduction op).  Runs on the device. */
+int h2b_g1_sum(h2b_ctx* ctx, const uint64_t* points_xyz, size_t m, uint64_t out_xyz[12]);
+int h2b_g1_sum_dev(h2b_ctx* ctx, const void* d_points_xyz, size_t m, void* d_out);
+/* Batch-normalise m Jacobian points to affine-normalised form (x, y, R) / identity (0, R, 0), in place. */
+int h2b_g1_normalize(h2b_ctx* ctx, uint64_t* points_xyz, size_t m);
+/* out[i] = scalars[i] * base (affine, n x 8 limbs): the per-point work of ParamsKZG::setup
+ * (g[i] = s^i * G, halo2-base/src/utils/mod.rs:439-443). */
+int h2b_g1_fixed_base_mul(h2b_ctx* ctx, const uint64_t base_xy[8], const uint64_t* scalars, size_t n,
+                          uint64_t* out_xy);
+int h2b_g1_fixed_base_mul_dev(h2b_ctx* ctx, const uint64_t base_xy[8], const void* d_scalars, size_t n,
+                              void* d_out_xy);
+
+/* ---- NTT: replaces halo2-axiom 0.5.3 arithmetic::best_fft and poly::EvaluationDomain -- */
+/* best_fft(a, omega, log_n): in place, natural order in and out, out[i] = sum_j a[j] * omega^(i*j).
+ * scale_by_n_inv != 0 additionally multiplies by 2^-log_n (EvaluationDomain::ifft). */
+int h2b_ntt_fr(h2b_ctx* ctx, uint64_t* a, uint32_t log_n, const uint64_t omega[4], int scale_by_n_inv);
+int h2b_ntt_fr_dev(h2b_ctx* ctx, void* d_a, uint32_t log_n, const uint64_t omega[4], int scale_by_n_inv);
+/* omega of the 2^k domain (ROOT_OF_UNITY^(2^(28-k))), Montgomery limbs. */
+int h2b_domain_omega(uint32_t k, uint64_t omega_out[4]);
+/* EvaluationDomain::lagrange_to_coeff / coeff_to_lagrange on the 2^k domain, in place. */
+int h2b_lagrange_to_coeff(h2b_ctx* ctx, uint64_t* a, uint32_t k);
+int h2b_coeff_to_lagrange(h2b_ctx* ctx, uint64_t* a, uint32_t k);
+int h2b_lagrange_to_coeff_dev(h2b_ctx* ctx, void* d_a, uint32_t k);
+int h2b_coeff_to_lagrange_dev(h2b_ctx* ctx, void* d_a, uint32_t k);
+/* EvaluationDomain::coeff_to_extended: coeffs[i] *= zeta^(i mod 3), zero-pad n_coeffs -> 2^ext_k,
+ * best_fft(extended_omega).  out holds 2^ext_k elements. */
+int h2b_coeff_to_extended(h2b_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, uint32_t ext_k, uint64_t* out);
+int h2b_coeff_to_extended_dev(h2b_ctx* ctx, const void* d_coeffs, size_t n_coeffs, uint32_t ext_k, void* d_out);
+/* EvaluationDomain::extended_to_coeff: best_fft(extended_omega^-1), scale by 2^-ext_k, a[i] *= zeta^-(i mod 3),
+ * in place on 2^ext_k elements (the caller truncates to n*(d-1)). */
+int h2b_extended_to_coeff(h2b_ctx* ctx, uint64_t* a, uint32_t ext_k);
+int h2b_extended_to_coeff_dev(h2b_ctx* ctx, void* d_a, uint32_t ext_k);
+
+/* ---- witness assignment: replaces the per-cell loop of assign_witnesses
+ *      (halo2-base/src/gates/flex_gate/threads/single_phase.rs:273-312 -> utils/halo2.rs:20-27) ------ */
+/* vcol = concatenation of ctx.advice over all threads (N x 4 limbs, `Trivial` payloads); break_points =
+ * the pinned ThreadBreakPoints of the phase; cols = ncols x 2^k x 4 limbs, fully written (unassigned rows
+ * zero).  H2B_ERR_LAYOUT where the Rust loop panics (break point walks past the last column, or a column
+ * overflows 2^k rows, or cells exist with ncols == 0). */
+int h2b_assign_columns(h2b_ctx* ctx, const uint64_t* vcol, size_t N, const uint64_t* break_points, size_t nbp,
+                       uint32_t k, size_t ncols, uint64_t* cols);
+int h2b_assign_columns_dev(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64_t* break_points,
+                           size_t nbp, uint32_t k, size_t ncols, void* d_cols);
+/* LookupAnyManager::assign_raw (halo2-base/src/virtual_region/lookups.rs:130-155): value j -> lookup
+ * column j mod L, row j div L.  cols = L x 2^k x 4 limbs. */
+int h2b_assign_lookups(h2b_ctx* ctx, const uint64_t* vals, size_t N, uint32_t k, size_t L, uint64_t* cols);
+int h2b_assign_lookups_dev(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols);
+/* Assigned::Rational cells (halo2-base/src/lib.rs:59-60,249-251): out[i] = num[i] * den[i]^-1, den = 0 -> 0
+ * (what the prover's batch_invert_assigned yields before committing). */
+int h2b_eval_rational(h2b_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out);
+int h2b_eval_rational_dev(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
+
+/* ---- test hooks (field arithmetic of the kernels, element-wise on the device) --------------------- */
+/* field: 0 = Fq, 1 = Fr; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 from_mont(a), 5 to_mont(a) */
+int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2B200_H */
