@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py — create_proof-schedule benchmark for the B200 back end (BASELINE.json metric:
+"create_proof ms + MSM G1-pairs/s at k=19 ECDSA").
+
+One "step" = one pass of the prover hot path for ONE proof of the halo2-ecc secp256k1 ECDSA circuit at k=19
+(BASELINE.json configs[2]; column shape 1 advice / q_lookup / 1 fixed, halo2-ecc/configs/secp256k1/bench_ecdsa.config:1):
+the witness-column assignment, the 12 MSMs of size 2^19 and the (coset) NTTs create_proof issues for that
+constraint system (restated — the prover crate is not vendored).  `value` is the MSM
+throughput of the whole step (G1 pairs / step time); `ms_per_step` is the create_proof-schedule time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--k 19]
+"""
+from __future__ import annotations
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+# ---- the restated create_proof schedule for the ECDSA circuit (1 advice, lookup on the same column, d = 5)
+# (basis, scalar class): witness-like columns are dominated by 0/1 bits and <= 88-bit limbs
+MSM_SCHEDULE = (
+    [("lagrange", "witness")] * 1      # advice column commitment                       (§3.3 step 2)
+    + [("lagrange", "witness")] * 2    # lookup permuted input / table                  (step 3)
+    + [("lagrange", "uniform")] * 2    # permutation grand product, lookup grand product (step 4)
+    + [("monomial", "uniform")] * 1    # vanishing argument random polynomial           (step 5)
+    + [("monomial", "uniform")] * 4    # h(X) pieces, d - 1 = 4                         (step 6)
+    + [("monomial", "uniform")] * 2    # SHPLONK                                        (step 8)
+)
+N_INTT = 5        # lagrange_to_coeff: advice, 2 permuted, 2 grand products          (steps 3,4,6)
+N_COSET = 5       # coeff_to_extended (2^k -> 2^(k+2)) of the same five polynomials  (step 6)
+N_COSET_INV = 1   # extended_to_coeff of h(X)                                        (step 6)
+QUOTIENT_J = 5    # cs.degree() with the q_lookup lookup: extended_k = k + 2
+
+
+def witness_like(rng, n):
+    """canonical ints: 35% zero, 25% one, 30% < 2^88, 10% uniform Fr (SURVEY.md §8d distribution W)"""
+    cls = rng.random(n)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    one = (cls >= 0.35) & (cls < 0.60)
+    small = (cls >= 0.60) & (cls < 0.90)
+    full = cls >= 0.90
+    out[one, 0] = 1
+    k = int(small.sum())
+    out[small, 0] = rng.integers(0, 1 << 63, size=k, dtype=np.int64).astype(np.uint64) * np.uint64(2) + rng.integers(0, 2, size=k, dtype=np.int64).astype(np.uint64)
+    out[small, 1] = rng.integers(0, 1 << 24, size=k, dtype=np.int64).astype(np.uint64)
+    k = int(full.sum())
+    out[full] = uniform_residues(rng, k)
+    return out
+
+
+def uniform_residues(rng, n):
+    """n uniform values < 2^252 < r as 4 x u64 limbs (valid Montgomery residues and valid canonical values)"""
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    a[:, :3] = a[:, :3] * np.uint64(2) + rng.integers(0, 2, size=(n, 3), dtype=np.int64).astype(np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    return a
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(k: int, threads: int | None = None):
+    """Times the CPU restatement (oracle/, OpenMP, all host threads) on one op of each class of the schedule and
+    composes the step time: sum(count_i * t_i).  ~10-30 s of CPU work on a typical host."""
+    from oracle import oracle as orc
+    try:  # a -march=native build for the host it runs on (the shipped .so is x86-64-v3)
+        so = os.path.join(ROOT, "oracle", "_build", "liboracle_native.so")
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "MARCH=native", f"OUT={so}"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        import ctypes
+        orc._lib = None
+        orc._SO = so
+    except Exception:
+        pass
+    threads = threads or orc.max_threads()
+    n = 1 << k
+    ext_k = k + 2
+    rng = np.random.default_rng(0xB2000000 + k)
+    # bases: any valid curve points time the same; build n points a_i * G cheaply with the oracle itself
+    from util import affine_to_limbs, mont
+    from oracle import pyref
+    g = affine_to_limbs([pyref.G1])[0]
+    small = np.zeros((n, 4), dtype=np.uint64)
+    small[:, 0] = np.arange(3, 3 + 5 * n, 5, dtype=np.uint64)  # canonical small scalars
+    t0 = time.perf_counter()
+    bases = orc.g1_fixed_base_mul(orc.to_mont(orc.FR, small), g)
+    t_setup = time.perf_counter() - t0
+    s_uni = uniform_residues(rng, n)
+    s_wit = orc.to_mont(orc.FR, witness_like(rng, n))
+    # warm the OpenMP pool and the code paths on a tiny instance before timing anything
+    orc.msm_pippenger(s_uni[:256], bases[:256], threads)
+    orc.extended_to_coeff(orc.coeff_to_extended(orc.lagrange_to_coeff(s_uni[:256], 8, threads), 10, threads), 10, threads)
+    times = {}
+    t0 = time.perf_counter(); orc.msm_pippenger(s_uni, bases, threads); times["msm_uniform"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); orc.msm_pippenger(s_wit, bases, threads); times["msm_witness"] = time.perf_counter() - t0
+    a = uniform_residues(rng, n)
+
+    def best_of_2(fn):  # the first parallel region after a different team shape pays a one-off wake-up cost
+        best, res = None, None
+        for _ in range(2):
+            t0 = time.perf_counter(); res = fn(); dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best, res
+    times["intt"], coeffs = best_of_2(lambda: orc.lagrange_to_coeff(a, k, threads))
+    times["coset_ntt"], ext = best_of_2(lambda: orc.coeff_to_extended(coeffs, ext_k, threads))
+    times["coset_intt"], _ = best_of_2(lambda: orc.extended_to_coeff(ext, ext_k, threads))
+    times["assign"], _ = best_of_2(lambda: orc.assign_witnesses(a[: n - 20], np.zeros(0, dtype=np.uint64), k, 1))
+    n_wit = sum(1 for _, c in MSM_SCHEDULE if c == "witness")
+    n_uni = len(MSM_SCHEDULE) - n_wit
+    step_s = (n_uni * times["msm_uniform"] + n_wit * times["msm_witness"] + N_INTT * times["intt"] + N_COSET * times["coset_ntt"]
+              + N_COSET_INV * times["coset_intt"] + times["assign"])
+    pairs = len(MSM_SCHEDULE) * n
+    return {
+        "value": pairs / step_s,
+        "unit": "G1 pairs/s",
+        "cores": threads,
+        "kind": "port",
+        "sample": (f"oracle/bn254_oracle.c (restated CPU path, OpenMP x{threads}; the Rust reference cannot be built here): one MSM(2^{k}) per scalar "
+                   f"class + one iNTT(2^{k}) + one coeff_to_extended/extended_to_coeff(2^{ext_k}) + one assignment, composed by the schedule counts"),
+        "step_ms": step_s * 1e3,
+        "op_ms": {kk: v * 1e3 for kk, v in times.items()},
+        "setup_s": t_setup,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_sample(args.k)
+        if i >= args.warmup:
+            vals.append(last)
+    step_ms = float(np.mean([v["step_ms"] for v in vals]))
+    pairs = len(MSM_SCHEDULE) * (1 << args.k)
+    value = pairs / (step_ms / 1e3)
+    cb = dict(last)
+    cb["value"] = value
+    print(json.dumps({
+        "impl": "reference", "metric": "msm_g1_pairs_per_s (create_proof schedule, ECDSA k=%d)" % args.k, "value": value, "unit": "G1 pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
+        "config": workload_config(args.k, args.gpus), "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": "G1 pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "create_proof_schedule_ms": step_ms,
+    }))
+
+
+def workload_config(k, gpus):
+    return {
+        "workload": f"halo2-ecc secp256k1 ECDSA verify circuit, k={k} (BASELINE.json configs[2]): create_proof schedule restated in SURVEY.md §3.3/§8",
+        "k": k, "columns": "1 advice / q_lookup / 1 fixed", "msm": f"{len(MSM_SCHEDULE)} x 2^{k} ({sum(1 for b, _ in MSM_SCHEDULE if b == 'lagrange')} lagrange + {sum(1 for b, _ in MSM_SCHEDULE if b == 'monomial')} monomial basis)",
+        "ntt": f"{N_INTT} x iNTT(2^{k}) + {N_COSET} x coeff_to_extended(2^{k + 2}) + {N_COSET_INV} x extended_to_coeff(2^{k + 2})",
+        "assignment": f"1 column x 2^{k} rows", "scalars": "3 witness-like + 9 uniform columns (SURVEY.md §8d)",
+        "parallelism": f"msm point-range sharded x{gpus} + all-gather of partial sums; NTT one polynomial per device" if gpus > 1 else "single GPU",
+        "l2_policy": "inputs larger than L2: 12 distinct scalar columns + two 15-level base tables (~1 GB) + NTT buffers (~0.5 GB) per step vs 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import ctypes as C
+    import halo2_lib_b200 as h
+    from halo2_lib_b200._capi import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    k = args.k
+    n = 1 << k
+    ext_k = k + 2
+    n_loc = n // world
+    begin = rank * n_loc
+    ctx = h.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(0xB2000000 + k)
+
+    def dev_u64(arr):
+        return torch.from_numpy(arr.view(np.int64)).to(dev)
+
+    # ---- setup (untimed): SRS-like bases on the GPU, this rank's shard only
+    gbase = np.array([0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f,  # x = 1 (Montgomery)
+                      0xa6ba871b8b1e1b3a, 0x14f1d651eb8e167b, 0xccdd46def0f28c58, 0x1c14ef83340fbe5e], dtype=np.uint64)  # y = 2
+    tables = {}
+    for name, (a0, d) in {"monomial": (3, 5), "lagrange": (7, 11)}.items():
+        sc = np.zeros((n_loc, 4), dtype=np.uint64)
+        sc[:, 0] = (a0 + d * (begin + np.arange(n_loc, dtype=np.uint64))).astype(np.uint64)
+        sc_m = ctx.field_op(1, 5, sc)  # to Montgomery form on the GPU
+        d_sc = dev_u64(sc_m)
+        d_pts = torch.empty((n_loc, 8), dtype=torch.int64, device=dev)
+        ctx.check(lib.h2b_g1_fixed_base_mul_dev(ctx.h, C.c_void_p(gbase.ctypes.data), C.c_void_p(d_sc.data_ptr()), n_loc, C.c_void_p(d_pts.data_ptr())))
+        tables[name] = d_pts
+    torch.cuda.synchronize()
+    params = h.ParamsKZG(ctx, k, g=tables["monomial"].data_ptr(), g_lagrange=tables["lagrange"].data_ptr(), begin=begin, count=n_loc, device_ptrs=True)
+    del tables
+    # ---- inputs: 12 scalar columns (host pinned + device resident), NTT polynomials, the virtual witness column
+    cols_host, cols_dev = [], []
+    for basis, cls in MSM_SCHEDULE:
+        full = uniform_residues(rng, n) if cls == "uniform" else ctx.field_op(1, 5, witness_like(rng, n))
+        shard = np.ascontiguousarray(full[begin:begin + n_loc])
+        th = torch.from_numpy(shard.view(np.int64)).pin_memory()
+        cols_host.append(th)
+        cols_dev.append(th.to(dev))
+    basis_id = [0 if b == "monomial" else 1 for b, _ in MSM_SCHEDULE]
+    my_ntt = lambda i: (i % world) == rank  # one polynomial per device, round-robin
+    polys_host = [torch.from_numpy(uniform_residues(rng, n).view(np.int64)).pin_memory() for _ in range(N_INTT)]
+    polys_dev = [p.to(dev) for p in polys_host]
+    ext_host = [torch.empty((1 << ext_k, 4), dtype=torch.int64).pin_memory() for _ in range(N_COSET)]
+    ext_dev = [torch.empty((1 << ext_k, 4), dtype=torch.int64, device=dev) for _ in range(N_COSET)]
+    n_cells = n - 20
+    vcol_host = torch.from_numpy(ctx.field_op(1, 5, witness_like(rng, n_cells)).view(np.int64)).pin_memory()
+    vcol_dev = vcol_host.to(dev)
+    acol_host = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    acol_dev = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    outs_dev = torch.zeros((len(MSM_SCHEDULE), 12), dtype=torch.int64, device=dev)
+    gather_dev = torch.zeros((world, 12), dtype=torch.int64, device=dev) if world > 1 else None
+    outs_host = np.zeros((len(MSM_SCHEDULE), 12), dtype=np.uint64)
+    vp = C.c_void_p
+
+    def step_resident():
+        if rank == 0:
+            ctx.check(lib.h2b_assign_columns_dev(ctx.h, vp(vcol_dev.data_ptr()), n_cells, None, 0, k, 1, vp(acol_dev.data_ptr())))
+        for j in range(len(MSM_SCHEDULE)):
+            params.commit_dev(basis_id[j], cols_dev[j].data_ptr(), n_loc, outs_dev[j].data_ptr())
+            if world > 1:  # all-reduce under EC addition = all-gather of the 96-byte partials + local adds
+                dist.all_gather_into_tensor(gather_dev, outs_dev[j])
+                ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(gather_dev.data_ptr()), world, vp(outs_dev[j].data_ptr())))
+        for i in range(N_INTT):
+            if my_ntt(i):
+                ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(polys_dev[i].data_ptr()), k))
+        for i in range(N_COSET):
+            if my_ntt(i):
+                ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(polys_dev[i % N_INTT].data_ptr()), n, ext_k, vp(ext_dev[i].data_ptr())))
+        if my_ntt(N_COSET):
+            ctx.check(lib.h2b_extended_to_coeff_dev(ctx.h, vp(ext_dev[0].data_ptr()), ext_k))
+
+    def step_e2e():
+        """the same step through the host-pointer C ABI: pinned host buffers in, host buffers out"""
+        if rank == 0:
+            ctx.check(lib.h2b_assign_columns(ctx.h, vp(vcol_host.data_ptr()), n_cells, None, 0, k, 1, vp(acol_host.data_ptr())))
+        for b in (1, 0):
+            idx = [j for j in range(len(MSM_SCHEDULE)) if basis_id[j] == b]
+            ptrs = (C.c_void_p * len(idx))(*[cols_host[j].data_ptr() for j in idx])
+            out = np.empty((len(idx), 12), dtype=np.uint64)
+            ctx.check(lib.h2b_msm_g1_batch(ctx.h, params.h, b, ptrs, len(idx), n_loc, vp(out.ctypes.data)))
+            if world > 1:
+                t = torch.from_numpy(out.view(np.int64)).to(dev)
+                g = torch.empty((world,) + tuple(t.shape), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(g, t)
+                g = g.transpose(0, 1).contiguous()
+                for jj in range(len(idx)):
+                    ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(g[jj].data_ptr()), world, vp(t[jj].data_ptr())))
+                out = t.cpu().numpy().view(np.uint64)
+            outs_host[idx] = out
+        for i in range(N_INTT):
+            if my_ntt(i):
+                ctx.check(lib.h2b_lagrange_to_coeff(ctx.h, vp(polys_host[i].data_ptr()), k))
+        for i in range(N_COSET):
+            if my_ntt(i):
+                ctx.check(lib.h2b_coeff_to_extended(ctx.h, vp(polys_host[i % N_INTT].data_ptr()), n, ext_k, vp(ext_host[i].data_ptr())))
+        if my_ntt(N_COSET):
+            ctx.check(lib.h2b_extended_to_coeff(ctx.h, vp(ext_host[0].data_ptr()), ext_k))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, prof=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if prof:
+            ctx.profile_reset()
+            ctx.profile_enable(prof)
+        l0 = ctx.kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if prof:
+            ctx.profile_enable(None)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, ctx.kernel_launches - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches = timed(step_resident, args.steps, args.warmup, prof="k_accumulate")
+    acc_ms, acc_cnt = ctx.profile_read("k_accumulate")
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 5)), 1)
+
+    # per-op device timings (context for the headline; same CUDA-event method, 3 reps each)
+    def time_op(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    iu = next(j for j, (_, c) in enumerate(MSM_SCHEDULE) if c == "uniform")
+    iw = next(j for j, (_, c) in enumerate(MSM_SCHEDULE) if c == "witness")
+    op_ms = {
+        "msm_uniform": time_op(lambda: params.commit_dev(basis_id[iu], cols_dev[iu].data_ptr(), n_loc, outs_dev[iu].data_ptr())),
+        "msm_witness": time_op(lambda: params.commit_dev(basis_id[iw], cols_dev[iw].data_ptr(), n_loc, outs_dev[iw].data_ptr())),
+        "intt": time_op(lambda: ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(polys_dev[0].data_ptr()), k))),
+        "coset_ntt": time_op(lambda: ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(polys_dev[0].data_ptr()), n, ext_k, vp(ext_dev[0].data_ptr())))),
+        "coset_intt": time_op(lambda: ctx.check(lib.h2b_extended_to_coeff_dev(ctx.h, vp(ext_dev[0].data_ptr()), ext_k))),
+        "assign": time_op(lambda: ctx.check(lib.h2b_assign_columns_dev(ctx.h, vp(vcol_dev.data_ptr()), n_cells, None, 0, k, 1, vp(acol_dev.data_ptr())))),
+    }
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pairs = len(MSM_SCHEDULE) * n
+    value = pairs / (ms_step / 1e3)
+    peak, peak_src = measured_hbm_peak()
+    acc_avg_ms = acc_ms / max(acc_cnt, 1)
+    achieved = 96.0 * n_loc / (acc_avg_ms / 1e3) / 1e9  # algorithmic 96 B per pair (32 B scalar + 64 B base), SURVEY.md §8d
+    roofline = {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt,
+                "algorithmic_bytes_per_launch": 96 * n_loc,
+                "note": "bucket accumulation is integer-issue-bound (254-bit Montgomery on the IMAD pipe), not HBM-bound: see DESIGN.md"}
+    h2d = (len(MSM_SCHEDULE) * n_loc * 32 + (N_INTT * n * 32 + N_COSET * n * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n_cells * 32)
+    d2h = (len(MSM_SCHEDULE) * 96 + (N_INTT * n * 32 + N_COSET * (1 << ext_k) * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n * 32)
+    cpu = cpu_sample(k) if world == 1 and not args.no_cpu else None
+    line = {
+        "metric": "msm_g1_pairs_per_s (create_proof schedule, ECDSA k=%d)" % k, "value": value, "unit": "G1 pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
+        "config": workload_config(k, world),
+        "create_proof_schedule_ms": ms_step,
+        "ntt_fr_elements_per_s": (1 << ext_k) / (op_ms["coset_ntt"] / 1e3),
+        "msm_only_pairs_per_s": n / (op_ms["msm_uniform"] / 1e3),
+        "op_ms": op_ms,
+        "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "G1 pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "path": "h2b_assign_columns / h2b_msm_g1_batch / h2b_lagrange_to_coeff / h2b_coeff_to_extended / h2b_extended_to_coeff with pinned host buffers"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--k", type=int, default=19)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

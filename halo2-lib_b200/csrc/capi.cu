@@ -43,6 +43,17 @@ void* h2b_ctx::get_pinned(int slot, size_t bytes) {
     return b.p;
 }
 
+cudaEvent_t h2b_ctx::prof_event() {
+    if (!prof_pool.empty()) {
+        cudaEvent_t e = prof_pool.back();
+        prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    H2B_CUDA(cudaEventCreate(&e));
+    return e;
+}
+
 // Runs `body` under the context lock with the context's device current; translates every failure.
 template <class Fn>
 static int guarded(h2b_ctx* ctx, Fn&& body) {
@@ -117,6 +128,8 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
         if (b.p) cudaFreeHost(b.p);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -130,6 +143,35 @@ int h2b_ctx_synchronize(h2b_ctx* ctx) {
 }
 const char* h2b_last_error(const h2b_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 uint64_t h2b_kernel_launches(const h2b_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ profiling
+int h2b_profile_enable(h2b_ctx* ctx, const char* filter) {
+    return guarded(ctx, [&] { ctx->prof_filter = filter ? filter : ""; });
+}
+int h2b_profile_reset(h2b_ctx* ctx) {
+    return guarded(ctx, [&] {
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (auto& r : ctx->prof_recs) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
+        ctx->prof_recs.clear();
+    });
+}
+int h2b_profile_read(h2b_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(kernel && total_ms && launches, "profile_read: null pointer");
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+        double ms = 0;
+        uint64_t cnt = 0;
+        for (auto& r : ctx->prof_recs) {
+            if (std::string(r.name).find(kernel) == std::string::npos) continue;
+            float t = 0;
+            H2B_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+            ms += t;
+            cnt++;
+        }
+        *total_ms = ms;
+        *launches = cnt;
+    });
+}
 
 // ------------------------------------------------------------------------------------------------ SRS
 static void srs_build(h2b_ctx* ctx, const void* d_g, const void* d_gl, uint32_t k, size_t begin, size_t count, h2b_srs** out) {

@@ -80,6 +80,19 @@ struct h2b_ctx {
     Buf pinned[2];
     std::map<std::array<uint64_t, 5>, h2b::NttPlan*> ntt_plans;
 
+    // optional per-kernel device timing (h2b_profile_*): event pairs around launches whose name matches
+    std::string prof_filter;  // empty = off, "*" = every kernel, else substring of the kernel name
+    struct ProfRec {
+        const char* name;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    bool prof_match(const char* name) const {
+        return !prof_filter.empty() && (prof_filter == "*" || std::string(name).find(prof_filter) != std::string::npos);
+    }
+    cudaEvent_t prof_event();
+
     // grow-only; growing synchronises the device first (a kernel may still read the old block)
     void* get(int slot, size_t bytes);
     void* get_pinned(int slot, size_t bytes);
@@ -96,9 +109,20 @@ namespace h2b {
 
 #define H2B_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
     do {                                                                         \
+        const bool _prof = (ctx)->prof_match(#kernel);                           \
+        cudaEvent_t _ea = nullptr, _eb = nullptr;                                \
+        if (_prof) {                                                             \
+            _ea = (ctx)->prof_event();                                           \
+            _eb = (ctx)->prof_event();                                           \
+            H2B_CUDA(cudaEventRecord(_ea, (ctx)->stream));                       \
+        }                                                                        \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
         (ctx)->launches++;                                                       \
         H2B_CUDA(cudaGetLastError());                                            \
+        if (_prof) {                                                             \
+            H2B_CUDA(cudaEventRecord(_eb, (ctx)->stream));                       \
+            (ctx)->prof_recs.push_back({#kernel, _ea, _eb});                     \
+        }                                                                        \
     } while (0)
 
 static inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

@@ -66,6 +66,17 @@ class Context:
     def kernel_launches(self) -> int:
         return int(lib.h2b_kernel_launches(self.h))
 
+    def profile_enable(self, filt: str | None):
+        self.check(lib.h2b_profile_enable(self.h, filt.encode() if filt else None))
+
+    def profile_reset(self):
+        self.check(lib.h2b_profile_reset(self.h))
+
+    def profile_read(self, kernel: str) -> tuple[float, int]:
+        ms, cnt = C.c_double(), C.c_uint64()
+        self.check(lib.h2b_profile_read(self.h, kernel.encode(), C.byref(ms), C.byref(cnt)))
+        return ms.value, int(cnt.value)
+
     def close(self):
         if self.h:
             lib.h2b_ctx_destroy(self.h)

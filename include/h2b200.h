@@ -56,6 +56,13 @@ const char* h2b_last_error(const h2b_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
 uint64_t h2b_kernel_launches(const h2b_ctx* ctx);
 const char* h2b_version(void);
+/* Device-side timing of the library's own kernels (CUDA events on the launching stream): `filter` is a
+ * substring of the kernel name ("k_accumulate"), "*" for all, NULL/"" to switch off.  h2b_profile_read
+ * synchronises the stream and returns the summed duration and count of the matching launches since the
+ * last h2b_profile_reset.  Used by bench.py for the roofline of the dominant kernel. */
+int h2b_profile_enable(h2b_ctx* ctx, const char* filter);
+int h2b_profile_reset(h2b_ctx* ctx);
+int h2b_profile_read(h2b_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches);
 
 /* ---- SRS: replaces the base arrays of ParamsKZG<Bn256> (halo2-base/src/utils/mod.rs:401-443) ------- */
 /* Uploads this device's shard [begin, begin+count) of the 2^k monomial bases `g` and Lagrange bases

@@ -271,9 +271,9 @@ def test_assign_lookups_and_rational(ctx, h2b):
     rng = np.random.default_rng(31)
     vals = mont(rand_ints(rng, 1000, R), R)
     for L in (1, 3, 4):
-        rc, want = orc.assign_lookups(vals, 9, L)
+        rc, want = orc.assign_lookups(vals, 10, L)
         assert rc == 0
-        assert np.array_equal(h2b.assign_lookups(ctx, vals, 9, L), want)
+        assert np.array_equal(h2b.assign_lookups(ctx, vals, 10, L), want)
     with pytest.raises(h2b.LayoutError):
         h2b.assign_lookups(ctx, vals, 3, 2)
     num, den = mont(rand_ints(rng, 200, R), R), mont([0, 1] + rand_ints(rng, 198, R), R)
