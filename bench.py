@@ -37,6 +37,10 @@ MSM_SCHEDULE = (
     + [("monomial", "uniform")] * 4    # h(X) pieces, d - 1 = 4                         (step 6)
     + [("monomial", "uniform")] * 2    # SHPLONK                                        (step 8)
 )
+# prover phases: the MSMs inside one phase are independent (batched over the library's lanes); a phase can only start
+# when the commitments of the previous one have been hashed into the transcript (challenge dependency), so phases
+# are serialised on the stream.  Indices into MSM_SCHEDULE.
+MSM_PHASES = [[0], [1, 2], [3, 4, 5], [6, 7, 8, 9], [10], [11]]
 N_INTT = 5        # lagrange_to_coeff: advice, 2 permuted, 2 grand products          (steps 3,4,6)
 N_COSET = 5       # coeff_to_extended (2^k -> 2^(k+2)) of the same five polynomials  (step 6)
 N_COSET_INV = 1   # extended_to_coeff of h(X)                                        (step 6)
@@ -244,7 +248,11 @@ def run_b200(args):
     n_loc = n // world
     begin = rank * n_loc
     ctx = h.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the library treats a NULL stream as "use the context's own stream", and the
+    # CUDA events below must be recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     rng = np.random.default_rng(0xB2000000 + k)
 
@@ -286,18 +294,22 @@ def run_b200(args):
     acol_host = torch.empty((n, 4), dtype=torch.int64).pin_memory()
     acol_dev = torch.empty((n, 4), dtype=torch.int64, device=dev)
     outs_dev = torch.zeros((len(MSM_SCHEDULE), 12), dtype=torch.int64, device=dev)
-    gather_dev = torch.zeros((world, 12), dtype=torch.int64, device=dev) if world > 1 else None
+    gather_bufs = {m: torch.zeros((world, m, 12), dtype=torch.int64, device=dev) for m in {len(p) for p in MSM_PHASES}} if world > 1 else None
     outs_host = np.zeros((len(MSM_SCHEDULE), 12), dtype=np.uint64)
     vp = C.c_void_p
 
     def step_resident():
         if rank == 0:
             ctx.check(lib.h2b_assign_columns_dev(ctx.h, vp(vcol_dev.data_ptr()), n_cells, None, 0, k, 1, vp(acol_dev.data_ptr())))
-        for j in range(len(MSM_SCHEDULE)):
-            params.commit_dev(basis_id[j], cols_dev[j].data_ptr(), n_loc, outs_dev[j].data_ptr())
+        for phase in MSM_PHASES:
+            j0 = phase[0]
+            params.commit_batch_dev([basis_id[j] for j in phase], [cols_dev[j].data_ptr() for j in phase], n_loc, outs_dev[j0].data_ptr())
             if world > 1:  # all-reduce under EC addition = all-gather of the 96-byte partials + local adds
-                dist.all_gather_into_tensor(gather_dev, outs_dev[j])
-                ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(gather_dev.data_ptr()), world, vp(outs_dev[j].data_ptr())))
+                npts = len(phase)
+                dist.all_gather_into_tensor(gather_bufs[npts], outs_dev[j0:j0 + npts])
+                gt = gather_bufs[npts].transpose(0, 1).contiguous()  # npts x world x 12
+                for jj in range(npts):
+                    ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(gt[jj].data_ptr()), world, vp(outs_dev[j0 + jj].data_ptr())))
         for i in range(N_INTT):
             if my_ntt(i):
                 ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(polys_dev[i].data_ptr()), k))
@@ -311,20 +323,21 @@ def run_b200(args):
         """the same step through the host-pointer C ABI: pinned host buffers in, host buffers out"""
         if rank == 0:
             ctx.check(lib.h2b_assign_columns(ctx.h, vp(vcol_host.data_ptr()), n_cells, None, 0, k, 1, vp(acol_host.data_ptr())))
-        for b in (1, 0):
-            idx = [j for j in range(len(MSM_SCHEDULE)) if basis_id[j] == b]
-            ptrs = (C.c_void_p * len(idx))(*[cols_host[j].data_ptr() for j in idx])
-            out = np.empty((len(idx), 12), dtype=np.uint64)
-            ctx.check(lib.h2b_msm_g1_batch(ctx.h, params.h, b, ptrs, len(idx), n_loc, vp(out.ctypes.data)))
+        for phase in MSM_PHASES:
+            m = len(phase)
+            ptrs = (C.c_void_p * m)(*[cols_host[j].data_ptr() for j in phase])
+            bs = (C.c_int * m)(*[basis_id[j] for j in phase])
+            out = np.empty((m, 12), dtype=np.uint64)
+            ctx.check(lib.h2b_msm_g1_batch(ctx.h, params.h, bs, ptrs, m, n_loc, vp(out.ctypes.data)))
             if world > 1:
                 t = torch.from_numpy(out.view(np.int64)).to(dev)
                 g = torch.empty((world,) + tuple(t.shape), dtype=torch.int64, device=dev)
                 dist.all_gather_into_tensor(g, t)
                 g = g.transpose(0, 1).contiguous()
-                for jj in range(len(idx)):
+                for jj in range(m):
                     ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(g[jj].data_ptr()), world, vp(t[jj].data_ptr())))
                 out = t.cpu().numpy().view(np.uint64)
-            outs_host[idx] = out
+            outs_host[phase] = out
         for i in range(N_INTT):
             if my_ntt(i):
                 ctx.check(lib.h2b_lagrange_to_coeff(ctx.h, vp(polys_host[i].data_ptr()), k))

@@ -14,7 +14,7 @@ using namespace h2b;
 
 void* h2b_ctx::get(int slot, size_t bytes) {
     if (bytes == 0) bytes = 16;
-    Buf& b = ws[slot];
+    Buf& b = ws[cur_lane][slot];
     if (b.cap >= bytes) return b.p;
     if (b.p) {
         H2B_CUDA(cudaDeviceSynchronize());
@@ -100,6 +100,13 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (auto& ev : ctx->ev) H2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (int l = 0; l < h2b_ctx::NLANES; l++) {
+            H2B_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+            H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_done[l], cudaEventDisableTiming));
+            H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_ready[l], cudaEventDisableTiming));
+            H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_consumed[l], cudaEventDisableTiming));
+        }
+        H2B_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
         ctx->stream = ctx->own_stream;
         cudaDeviceProp prop;
         H2B_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -122,8 +129,16 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ntt_free_plans(ctx);
-    for (auto& b : ctx->ws)
-        if (b.p) cudaFree(b.p);
+    for (auto& lane : ctx->ws)
+        for (auto& b : lane)
+            if (b.p) cudaFree(b.p);
+    for (int l = 0; l < h2b_ctx::NLANES; l++) {
+        if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+        if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
+        if (ctx->lane_ready[l]) cudaEventDestroy(ctx->lane_ready[l]);
+        if (ctx->lane_consumed[l]) cudaEventDestroy(ctx->lane_consumed[l]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     for (auto& b : ctx->pinned)
         if (b.p) cudaFreeHost(b.p);
     for (auto& ev : ctx->ev)
@@ -255,38 +270,75 @@ int h2b_msm_g1_bases_dev(h2b_ctx* ctx, const void* d_bases, const void* d_scalar
         msm_run_adhoc(ctx, d_bases, n, d_scalars, d_out);
     });
 }
-int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* const* scalars, size_t m, size_t n,
+int h2b_msm_g1_batch_dev(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const void* const* d_scalars, size_t m, size_t n,
+                         void* d_out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(basis && d_scalars && d_out, "msm: null pointer");
+        std::vector<const void*> tables(m);
+        for (size_t j = 0; j < m; j++) {
+            H2B_REQUIRE(d_scalars[j], "msm: null scalar column");
+            tables[j] = srs_table(srs, basis[j], n);
+        }
+        msm_run_batch(ctx, tables.data(), n, srs->c, srs->W, d_scalars, m, d_out);
+    });
+}
+int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
                      uint64_t* out_xyz) {
     return guarded(ctx, [&] {
-        H2B_REQUIRE(scalars && out_xyz, "msm: null pointer");
-        const void* t = srs_table(srs, basis, n);
+        H2B_REQUIRE(basis && scalars && out_xyz, "msm: null pointer");
         if (m == 0) return;
-        void* stage[2] = {ctx->get(WS_SCALARS, n * 32), ctx->get(WS_SCALARS2, n * 32)};
-        void* d_out = ctx->get(WS_OUT, m * 96);
-        cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
-        // ev[0..1]: staging buffer b filled; ev[2..3]: staging buffer b consumed
-        for (size_t j = 0; j < m; j++) {
-            int b = (int)(j & 1);
-            H2B_REQUIRE(scalars[j], "msm: null scalar column");
-            if (j >= 2) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2 + b], 0));
-            else if (j == 0) {  // order the first upload after whatever the compute stream was doing with the buffers
-                H2B_CUDA(cudaEventRecord(ctx->ev[2], ks));
-                H2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev[2], 0));
-            }
-            H2B_CUDA(cudaMemcpyAsync(stage[b], scalars[j], n * 32, cudaMemcpyHostToDevice, cs));
-            H2B_CUDA(cudaEventRecord(ctx->ev[b], cs));
-            H2B_CUDA(cudaStreamWaitEvent(ks, ctx->ev[b], 0));
-            msm_run(ctx, t, n, srs->c, srs->W, srs->W, stage[b], (char*)d_out + 96 * j);
-            H2B_CUDA(cudaEventRecord(ctx->ev[2 + b], ks));
+        std::vector<const void*> tables(m);
+        for (size_t j = 0; j < m; j++) tables[j] = srs_table(srs, basis[j], n);
+        constexpr int NL = h2b_ctx::NLANES;
+        const int nl = (int)(m < (size_t)NL ? m : (size_t)NL);
+        void* stage[NL];
+        for (int l = 0; l < nl; l++) {
+            ctx->cur_lane = l;
+            stage[l] = ctx->get(WS_SCALARS, n * 32);
         }
-        H2B_CUDA(cudaMemcpyAsync(out_xyz, d_out, m * 96, cudaMemcpyDeviceToHost, ks));
+        ctx->cur_lane = 0;
+        void* d_out = ctx->get(WS_OUT, m * 96);
+        uint64_t* h_out = (uint64_t*)ctx->get_pinned(0, m * 96);
+        cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+        // uploads run on the copy stream into per-lane staging buffers; lane l's MSM waits for its upload and
+        // releases the buffer as soon as k_digits has consumed it
+        H2B_CUDA(cudaEventRecord(ctx->fork_ev, ks));
+        H2B_CUDA(cudaStreamWaitEvent(cs, ctx->fork_ev, 0));
+        for (int l = 0; l < nl; l++) H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork_ev, 0));
+        for (size_t j = 0; j < m; j++) {
+            const int l = (int)(j % nl);
+            H2B_REQUIRE(scalars[j], "msm: null scalar column");
+            if (j >= (size_t)nl) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->lane_consumed[l], 0));
+            H2B_CUDA(cudaMemcpyAsync(stage[l], scalars[j], n * 32, cudaMemcpyHostToDevice, cs));
+            H2B_CUDA(cudaEventRecord(ctx->lane_ready[l], cs));
+            H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_ready[l], 0));
+            cudaStream_t saved = ctx->stream;
+            ctx->stream = ctx->lane_stream[l];
+            ctx->cur_lane = l;
+            try {
+                msm_run(ctx, tables[j], n, srs->c, srs->W, srs->W, stage[l], (char*)d_out + 96 * j, ctx->lane_consumed[l]);
+            } catch (...) {
+                ctx->stream = saved;
+                ctx->cur_lane = 0;
+                throw;
+            }
+            ctx->stream = saved;
+            ctx->cur_lane = 0;
+        }
+        for (int l = 0; l < nl; l++) {
+            H2B_CUDA(cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]));
+            H2B_CUDA(cudaStreamWaitEvent(ks, ctx->lane_done[l], 0));
+        }
+        H2B_CUDA(cudaMemcpyAsync(h_out, d_out, m * 96, cudaMemcpyDeviceToHost, ks));
         H2B_CUDA(cudaStreamSynchronize(ks));
+        memcpy(out_xyz, h_out, m * 96);
     });
 }
 int h2b_msm_g1(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
     const uint64_t* cols[1] = {scalars};
+    const int bases[1] = {basis};
     if (!scalars) return guarded(ctx, [&] { H2B_REQUIRE(false, "msm: null pointer"); });
-    return h2b_msm_g1_batch(ctx, srs, basis, cols, 1, n, out_xyz);
+    return h2b_msm_g1_batch(ctx, srs, bases, cols, 1, n, out_xyz);
 }
 int h2b_msm_g1_bases(h2b_ctx* ctx, const uint64_t* bases, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
     return guarded(ctx, [&] {
@@ -297,8 +349,10 @@ int h2b_msm_g1_bases(h2b_ctx* ctx, const uint64_t* bases, const uint64_t* scalar
         H2B_CUDA(cudaMemcpyAsync(d_b, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
         H2B_CUDA(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
         msm_run_adhoc(ctx, d_b, n, d_s, d_o);
-        H2B_CUDA(cudaMemcpyAsync(out_xyz, d_o, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        uint64_t* h_out = (uint64_t*)ctx->get_pinned(0, 96);
+        H2B_CUDA(cudaMemcpyAsync(h_out, d_o, 96, cudaMemcpyDeviceToHost, ctx->stream));
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(out_xyz, h_out, 96);
     });
 }
 int h2b_g1_sum_dev(h2b_ctx* ctx, const void* d_points_xyz, size_t m, void* d_out) {
@@ -314,8 +368,10 @@ int h2b_g1_sum(h2b_ctx* ctx, const uint64_t* points_xyz, size_t m, uint64_t out_
         void* d_o = (char*)d_p + m * 96;
         H2B_CUDA(cudaMemcpyAsync(d_p, points_xyz, m * 96, cudaMemcpyHostToDevice, ctx->stream));
         g1_sum_run(ctx, d_p, m, d_o);
-        H2B_CUDA(cudaMemcpyAsync(out_xyz, d_o, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        uint64_t* h_out = (uint64_t*)ctx->get_pinned(0, 96);
+        H2B_CUDA(cudaMemcpyAsync(h_out, d_o, 96, cudaMemcpyDeviceToHost, ctx->stream));
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(out_xyz, h_out, 96);
     });
 }
 int h2b_g1_normalize(h2b_ctx* ctx, uint64_t* points_xyz, size_t m) {

@@ -74,7 +74,7 @@ struct FrParams {
 };
 
 template <class P>
-struct Fp {
+struct __align__(16) Fp {
     u32 l[8];
 
     __device__ __forceinline__ static Fp zero() {

@@ -72,11 +72,22 @@ struct h2b_ctx {
     mutable std::mutex mu;
     std::string err;
     uint64_t launches = 0;
+    bool reduce_counter_zeroed = false;
+    void* reduce_counter_ptr = nullptr;
     struct Buf {
         void* p = nullptr;
         size_t cap = 0;
     };
-    Buf ws[h2b::WS_COUNT];
+    // MSM lanes: independent (stream, workspace) sets so that the latency-bound tail of one MSM (bucket
+    // reduction: a few CTAs) overlaps the throughput-bound phases of the next MSM of the same batch
+    static constexpr int NLANES = 3;
+    cudaStream_t lane_stream[NLANES] = {nullptr, nullptr, nullptr};
+    cudaEvent_t lane_done[NLANES] = {nullptr, nullptr, nullptr};
+    cudaEvent_t lane_ready[NLANES] = {nullptr, nullptr, nullptr};     // staging buffer filled (host batch API)
+    cudaEvent_t lane_consumed[NLANES] = {nullptr, nullptr, nullptr};  // staging buffer read by k_digits
+    cudaEvent_t fork_ev = nullptr;
+    int cur_lane = 0;  // workspace set used by get()
+    Buf ws[NLANES][h2b::WS_COUNT];
     Buf pinned[2];
     std::map<std::array<uint64_t, 5>, h2b::NttPlan*> ntt_plans;
 
@@ -136,7 +147,10 @@ static inline int ceil_log2(size_t n) {
 int msm_choose_c_fixed(size_t n);
 void msm_build_table(h2b_ctx* ctx, const void* d_bases, size_t count, int c, int W, void* d_table);
 // table mode: q = W (one bucket set), table = W x n affine; ad-hoc mode: q = 1, table = n affine
-void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out);
+void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out,
+             cudaEvent_t after_digits = nullptr);
+// m MSMs over the same table, spread over the context's lanes; joins on ctx->stream
+void msm_run_batch(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, int W, const void* const* d_scalars, size_t m, void* d_out);
 void g1_sum_run(h2b_ctx* ctx, const void* d_points, size_t m, void* d_out);
 void g1_normalize_run(h2b_ctx* ctx, void* d_points, size_t m);
 void g1_fixed_base_mul_run(h2b_ctx* ctx, const uint64_t base_xy[8], const void* d_scalars, size_t n, void* d_out);

@@ -13,8 +13,8 @@
 //                     64-byte affine points with 128-bit loads, XYZZ mixed adds; buckets that end inside
 //                     the chunk are written directly, runs cut by a chunk border go to a partial array
 //   k_collect(_big)   per bucket: add the partials of the chunks it spans
-//   k_reduce_level    running sums over slices of 8 buckets, hierarchical (weights folded as doublings)
-//   k_sum_level/k_finalize  plain tree sums (shared memory + per-thread serial), Horner over bucket sets
+//   k_rowcol_sums     bucket grid 2^mh x 2^ml: one warp per row sum / column sum (shuffle tree)
+//   k_weighted_final  lo * R_lo and hi * C_hi by small double-and-add, block sums, Horner over bucket sets
 //
 // Fixed bases (the SRS): `table[w*n + i] = 2^(c*w) * P_i` is built once per SRS (k_precompute_level), so all
 // windows of a scalar fall into ONE bucket set: no per-window reduction and no final doublings.
@@ -28,7 +28,6 @@ namespace h2b {
 static constexpr u32 SIGN_BIT = 0x80000000u;
 static constexpr int ACC_L = 16;       // sorted entries per accumulate thread
 static constexpr int BIG_PARTIALS = 64;  // buckets spanning more chunks than this are summed by a whole CTA
-static constexpr int RED_S = 8;        // buckets per reduce slice
 
 // ------------------------------------------------------------------------------------------------ digits
 // One thread per scalar.  keys/vals are window-major (index w*n + i) so that stores coalesce.
@@ -98,7 +97,7 @@ __device__ __forceinline__ Affine load_signed(const Affine* __restrict__ table, 
 }
 
 template <int L>
-__global__ void __launch_bounds__(128) k_accumulate(const u32* __restrict__ keys, const u32* __restrict__ vals,
+__global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ keys, const u32* __restrict__ vals,
                                                     const u32* __restrict__ off, u32 nb_total,
                                                     const Affine* __restrict__ table, XYZZ* __restrict__ buckets,
                                                     XYZZ* __restrict__ partials) {
@@ -197,41 +196,75 @@ __global__ void __launch_bounds__(256) k_collect_big(const u32* __restrict__ off
 }
 
 // ------------------------------------------------------------------------------------------------ bucket reduce
-// One level of V = sum_b (b+1) B_b = sum_b B_b + sum_b b*B_b.  With slices of S consecutive inputs,
-//   sum_j j*T_j = sum_J [ sum_i i*T_{JS+i} ] + S * sum_J J*T'_J ,  T'_J = sum_i T_{JS+i}
-// so each level emits T' (input of the next level) and R_J = sum_i i*T_{JS+i} scaled by the product of the
-// slice sizes of the levels below (2^dbl) into a pool that is summed plainly at the end.
-__global__ void __launch_bounds__(128) k_reduce_level(const XYZZ* __restrict__ tin, u32 n_in, int S, int dbl,
-                                                      u32 nsets, XYZZ* __restrict__ tout,
-                                                      XYZZ* __restrict__ pool, u32 pool_stride, u32 pool_off) {
-    const u32 n_out = n_in / S;
-    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_out * nsets) return;
-    const u32 set = g / n_out, J = g % n_out;
-    const XYZZ* src = tin + (size_t)set * n_in + (size_t)J * S;
-    XYZZ run = XYZZ::identity(), acc = XYZZ::identity();
-    for (int i = S - 1; i >= 1; i--) {
-        xyzz_add(run, XYZZ::load(src + i));
-        xyzz_add(acc, run);
+// V = sum_b (b+1) * B_b over one bucket set of 2^m buckets, arranged as a 2^mh x 2^ml grid (b = hi * 2^ml + lo):
+//     V = sum_b B_b  +  sum_lo lo * R_lo  +  2^ml * sum_hi hi * C_hi ,   R_lo = sum_hi B[hi][lo],  C_hi = sum_lo B[hi][lo].
+// A running sum over 2^16 buckets is a dependency chain of ~10^5 point additions; this form has depth
+// ~(2^mh / 32 + 5) for the row/column sums (one warp each, shuffle tree), ~2*ml for the small scalar
+// multiplications lo * R_lo / hi * C_hi (one thread each) and ~10 for the block sums and the final doublings.
+__device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
+    XYZZ r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], delta);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], delta);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], delta);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], delta);
     }
-    xyzz_add(run, XYZZ::load(src));
-    run.store(tout + (size_t)set * n_out + J);
-    for (int d = 0; d < dbl; d++) acc = xyzz_dbl(acc);
-    acc.store(pool + (size_t)set * pool_stride + pool_off + J);
+    return r;
+}
+// sum over the 32 lanes; valid in lane 0
+__device__ __forceinline__ XYZZ warp_sum(XYZZ v) {
+#pragma unroll 1
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        XYZZ o = shfl_down_xyzz(v, delta);
+        xyzz_add(v, o);
+    }
+    return v;
+}
+// block sum for up to 1024 threads: warp shuffle tree, then the first warp over the per-warp results
+__device__ __forceinline__ XYZZ block_sum(XYZZ v, XYZZ* sh32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // sh32 may still be read from a previous call
+    if (lane == 0) v.store(sh32 + wid);
+    __syncthreads();
+    XYZZ r = XYZZ::identity();
+    if (wid == 0) {
+        if (lane < nw) r = XYZZ::load(sh32 + lane);
+        r = warp_sum(r);
+    }
+    return r;  // valid in thread 0
 }
 
-// plain sums: out[set][j] = sum of up to G consecutive in[set][*]
-__global__ void __launch_bounds__(128) k_sum_level(const XYZZ* __restrict__ in, u32 n_in, u32 in_stride, int G,
-                                                   u32 nsets, XYZZ* __restrict__ out, u32 out_stride) {
-    const u32 n_out = (n_in + G - 1) / G;
-    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_out * nsets) return;
-    const u32 set = g / n_out, j = g % n_out;
-    const XYZZ* src = in + (size_t)set * in_stride;
-    u32 lo = j * G, hi = min(lo + (u32)G, n_in);
-    XYZZ acc = XYZZ::load(src + lo);
-    for (u32 i = lo + 1; i < hi; i++) xyzz_add(acc, XYZZ::load(src + i));
-    acc.store(out + (size_t)set * out_stride + j);
+// one warp per row sum R_lo / column sum C_hi.  rc[set][0 .. 2^ml) = R, rc[set][2^ml .. 2^ml + 2^mh) = C
+__global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ buckets, int ml, int mh, u32 nsets,
+                                                     XYZZ* __restrict__ rc) {
+    const u32 per_set = (1u << ml) + (1u << mh);
+    const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wg >= per_set * nsets) return;
+    const u32 set = wg / per_set, idx = wg % per_set;
+    const XYZZ* base = buckets + ((size_t)set << (ml + mh));
+    XYZZ acc = XYZZ::identity();
+    if (idx < (1u << ml)) {  // row sum over hi, stride 2^ml
+        for (u32 hi = lane; hi < (1u << mh); hi += 32) xyzz_add(acc, XYZZ::load(base + ((size_t)hi << ml) + idx));
+    } else {  // column sum over lo, contiguous
+        const u32 hi = idx - (1u << ml);
+        for (u32 lo = lane; lo < (1u << ml); lo += 32) xyzz_add(acc, XYZZ::load(base + ((size_t)hi << ml) + lo));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) acc.store(rc + (size_t)set * per_set + idx);
+}
+
+// k * p by left-to-right double-and-add (k < 2^bits)
+__device__ __forceinline__ XYZZ small_mul(const XYZZ& p, u32 k, int bits) {
+    XYZZ acc = XYZZ::identity();
+#pragma unroll 1
+    for (int b = bits - 1; b >= 0; b--) {
+        acc = xyzz_dbl(acc);
+        if ((k >> b) & 1) xyzz_add(acc, p);
+    }
+    return acc;
 }
 
 __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
@@ -250,27 +283,66 @@ __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
     z.store(o + 64);
 }
 
-// single CTA: V_set = top[set] + sum(pool[set][0..n_pool)), then Horner over sets with `shift` doublings
-__global__ void __launch_bounds__(256) k_finalize(const XYZZ* __restrict__ top, const XYZZ* __restrict__ pool,
-                                                  u32 n_pool, u32 pool_stride, u32 nsets, int shift,
-                                                  void* __restrict__ out) {
-    __shared__ XYZZ sh[256];
-    __shared__ XYZZ vset;
-    XYZZ total = XYZZ::identity();  // meaningful in thread 0
-    for (int set = (int)nsets - 1; set >= 0; set--) {
-        XYZZ acc = XYZZ::identity();
-        for (u32 i = threadIdx.x; i < n_pool; i += 256) xyzz_add(acc, XYZZ::load(pool + (size_t)set * pool_stride + i));
-        XYZZ r = block_sum_256(acc, sh);
-        if (threadIdx.x == 0) {
-            xyzz_add(r, XYZZ::load(top + set));
-            if (set != (int)nsets - 1)
-                for (int d = 0; d < shift; d++) total = xyzz_dbl(total);
-            xyzz_add(total, r);
-        }
-        __syncthreads();
+// grid = 2 * nsets CTAs: CTA (set, 0) -> S_lo = sum_lo lo * R_lo;  CTA (set, 1) -> S_hi = sum_hi hi * C_hi and T = sum C_hi.
+// The last CTA to finish combines V_set = T + S_lo + 2^ml * S_hi, runs Horner over the sets (shift doublings
+// between consecutive sets; one set when the bases are tabulated) and stores the Jacobian result.
+__global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__ rc, int ml, int mh, u32 nsets, int shift,
+                                                        XYZZ* __restrict__ parts /* nsets x 3 */, u32* __restrict__ done,
+                                                        void* __restrict__ out) {
+    __shared__ XYZZ sh32[32];
+    __shared__ u32 is_last;
+    const u32 set = blockIdx.x >> 1, kind = blockIdx.x & 1;
+    const u32 per_set = (1u << ml) + (1u << mh);
+    const XYZZ* src = rc + (size_t)set * per_set + (kind ? (1u << ml) : 0);
+    const int bits = kind ? mh : ml;
+    const u32 cnt = 1u << bits;
+    XYZZ wsum = XYZZ::identity(), psum = XYZZ::identity();
+    for (u32 j = threadIdx.x; j < cnt; j += blockDim.x) {
+        XYZZ p = XYZZ::load(src + j);
+        if (kind) xyzz_add(psum, p);
+        XYZZ w = small_mul(p, j, bits);
+        xyzz_add(wsum, w);
     }
-    if (threadIdx.x == 0) store_jacobian(total, out);
-    (void)vset;
+    XYZZ r = block_sum(wsum, sh32);
+    if (threadIdx.x == 0) r.store(parts + 3 * (size_t)set + kind);
+    if (kind) {
+        XYZZ t = block_sum(psum, sh32);
+        if (threadIdx.x == 0) t.store(parts + 3 * (size_t)set + 2);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // V_set for every set in parallel (one thread per set), then serial Horner in thread 0
+    XYZZ v = XYZZ::identity();
+    if (threadIdx.x < nsets) {
+        const XYZZ* p = parts + 3 * (size_t)threadIdx.x;
+        v = XYZZ::load(p + 1);  // S_hi
+        for (int d = 0; d < ml; d++) v = xyzz_dbl(v);
+        xyzz_add(v, XYZZ::load(p));      // + S_lo
+        xyzz_add(v, XYZZ::load(p + 2));  // + T
+    }
+    if (nsets == 1) {
+        if (threadIdx.x == 0) {
+            store_jacobian(v, out);
+            *done = 0;
+        }
+        return;
+    }
+    __shared__ XYZZ vsets[64];
+    if (threadIdx.x < nsets) v.store(vsets + threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XYZZ total = XYZZ::load(vsets + nsets - 1);
+        for (int s2 = (int)nsets - 2; s2 >= 0; s2--) {
+            for (int d = 0; d < shift; d++) total = xyzz_dbl(total);
+            xyzz_add(total, XYZZ::load(vsets + s2));
+        }
+        store_jacobian(total, out);
+        *done = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ SRS table
@@ -366,7 +438,8 @@ void msm_build_table(h2b_ctx* ctx, const void* d_bases, size_t count, int c, int
                    t + (size_t)w * count, (u32)count, c);
 }
 
-void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out) {
+void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out,
+             cudaEvent_t after_digits) {
     H2B_REQUIRE(n >= 1 && n <= ((size_t)1 << 27), "msm: n out of range");
     H2B_REQUIRE((size_t)W * n < ((size_t)1 << 31), "msm: n * windows exceeds the 31-bit table index");
     const u32 nbw = 1u << (c - 1);
@@ -387,6 +460,7 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
 
     H2B_LAUNCH(ctx, k_digits, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, nb_total,
                keys_a, vals_a);
+    if (after_digits) H2B_CUDA(cudaEventRecord(after_digits, st));
 
     const int key_bits = ceil_log2((size_t)nb_total + 1);
     size_t tmp_bytes = 0;
@@ -401,46 +475,17 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, ACC_L, partials, buckets, big + 1, big);
     H2B_LAUNCH(ctx, k_collect_big, 2 * ctx->sm_count, 256, 0, off, ACC_L, partials, buckets, big + 1, big);
 
-    // hierarchical bucket reduction
-    u32 pool_per_set = 0;
-    {
-        u32 nin = nbw;
-        while (nin > 1) {
-            int S = nin >= (u32)RED_S ? RED_S : (int)nin;
-            nin /= S;
-            pool_per_set += nin;
-        }
-    }
-    XYZZ* ta = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)nsets * (nbw / 2 + 1) * sizeof(XYZZ));
-    XYZZ* tb = (XYZZ*)ctx->get(WS_REDUCE_B, (size_t)nsets * (nbw / 2 + 1) * sizeof(XYZZ));
-    XYZZ* pool = (XYZZ*)ctx->get(WS_POOL, (size_t)nsets * (pool_per_set + 1) * sizeof(XYZZ));
-    XYZZ* pool2 = (XYZZ*)ctx->get(WS_POOL2, (size_t)nsets * (pool_per_set / 8 + 2) * sizeof(XYZZ));
-    const XYZZ* cur = buckets;
-    u32 nin = nbw, pool_off = 0;
-    int dbl = 0;
-    XYZZ* nxt = ta;
-    while (nin > 1) {
-        int S = nin >= (u32)RED_S ? RED_S : (int)nin;
-        u32 nout = nin / S;
-        H2B_LAUNCH(ctx, k_reduce_level, ceil_div((size_t)nout * nsets, 128), 128, 0, cur, nin, S, dbl, nsets, nxt, pool,
-                   pool_per_set, pool_off);
-        pool_off += nout;
-        dbl += ceil_log2(S);
-        nin = nout;
-        cur = nxt;
-        nxt = (nxt == ta) ? tb : ta;
-    }
-    // cur[set] is the plain sum of the set's buckets; pool[set][0..pool_per_set) the weighted parts
-    const XYZZ* pcur = pool;
-    u32 pn = pool_per_set, pstride = pool_per_set;
-    if (pn > 2048) {
-        u32 pout = (pn + 7) / 8;
-        H2B_LAUNCH(ctx, k_sum_level, ceil_div((size_t)pout * nsets, 128), 128, 0, pcur, pn, pstride, 8, nsets, pool2, pout);
-        pcur = pool2;
-        pn = pout;
-        pstride = pout;
-    }
-    H2B_LAUNCH(ctx, k_finalize, 1, 256, 0, cur, pcur, pn, pstride, nsets, c * q, d_out);
+    // bucket reduction: row/column sums of the 2^mh x 2^ml bucket grid, small scalar multiples, final combine
+    const int m = c - 1, ml = (m + 1) / 2, mh = m - ml;
+    H2B_REQUIRE(nsets <= 64, "msm: too many bucket sets");
+    const u32 per_set = (1u << ml) + (1u << mh);
+    XYZZ* rc = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)nsets * per_set * sizeof(XYZZ));
+    char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)nsets * 3 * sizeof(XYZZ) + 256);
+    XYZZ* parts = (XYZZ*)rb;
+    u32* done = (u32*)(rb + (size_t)nsets * 3 * sizeof(XYZZ));
+    H2B_CUDA(cudaMemsetAsync(done, 0, 4, st));
+    H2B_LAUNCH(ctx, k_rowcol_sums, ceil_div((size_t)nsets * per_set * 32, 128), 128, 0, buckets, ml, mh, nsets, rc);
+    H2B_LAUNCH(ctx, k_weighted_final, 2 * nsets, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
 }
 
 void g1_sum_run(h2b_ctx* ctx, const void* d_points, size_t m, void* d_out) {
@@ -462,6 +507,42 @@ void field_op_run(h2b_ctx* ctx, int field, int op, const void* a, const void* b,
         H2B_LAUNCH(ctx, k_field_op<Fq>, ceil_div(n, 128), 128, 0, op, (const uint64_t*)a, (const uint64_t*)b, (u32)n, (uint64_t*)out);
     else
         H2B_LAUNCH(ctx, k_field_op<Fr>, ceil_div(n, 128), 128, 0, op, (const uint64_t*)a, (const uint64_t*)b, (u32)n, (uint64_t*)out);
+}
+
+// Runs `fn(lane)` with the context switched to lane `lane` (its stream and workspace set).
+struct LaneScope {
+    h2b_ctx* ctx;
+    cudaStream_t saved_stream;
+    int saved_lane;
+    LaneScope(h2b_ctx* c, int lane) : ctx(c), saved_stream(c->stream), saved_lane(c->cur_lane) {
+        c->stream = c->lane_stream[lane];
+        c->cur_lane = lane;
+    }
+    ~LaneScope() {
+        ctx->stream = saved_stream;
+        ctx->cur_lane = saved_lane;
+    }
+};
+
+void msm_run_batch(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, int W, const void* const* d_scalars, size_t m,
+                   void* d_out) {
+    if (m == 0) return;
+    if (m == 1) {  // nothing to overlap: stay on the caller's stream
+        msm_run(ctx, d_tables[0], n, c, W, W, d_scalars[0], d_out);
+        return;
+    }
+    cudaStream_t main = ctx->stream;
+    H2B_CUDA(cudaEventRecord(ctx->fork_ev, main));
+    const int nl = (int)(m < (size_t)h2b_ctx::NLANES ? m : (size_t)h2b_ctx::NLANES);
+    for (int l = 0; l < nl; l++) H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork_ev, 0));
+    for (size_t j = 0; j < m; j++) {
+        LaneScope scope(ctx, (int)(j % nl));
+        msm_run(ctx, d_tables[j], n, c, W, W, d_scalars[j], (char*)d_out + 96 * j);
+    }
+    for (int l = 0; l < nl; l++) {
+        H2B_CUDA(cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]));
+        H2B_CUDA(cudaStreamWaitEvent(main, ctx->lane_done[l], 0));
+    }
 }
 
 // ad-hoc bases: W bucket sets, no table

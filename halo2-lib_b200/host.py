@@ -181,13 +181,21 @@ class ParamsKZG:
         """ParamsKZG::commit_lagrange(poly: Lagrange form) -> G1 (basis `g_lagrange`)."""
         return self._commit(BASIS_LAGRANGE, poly)
 
-    def commit_batch(self, basis: int, polys) -> np.ndarray:
+    def commit_batch(self, basis, polys) -> np.ndarray:
+        """m commitments of one prover phase; `basis` is an int or a per-column list (0 monomial, 1 lagrange)."""
         cols = [_u64(p, 4) for p in polys]
         m = len(cols)
         out = np.empty((m, 12), dtype=np.uint64)
         ptrs = (C.c_void_p * m)(*[c.ctypes.data for c in cols])
-        self.ctx.check(lib.h2b_msm_g1_batch(self.ctx.h, self.h, basis, ptrs, m, len(cols[0]) if m else 0, _ptr(out)))
+        bs = (C.c_int * m)(*([basis] * m if isinstance(basis, int) else list(basis)))
+        self.ctx.check(lib.h2b_msm_g1_batch(self.ctx.h, self.h, bs, ptrs, m, len(cols[0]) if m else 0, _ptr(out)))
         return out
+
+    def commit_batch_dev(self, basis, d_scalar_ptrs, n: int, d_out: int):
+        m = len(d_scalar_ptrs)
+        ptrs = (C.c_void_p * m)(*d_scalar_ptrs)
+        bs = (C.c_int * m)(*([basis] * m if isinstance(basis, int) else list(basis)))
+        self.ctx.check(lib.h2b_msm_g1_batch_dev(self.ctx.h, self.h, bs, ptrs, m, n, C.c_void_p(d_out)))
 
     def commit_dev(self, basis: int, d_scalars: int, n: int, d_out: int):
         self.ctx.check(lib.h2b_msm_g1_dev(self.ctx.h, self.h, basis, C.c_void_p(d_scalars), n, C.c_void_p(d_out)))

@@ -81,9 +81,10 @@ void h2b_srs_destroy(h2b_ctx* ctx, h2b_srs* srs);
  * (n == count of the SRS).  Result: a valid Jacobian representative (not normalised), like best_multiexp. */
 int h2b_msm_g1(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* scalars, size_t n,
                uint64_t out_xyz[12]);
-/* m commitments with the same basis (all advice columns of a phase, the h(X) pieces, ...): scalars[j] points
- * at n scalars; out = m x 12 limbs.  Uploads are double-buffered against the kernels. */
-int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* const* scalars, size_t m,
+/* m independent commitments of one prover phase (all advice columns, the lookup permuted pair, the h(X) pieces,
+ * ...): basis[j] selects the basis of column j, scalars[j] points at its n scalars; out = m x 12 limbs.  Uploads
+ * are pipelined against the kernels and the MSMs are spread over the context's lanes (see h2b_msm_g1_batch_dev). */
+int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m,
                      size_t n, uint64_t* out_xyz);
 /* Ad-hoc bases (n x 8 limbs on the host), no precomputation. */
 int h2b_msm_g1_bases(h2b_ctx* ctx, const uint64_t* bases, const uint64_t* scalars, size_t n,
@@ -91,6 +92,12 @@ int h2b_msm_g1_bases(h2b_ctx* ctx, const uint64_t* bases, const uint64_t* scalar
 /* Device-resident variants: d_scalars = n x 4 limbs, d_out = 12 limbs, all on the device; asynchronous. */
 int h2b_msm_g1_dev(h2b_ctx* ctx, const h2b_srs* srs, int basis, const void* d_scalars, size_t n, void* d_out);
 int h2b_msm_g1_bases_dev(h2b_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, void* d_out);
+/* m device-resident columns (basis[j] per column); the MSMs are spread over the context's internal lanes
+ * (streams + workspaces) so that the latency-bound bucket reduction of one overlaps the bucket accumulation
+ * of the next, and joined back onto the context's stream.  d_scalars = host array of m device pointers;
+ * d_out = m x 12 limbs on the device. */
+int h2b_msm_g1_batch_dev(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const void* const* d_scalars, size_t m,
+                         size_t n, void* d_out);
 /* out = sum of m Jacobian points (host, m x 12 limbs): combines the per-GPU partial sums after the
  * all-gather (EC addition is not an NCCL reduction op).  Runs on the device. */
 int h2b_g1_sum(h2b_ctx* ctx, const uint64_t* points_xyz, size_t m, uint64_t out_xyz[12]);
