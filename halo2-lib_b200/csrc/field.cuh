@@ -175,7 +175,11 @@ struct __align__(16) Fp {
     // into X[i], the carry of that add entering the Y chain at position i+1 — exactly where it belongs.
     // Bounds: running total < 2p before a row and < 2^288 * 2^(32 i) after the products, so the chains
     // that would carry into position i+9 cannot, and the final sum is < 2p.
+#ifdef H2B_MUL_NOINLINE
+    __device__ __noinline__ friend Fp operator*(const Fp& a, const Fp& b) {
+#else
     __device__ __forceinline__ friend Fp operator*(const Fp& a, const Fp& b) {
+#endif
         u32 E[17], O[17];
 #pragma unroll
         for (int k = 0; k < 17; k++) { E[k] = 0; O[k] = 0; }

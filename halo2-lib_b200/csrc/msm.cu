@@ -26,7 +26,7 @@
 namespace h2b {
 
 static constexpr u32 SIGN_BIT = 0x80000000u;
-static constexpr int ACC_L = 16;       // sorted entries per accumulate thread
+static constexpr int ACC_L_DEFAULT = 32;  // sorted entries per accumulate thread (H2B_ACC_L overrides: 16/32/64)
 static constexpr int BIG_PARTIALS = 64;  // buckets spanning more chunks than this are summed by a whole CTA
 
 // ------------------------------------------------------------------------------------------------ digits
@@ -283,7 +283,7 @@ __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
     z.store(o + 64);
 }
 
-// grid = 2 * nsets CTAs: CTA (set, 0) -> S_lo = sum_lo lo * R_lo;  CTA (set, 1) -> S_hi = sum_hi hi * C_hi and T = sum C_hi.
+// grid = 3 * nsets CTAs: CTA (set, 0) -> S_lo = sum_lo lo * R_lo;  (set, 1) -> S_hi = sum_hi hi * C_hi;  (set, 2) -> T = sum C_hi.
 // The last CTA to finish combines V_set = T + S_lo + 2^ml * S_hi, runs Horner over the sets (shift doublings
 // between consecutive sets; one set when the bases are tabulated) and stores the Jacobian result.
 __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__ rc, int ml, int mh, u32 nsets, int shift,
@@ -291,24 +291,22 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
                                                         void* __restrict__ out) {
     __shared__ XYZZ sh32[32];
     __shared__ u32 is_last;
-    const u32 set = blockIdx.x >> 1, kind = blockIdx.x & 1;
+    const u32 set = blockIdx.x / 3, kind = blockIdx.x % 3;
     const u32 per_set = (1u << ml) + (1u << mh);
     const XYZZ* src = rc + (size_t)set * per_set + (kind ? (1u << ml) : 0);
     const int bits = kind ? mh : ml;
     const u32 cnt = 1u << bits;
-    XYZZ wsum = XYZZ::identity(), psum = XYZZ::identity();
+    XYZZ wsum = XYZZ::identity();
     for (u32 j = threadIdx.x; j < cnt; j += blockDim.x) {
         XYZZ p = XYZZ::load(src + j);
-        if (kind) xyzz_add(psum, p);
-        XYZZ w = small_mul(p, j, bits);
-        xyzz_add(wsum, w);
+        if (kind == 2) xyzz_add(wsum, p);
+        else {
+            XYZZ w = small_mul(p, j, bits);
+            xyzz_add(wsum, w);
+        }
     }
     XYZZ r = block_sum(wsum, sh32);
     if (threadIdx.x == 0) r.store(parts + 3 * (size_t)set + kind);
-    if (kind) {
-        XYZZ t = block_sum(psum, sh32);
-        if (threadIdx.x == 0) t.store(parts + 3 * (size_t)set + 2);
-    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(done, 1u) == gridDim.x - 1);
@@ -416,6 +414,10 @@ __global__ void __launch_bounds__(128) k_field_op(int op, const uint64_t* __rest
 // ------------------------------------------------------------------------------------------------ host side
 int msm_choose_c_fixed(size_t n) {
     // one bucket set of 2^(c-1) buckets, ceil(255/c) table levels: cost ~ 10*n*W + 32*2^(c-1) field mults
+    if (const char* e = getenv("H2B_MSM_C")) {  // experiment override
+        int v = atoi(e);
+        if (v >= 4 && v <= 24) return v;
+    }
     int lg = ceil_log2(n ? n : 1);
     int c = lg - 2;
     if (c < 8) c = 8;
@@ -454,6 +456,11 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     u32* vals_b = (u32*)ctx->get(WS_VALS_B, M * 4);
     u32* off = (u32*)ctx->get(WS_OFFSETS, ((size_t)nb_total + 2) * 4);
     XYZZ* buckets = (XYZZ*)ctx->get(WS_BUCKETS, (size_t)nb_total * sizeof(XYZZ));
+    static const int ACC_L = [] {
+        const char* e = getenv("H2B_ACC_L");
+        int v = e ? atoi(e) : ACC_L_DEFAULT;
+        return (v == 16 || v == 32 || v == 64) ? v : ACC_L_DEFAULT;
+    }();
     const size_t n_chunks = (M + ACC_L - 1) / ACC_L;
     XYZZ* partials = (XYZZ*)ctx->get(WS_PARTIALS, 2 * n_chunks * sizeof(XYZZ));
     u32* big = (u32*)ctx->get(WS_BIGLIST, ((size_t)nb_total + 1) * 4);  // [0] = counter, list follows
@@ -470,8 +477,12 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
 
     H2B_LAUNCH(ctx, k_bucket_offsets, ceil_div((size_t)nb_total + 1, 256), 256, 0, keys_b, (u32)M, nb_total, off);
     H2B_CUDA(cudaMemsetAsync(big, 0, 4, st));
-    H2B_LAUNCH(ctx, k_accumulate<ACC_L>, ceil_div(n_chunks, 128), 128, 0, keys_b, vals_b, off, nb_total,
-               (const Affine*)d_table, buckets, partials);
+    if (ACC_L == 16)
+        H2B_LAUNCH(ctx, k_accumulate<16>, ceil_div(n_chunks, 128), 128, 0, keys_b, vals_b, off, nb_total, (const Affine*)d_table, buckets, partials);
+    else if (ACC_L == 32)
+        H2B_LAUNCH(ctx, k_accumulate<32>, ceil_div(n_chunks, 128), 128, 0, keys_b, vals_b, off, nb_total, (const Affine*)d_table, buckets, partials);
+    else
+        H2B_LAUNCH(ctx, k_accumulate<64>, ceil_div(n_chunks, 128), 128, 0, keys_b, vals_b, off, nb_total, (const Affine*)d_table, buckets, partials);
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, ACC_L, partials, buckets, big + 1, big);
     H2B_LAUNCH(ctx, k_collect_big, 2 * ctx->sm_count, 256, 0, off, ACC_L, partials, buckets, big + 1, big);
 
@@ -485,7 +496,7 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     u32* done = (u32*)(rb + (size_t)nsets * 3 * sizeof(XYZZ));
     H2B_CUDA(cudaMemsetAsync(done, 0, 4, st));
     H2B_LAUNCH(ctx, k_rowcol_sums, ceil_div((size_t)nsets * per_set * 32, 128), 128, 0, buckets, ml, mh, nsets, rc);
-    H2B_LAUNCH(ctx, k_weighted_final, 2 * nsets, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
+    H2B_LAUNCH(ctx, k_weighted_final, 3 * nsets, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
 }
 
 void g1_sum_run(h2b_ctx* ctx, const void* d_points, size_t m, void* d_out) {
