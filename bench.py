@@ -245,8 +245,7 @@ def run_b200(args):
     k = args.k
     n = 1 << k
     ext_k = k + 2
-    n_loc = n // world
-    begin = rank * n_loc
+    begin, n_loc = h.shard_range(n, rank, world)
     ctx = h.Context(local_rank)
     # a dedicated non-default stream: the library treats a NULL stream as "use the context's own stream", and the
     # CUDA events below must be recorded on the stream the kernels are launched on
@@ -283,7 +282,7 @@ def run_b200(args):
         cols_host.append(th)
         cols_dev.append(th.to(dev))
     basis_id = [0 if b == "monomial" else 1 for b, _ in MSM_SCHEDULE]
-    my_ntt = lambda i: (i % world) == rank  # one polynomial per device, round-robin
+    my_ntt = lambda i: h.ntt_owner(i, world) == rank  # one polynomial per device, round-robin
     polys_host = [torch.from_numpy(uniform_residues(rng, n).view(np.int64)).pin_memory() for _ in range(N_INTT)]
     polys_dev = [p.to(dev) for p in polys_host]
     ext_host = [torch.empty((1 << ext_k, 4), dtype=torch.int64).pin_memory() for _ in range(N_COSET)]
@@ -294,7 +293,6 @@ def run_b200(args):
     acol_host = torch.empty((n, 4), dtype=torch.int64).pin_memory()
     acol_dev = torch.empty((n, 4), dtype=torch.int64, device=dev)
     outs_dev = torch.zeros((len(MSM_SCHEDULE), 12), dtype=torch.int64, device=dev)
-    gather_bufs = {m: torch.zeros((world, m, 12), dtype=torch.int64, device=dev) for m in {len(p) for p in MSM_PHASES}} if world > 1 else None
     outs_host = np.zeros((len(MSM_SCHEDULE), 12), dtype=np.uint64)
     vp = C.c_void_p
 
@@ -306,8 +304,7 @@ def run_b200(args):
             params.commit_batch_dev([basis_id[j] for j in phase], [cols_dev[j].data_ptr() for j in phase], n_loc, outs_dev[j0].data_ptr())
             if world > 1:  # all-reduce under EC addition = all-gather of the 96-byte partials + local adds
                 npts = len(phase)
-                dist.all_gather_into_tensor(gather_bufs[npts], outs_dev[j0:j0 + npts])
-                gt = gather_bufs[npts].transpose(0, 1).contiguous()  # npts x world x 12
+                gt = h.all_gather_points(outs_dev[j0:j0 + npts])  # npts x world x 12
                 for jj in range(npts):
                     ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(gt[jj].data_ptr()), world, vp(outs_dev[j0 + jj].data_ptr())))
         for i in range(N_INTT):
@@ -331,9 +328,7 @@ def run_b200(args):
             ctx.check(lib.h2b_msm_g1_batch(ctx.h, params.h, bs, ptrs, m, n_loc, vp(out.ctypes.data)))
             if world > 1:
                 t = torch.from_numpy(out.view(np.int64)).to(dev)
-                g = torch.empty((world,) + tuple(t.shape), dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(g, t)
-                g = g.transpose(0, 1).contiguous()
+                g = h.all_gather_points(t)
                 for jj in range(m):
                     ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(g[jj].data_ptr()), world, vp(t[jj].data_ptr())))
                 out = t.cpu().numpy().view(np.uint64)

@@ -22,7 +22,8 @@ static constexpr int NTT_THREADS = 256;
 static constexpr int NTT_TILE_LOG = 11;  // elements per tile (2^11 * 32 B = 64 KB of shared memory)
 static constexpr int NTT_MAX_R = 10;
 
-// Fr::ZETA and ZETA^2 in Montgomery form (halo2curves bn256::Fr::ZETA) — from oracle/pyref.py
+// Fr::ZETA and ZETA^2 in Montgomery form (halo2curves bn256::Fr::ZETA); the same values are
+// emitted as FR_ZETA_U32 by tools/gen_domain_consts.py
 __device__ __forceinline__ Fr fr_zeta(int pw) {  // pw in {1,2}
     Fr z;
     if (pw == 1) {
