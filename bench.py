@@ -140,7 +140,12 @@ def cpu_sample(k: int, threads: int | None = None):
         orc._SO = so
     except Exception:
         pass
-    threads = threads or orc.max_threads()
+    if threads is None:  # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
+    orc.set_threads(threads)
     n = 1 << k
     ext_k = k + 2
     rng = np.random.default_rng(0xB2000000 + k)

@@ -5,9 +5,10 @@
 // halo2-base/src/utils/testing.rs:40-48).  The result is the same group element.
 //
 // Pipeline (all on the context's stream, no host synchronisation):
-//   k_digits          scalars (Montgomery) -> canonical -> signed base-2^c digits -> (bucket key, table index|sign)
-//   cub radix sort    by bucket key (<= 22 key bits)
-//   k_bucket_offsets  first sorted position of every bucket (binary search)
+//   k_digits<0>       scalars (Montgomery) -> canonical -> signed base-2^c digits -> histogram of bucket keys
+//   k_scan_tiles/apply exclusive scan: first sorted position of every bucket
+//   k_digits<1>       same recoding, scatters (table index | sign) to its sorted position (counting sort;
+//                     warp-aggregated atomics so that hot buckets cost one atomic per warp)
 //   k_accumulate      every thread owns EXACTLY L consecutive sorted entries (perfect balance under any
 //                     scalar distribution, witness columns are dominated by 0/1/88-bit limbs), gathers the
 //                     64-byte affine points with 128-bit loads, XYZZ mixed adds; buckets that end inside
@@ -18,8 +19,6 @@
 //
 // Fixed bases (the SRS): `table[w*n + i] = 2^(c*w) * P_i` is built once per SRS (k_precompute_level), so all
 // windows of a scalar fall into ONE bucket set: no per-window reduction and no final doublings.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "curve.cuh"
 #include "h2b_internal.cuh"
 
@@ -29,25 +28,20 @@ static constexpr u32 SIGN_BIT = 0x80000000u;
 static constexpr int ACC_L_DEFAULT = 32;  // sorted entries per accumulate thread (H2B_ACC_L overrides: 16/32/64)
 static constexpr int BIG_PARTIALS = 64;  // buckets spanning more chunks than this are summed by a whole CTA
 
-// ------------------------------------------------------------------------------------------------ digits
-// One thread per scalar.  keys/vals are window-major (index w*n + i) so that stores coalesce.
-// Window w belongs to bucket set w / q and table level w % q.
-__global__ void __launch_bounds__(256) k_digits(const uint64_t* __restrict__ scalars, u32 n, int c, int W, int q,
-                                                u32 nbw, u32 invalid_key, u32* __restrict__ keys,
-                                                u32* __restrict__ vals) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr s = Fr::load_nc(scalars + 4 * (size_t)i).from_mont();  // canonical integer, as `to_repr()` gives
+// ------------------------------------------------------------------------------------------------ digits + counting sort
+// Signed base-2^c recoding of one canonical scalar; calls f(w, digit_magnitude (1..2^(c-1)), negative) for every
+// non-zero digit.  W*c >= 255 so the last carry is absorbed.
+template <class F>
+__device__ __forceinline__ void for_each_digit(const Fr& s, int c, int W, F&& f) {
     const u32 half = 1u << (c - 1);
-    const u32 mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
+    const u32 mask = (1u << c) - 1u;
     u32 carry = 0;
     for (int w = 0; w < W; w++) {
         int bit = w * c;
         u32 raw = 0;
         if (bit < 256) {
             int limb = bit >> 5, off = bit & 31;
-            // dynamic limb index on a register array: select through a small unrolled scan
-            u32 lo = 0, hi = 0;
+            u32 lo = 0, hi = 0;  // dynamic limb index on a register array: select through a small unrolled scan
 #pragma unroll
             for (int t = 0; t < 8; t++) {
                 if (t == limb) lo = s.l[t];
@@ -57,36 +51,108 @@ __global__ void __launch_bounds__(256) k_digits(const uint64_t* __restrict__ sca
             raw = (u32)(v >> off) & mask;
         }
         u32 d = raw + carry;
-        u32 neg = 0;
+        bool neg = false;
         if (d > half) {
             d = (1u << c) - d;
-            neg = SIGN_BIT;
+            neg = true;
             carry = 1;
         } else {
             carry = 0;
         }
-        size_t o = (size_t)w * n + i;
-        if (d == 0) {
-            keys[o] = invalid_key;
-            vals[o] = 0;
-        } else {
-            keys[o] = (u32)(w / q) * nbw + (d - 1);
-            vals[o] = ((u32)(w % q) * n + i) | neg;
-        }
+        f(w, d, neg);
     }
 }
 
-// off[b] = first sorted position with key >= b, for b in [0, nb_total]; off[nb_total] = number of valid entries
-__global__ void __launch_bounds__(256) k_bucket_offsets(const u32* __restrict__ keys, u32 M, u32 nb_total,
-                                                        u32* __restrict__ off) {
-    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nb_total) return;
-    u32 lo = 0, hi = M;
-    while (lo < hi) {
-        u32 mid = (lo + hi) >> 1;
-        if (__ldg(keys + mid) < b) lo = mid + 1; else hi = mid;
+// Counter increment with a fast path for warps whose active lanes all hit the SAME counter (constant columns,
+// padding runs): one atomic per warp instead of 32 on one address.  Mixed warps use plain atomics; a hot address
+// then serialises in L2 at about one atomic per clock, which is still far below the accumulation time.
+// All 32 lanes must call; returns the slot of the lane.
+__device__ __forceinline__ u32 warp_agg_add(u32* counters, u32 key, bool active) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!active) return 0;
+    const u32 kmin = __reduce_min_sync(mask, key), kmax = __reduce_max_sync(mask, key);
+    if (kmin == kmax) {
+        const int leader = __ffs(mask) - 1;
+        u32 base = 0;
+        if ((int)lane == leader) base = atomicAdd(counters + key, (u32)__popc(mask));
+        base = __shfl_sync(mask, base, leader);
+        return base + __popc(mask & ((1u << lane) - 1));
     }
-    off[b] = lo;
+    return atomicAdd(counters + key, 1u);
+}
+
+// MODE 0: histogram of bucket keys.  MODE 1: scatter (table index | sign) to its sorted position via the cursors.
+// One thread per scalar; window w belongs to bucket set w / q and table level w % q.  Zero digits are dropped.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_digits(const uint64_t* __restrict__ scalars, u32 n, int c, int W, int q, u32 nbw,
+                                                u32* __restrict__ counters, u32* __restrict__ vals_sorted) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    Fr s = Fr::zero();
+    if (live) s = Fr::load_nc(scalars + 4 * (size_t)i).from_mont();  // canonical integer, as `to_repr()` gives
+    for_each_digit(s, c, W, [&](int w, u32 d, bool neg) {
+        const bool active = live && d != 0;
+        const u32 key = active ? (u32)(w / q) * nbw + (d - 1) : 0;
+        const u32 slot = warp_agg_add(counters, key, active);
+        if (MODE == 1 && active) vals_sorted[slot] = ((u32)(w % q) * n + i) | (neg ? SIGN_BIT : 0u);
+    });
+}
+
+// Exclusive scan of the histogram in two launches.  Tile = 2048 counters per CTA.
+// k_scan_tiles: off[b] = exclusive prefix inside the tile, tile_sums[tile] = tile total.
+// k_scan_apply: adds the sum of the preceding tile totals; cursor[b] = off[b]; off[nb] = grand total.
+static constexpr int SCAN_TILE = 2048;
+__global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ hist, u32 nb, u32* __restrict__ off,
+                                                    u32* __restrict__ tile_sums) {
+    __shared__ u32 sh[SCAN_TILE];
+    __shared__ u32 wsum[8];
+    const u32 base = blockIdx.x * SCAN_TILE, t = threadIdx.x;
+    for (u32 e = t; e < SCAN_TILE; e += 256) sh[e] = (base + e < nb) ? hist[base + e] : 0;  // coalesced
+    __syncthreads();
+    u32 v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = sh[t * 8 + j]; sum += v[j]; }
+    // block exclusive scan of the 256 per-thread sums: warp shuffle scan + scan of the 8 warp totals
+    u32 inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((t & 31) >= (u32)d) inc += o;
+    }
+    if ((t & 31) == 31) wsum[t >> 5] = inc;
+    __syncthreads();
+    u32 wbase = 0;
+    for (u32 w = 0; w < (t >> 5); w++) wbase += wsum[w];
+    u32 run = wbase + inc - sum;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sh[t * 8 + j] = run; run += v[j]; }
+    __syncthreads();
+    for (u32 e = t; e < SCAN_TILE; e += 256)
+        if (base + e < nb) off[base + e] = sh[e];
+    if (t == 255) tile_sums[blockIdx.x] = run;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(u32 nb, u32 ntiles, const u32* __restrict__ tile_sums,
+                                                    u32* __restrict__ off, u32* __restrict__ cursor) {
+    __shared__ u32 red[256];
+    const u32 t = threadIdx.x;
+    u32 s = 0;
+    for (u32 j = t; j < blockIdx.x; j += 256) s += tile_sums[j];  // sum of the preceding tiles
+    red[t] = s;
+    __syncthreads();
+    for (int d = 128; d >= 1; d >>= 1) {
+        if (t < (u32)d) red[t] += red[t + d];
+        __syncthreads();
+    }
+    const u32 add = red[0], base = blockIdx.x * SCAN_TILE;
+    for (u32 e = t; e < SCAN_TILE; e += 256)
+        if (base + e < nb) {
+            u32 o = off[base + e] + add;
+            off[base + e] = o;
+            cursor[base + e] = o;
+        }
+    if (blockIdx.x == ntiles - 1 && t == 0) off[nb] = add + tile_sums[ntiles - 1];
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
@@ -96,38 +162,53 @@ __device__ __forceinline__ Affine load_signed(const Affine* __restrict__ table, 
     return p;
 }
 
+// first bucket b in [lo, nb) with off[b + 1] > pos  (the bucket that owns sorted position pos)
+__device__ __forceinline__ u32 bucket_of(const u32* __restrict__ off, u32 lo, u32 nb, u32 pos) {
+    u32 hi = nb;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (__ldg(off + mid + 1) > pos) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 template <int L>
-__global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ keys, const u32* __restrict__ vals,
-                                                    const u32* __restrict__ off, u32 nb_total,
-                                                    const Affine* __restrict__ table, XYZZ* __restrict__ buckets,
-                                                    XYZZ* __restrict__ partials) {
+__global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ vals, const u32* __restrict__ off,
+                                                       u32 nb_total, const Affine* __restrict__ table,
+                                                       XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 mv = __ldg(off + nb_total);  // valid (non-zero-digit) entries
+    const u32 mv = __ldg(off + nb_total);  // number of (non-zero-digit) entries
     const u64 cs64 = (u64)t * L;
     if (cs64 >= mv) return;
     const u32 cs = (u32)cs64;
     const u32 ce = (mv - cs < (u32)L) ? mv : cs + L;
 
+    u32 cur = bucket_of(off, 0, nb_total, cs);
+    u32 run_end = __ldg(off + cur + 1);
     XYZZ acc = XYZZ::identity();
-    u32 cur = __ldg(keys + cs);
     Affine p = load_signed(table, __ldg(vals + cs));
     for (u32 i = cs; i < ce; i++) {
         Affine pn;
-        u32 kn = cur;
         const bool more = (i + 1 < ce);
-        if (more) {  // prefetch the next gather while this add runs
-            kn = __ldg(keys + i + 1);
-            pn = load_signed(table, __ldg(vals + i + 1));
-        }
+        if (more) pn = load_signed(table, __ldg(vals + i + 1));  // prefetch the next gather while this add runs
         xyzz_madd(acc, p);
-        if (!more || kn != cur) {
+        if (!more || i + 1 == run_end) {
             // the run of bucket `cur` ends here (inside this chunk or at its border)
-            const u32 s = __ldg(off + cur), e = __ldg(off + cur + 1);
-            if (s >= cs && e - cs <= (u32)L) acc.store(buckets + cur);          // bucket lies inside the chunk
+            const u32 s = __ldg(off + cur);
+            if (s >= cs && run_end - cs <= (u32)L) acc.store(buckets + cur);    // bucket lies inside the chunk
             else if (s <= cs) acc.store(partials + 2 * (size_t)t);              // covers the chunk start
             else acc.store(partials + 2 * (size_t)t + 1);                        // starts inside, runs past the end
             acc = XYZZ::identity();
-            cur = kn;
+            if (more) {  // next non-empty bucket: a few linear steps, then binary search (long empty gaps)
+                u32 b = cur + 1;
+                int steps = 0;
+                while (__ldg(off + b + 1) <= i + 1) {
+                    b++;
+                    if (++steps == 4) { b = bucket_of(off, b, nb_total, i + 1); break; }
+                }
+                cur = b;
+                run_end = __ldg(off + cur + 1);
+            }
         }
         if (more) p = pn;
     }
@@ -450,10 +531,10 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     const size_t M = (size_t)W * n;
     cudaStream_t st = ctx->stream;
 
-    u32* keys_a = (u32*)ctx->get(WS_KEYS_A, M * 4);
-    u32* keys_b = (u32*)ctx->get(WS_KEYS_B, M * 4);
-    u32* vals_a = (u32*)ctx->get(WS_VALS_A, M * 4);
-    u32* vals_b = (u32*)ctx->get(WS_VALS_B, M * 4);
+    u32* vals = (u32*)ctx->get(WS_VALS_A, M * 4);
+    u32* cnt = (u32*)ctx->get(WS_KEYS_A, (2 * ((size_t)nb_total + 2) + nb_total / SCAN_TILE + 2) * 4);  // histogram, cursors, tile sums
+    u32* hist = cnt;
+    u32* cursor = cnt + nb_total + 2;
     u32* off = (u32*)ctx->get(WS_OFFSETS, ((size_t)nb_total + 2) * 4);
     XYZZ* buckets = (XYZZ*)ctx->get(WS_BUCKETS, (size_t)nb_total * sizeof(XYZZ));
     static const int ACC_L = [] {
@@ -465,24 +546,23 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     XYZZ* partials = (XYZZ*)ctx->get(WS_PARTIALS, 2 * n_chunks * sizeof(XYZZ));
     u32* big = (u32*)ctx->get(WS_BIGLIST, ((size_t)nb_total + 1) * 4);  // [0] = counter, list follows
 
-    H2B_LAUNCH(ctx, k_digits, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, nb_total,
-               keys_a, vals_a);
+    // counting sort by bucket: histogram -> exclusive scan -> scatter (digits are recomputed, not stored)
+    H2B_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nb_total + 1) * 4, st));
+    H2B_LAUNCH(ctx, k_digits<0>, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, hist, (u32*)nullptr);
+    const u32 ntiles = (nb_total + SCAN_TILE - 1) / SCAN_TILE;
+    u32* tile_sums = cursor + nb_total + 2;
+    H2B_LAUNCH(ctx, k_scan_tiles, ntiles, 256, 0, hist, nb_total, off, tile_sums);
+    H2B_LAUNCH(ctx, k_scan_apply, ntiles, 256, 0, nb_total, ntiles, tile_sums, off, cursor);
+    H2B_LAUNCH(ctx, k_digits<1>, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, cursor, vals);
     if (after_digits) H2B_CUDA(cudaEventRecord(after_digits, st));
 
-    const int key_bits = ceil_log2((size_t)nb_total + 1);
-    size_t tmp_bytes = 0;
-    H2B_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, vals_a, vals_b, (int)M, 0, key_bits, st));
-    void* tmp = ctx->get(WS_SORT_TMP, tmp_bytes);
-    H2B_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, vals_a, vals_b, (int)M, 0, key_bits, st));
-
-    H2B_LAUNCH(ctx, k_bucket_offsets, ceil_div((size_t)nb_total + 1, 256), 256, 0, keys_b, (u32)M, nb_total, off);
     H2B_CUDA(cudaMemsetAsync(big, 0, 4, st));
     if (ACC_L == 16)
-        H2B_LAUNCH(ctx, k_accumulate<16>, ceil_div(n_chunks, 128), 128, 0, keys_b, vals_b, off, nb_total, (const Affine*)d_table, buckets, partials);
+        H2B_LAUNCH(ctx, k_accumulate<16>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, (const Affine*)d_table, buckets, partials);
     else if (ACC_L == 32)
-        H2B_LAUNCH(ctx, k_accumulate<32>, ceil_div(n_chunks, 128), 128, 0, keys_b, vals_b, off, nb_total, (const Affine*)d_table, buckets, partials);
+        H2B_LAUNCH(ctx, k_accumulate<32>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, (const Affine*)d_table, buckets, partials);
     else
-        H2B_LAUNCH(ctx, k_accumulate<64>, ceil_div(n_chunks, 128), 128, 0, keys_b, vals_b, off, nb_total, (const Affine*)d_table, buckets, partials);
+        H2B_LAUNCH(ctx, k_accumulate<64>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, (const Affine*)d_table, buckets, partials);
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, ACC_L, partials, buckets, big + 1, big);
     H2B_LAUNCH(ctx, k_collect_big, 2 * ctx->sm_count, 256, 0, off, ACC_L, partials, buckets, big + 1, big);
 

@@ -458,6 +458,13 @@ void orc_eval_rational(const u64 *num, const u64 *den, size_t n, u64 *out) {
         u64 di[4]; f_inv(&FR, di, den + 4 * i); f_mul(&FR, out + 4 * i, num + 4 * i, di);
     }
 }
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -64,6 +64,11 @@ def max_threads() -> int:
     return lib().orc_max_threads()
 
 
+def set_threads(n: int) -> None:
+    """override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to every rank)"""
+    lib().orc_set_threads(C.c_int(n))
+
+
 def g1_is_on_curve(xy) -> bool:
     xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(8)
     return bool(lib().orc_g1_is_on_curve(_p(xy)))
