@@ -20,6 +20,7 @@
 // Fixed bases (the SRS): `table[w*n + i] = 2^(c*w) * P_i` is built once per SRS (k_precompute_level), so all
 // windows of a scalar fall into ONE bucket set: no per-window reduction and no final doublings.
 #include "curve.cuh"
+#include "quad.cuh"
 #include "h2b_internal.cuh"
 
 namespace h2b {
@@ -317,35 +318,24 @@ __device__ __forceinline__ XYZZ block_sum(XYZZ v, XYZZ* sh32) {
     return r;  // valid in thread 0
 }
 
-// one warp per row sum R_lo / column sum C_hi.  rc[set][0 .. 2^ml) = R, rc[set][2^ml .. 2^ml + 2^mh) = C
+// One CTA of 128 threads (32 lane-quads, quad.cuh) per row sum R_lo / column sum C_hi: every quad adds its
+// stride-32 share of the row (column), then the 32 quads are summed.  rc[set][0 .. 2^ml) = R, rc[set][2^ml ..) = C.
 __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ buckets, int ml, int mh, u32 nsets,
                                                      XYZZ* __restrict__ rc) {
+    __shared__ XYZZ sh[4];
     const u32 per_set = (1u << ml) + (1u << mh);
-    const u32 wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wg >= per_set * nsets) return;
-    const u32 set = wg / per_set, idx = wg % per_set;
+    const u32 set = blockIdx.x / per_set, idx = blockIdx.x % per_set;
+    const u32 qid = threadIdx.x >> 2;
     const XYZZ* base = buckets + ((size_t)set << (ml + mh));
     XYZZ acc = XYZZ::identity();
     if (idx < (1u << ml)) {  // row sum over hi, stride 2^ml
-        for (u32 hi = lane; hi < (1u << mh); hi += 32) xyzz_add(acc, XYZZ::load(base + ((size_t)hi << ml) + idx));
+        for (u32 hi = qid; hi < (1u << mh); hi += 32) quad_add(acc, XYZZ::load(base + ((size_t)hi << ml) + idx));
     } else {  // column sum over lo, contiguous
         const u32 hi = idx - (1u << ml);
-        for (u32 lo = lane; lo < (1u << ml); lo += 32) xyzz_add(acc, XYZZ::load(base + ((size_t)hi << ml) + lo));
+        for (u32 lo = qid; lo < (1u << ml); lo += 32) quad_add(acc, XYZZ::load(base + ((size_t)hi << ml) + lo));
     }
-    acc = warp_sum(acc);
-    if (lane == 0) acc.store(rc + (size_t)set * per_set + idx);
-}
-
-// k * p by left-to-right double-and-add (k < 2^bits)
-__device__ __forceinline__ XYZZ small_mul(const XYZZ& p, u32 k, int bits) {
-    XYZZ acc = XYZZ::identity();
-#pragma unroll 1
-    for (int b = bits - 1; b >= 0; b--) {
-        acc = xyzz_dbl(acc);
-        if ((k >> b) & 1) xyzz_add(acc, p);
-    }
-    return acc;
+    acc = quad_block_sum(acc, sh);
+    if (threadIdx.x == 0) acc.store(rc + (size_t)set * per_set + idx);
 }
 
 __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
@@ -364,63 +354,72 @@ __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
     z.store(o + 64);
 }
 
-// grid = 3 * nsets CTAs: CTA (set, 0) -> S_lo = sum_lo lo * R_lo;  (set, 1) -> S_hi = sum_hi hi * C_hi;  (set, 2) -> T = sum C_hi.
-// The last CTA to finish combines V_set = T + S_lo + 2^ml * S_hi, runs Horner over the sets (shift doublings
-// between consecutive sets; one set when the bases are tabulated) and stores the Jacobian result.
+// Weighted sums S_lo = sum_lo lo * R_lo, S_hi = sum_hi hi * C_hi and T = sum_hi C_hi, 64 points (one per lane-quad)
+// per CTA.  CTAs of a set: [0, sub_lo) -> kind 0 (lo, weighted), then sub_hi CTAs kind 1 (hi, weighted), then sub_hi
+// CTAs kind 2 (hi, plain).  The last CTA to finish adds the CTA partials, forms V_set = T + S_lo + 2^ml * S_hi, runs
+// Horner over the sets (`shift` doublings between consecutive sets; one set when the bases are tabulated) and
+// stores the Jacobian result.
+static constexpr int WQ = 64;  // quads (points) per CTA of k_weighted_final
 __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__ rc, int ml, int mh, u32 nsets, int shift,
-                                                        XYZZ* __restrict__ parts /* nsets x 3 */, u32* __restrict__ done,
+                                                        XYZZ* __restrict__ parts, u32* __restrict__ done,
                                                         void* __restrict__ out) {
-    __shared__ XYZZ sh32[32];
+    __shared__ XYZZ sh[8];
+    __shared__ XYZZ comb[3];
+    __shared__ XYZZ vsets[64];
     __shared__ u32 is_last;
-    const u32 set = blockIdx.x / 3, kind = blockIdx.x % 3;
+    const u32 sub_lo = ((1u << ml) + WQ - 1) / WQ, sub_hi = ((1u << mh) + WQ - 1) / WQ;
+    const u32 cta_per_set = sub_lo + 2 * sub_hi;
+    const u32 set = blockIdx.x / cta_per_set, c = blockIdx.x % cta_per_set;
+    const u32 kind = c < sub_lo ? 0 : (c < sub_lo + sub_hi ? 1 : 2);
+    const u32 sub = kind == 0 ? c : (kind == 1 ? c - sub_lo : c - sub_lo - sub_hi);
     const u32 per_set = (1u << ml) + (1u << mh);
     const XYZZ* src = rc + (size_t)set * per_set + (kind ? (1u << ml) : 0);
     const int bits = kind ? mh : ml;
-    const u32 cnt = 1u << bits;
-    XYZZ wsum = XYZZ::identity();
-    for (u32 j = threadIdx.x; j < cnt; j += blockDim.x) {
+    const u32 qid = threadIdx.x >> 2;
+    const u32 j = sub * WQ + qid;
+    XYZZ w = XYZZ::identity();
+    if (j < (1u << bits)) {
         XYZZ p = XYZZ::load(src + j);
-        if (kind == 2) xyzz_add(wsum, p);
-        else {
-            XYZZ w = small_mul(p, j, bits);
-            xyzz_add(wsum, w);
-        }
+        w = (kind == 2) ? p : quad_small_mul(p, j, bits);
     }
-    XYZZ r = block_sum(wsum, sh32);
-    if (threadIdx.x == 0) r.store(parts + 3 * (size_t)set + kind);
+    w = quad_block_sum(w, sh);
+    if (threadIdx.x == 0) w.store(parts + (size_t)set * cta_per_set + c);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(done, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // V_set for every set in parallel (one thread per set), then serial Horner in thread 0
-    XYZZ v = XYZZ::identity();
-    if (threadIdx.x < nsets) {
-        const XYZZ* p = parts + 3 * (size_t)threadIdx.x;
-        v = XYZZ::load(p + 1);  // S_hi
-        for (int d = 0; d < ml; d++) v = xyzz_dbl(v);
-        xyzz_add(v, XYZZ::load(p));      // + S_lo
-        xyzz_add(v, XYZZ::load(p + 2));  // + T
-    }
-    if (nsets == 1) {
-        if (threadIdx.x == 0) {
-            store_jacobian(v, out);
-            *done = 0;
+
+    for (u32 s0 = 0; s0 < nsets; s0++) {
+        // three quads add the CTA partials of S_lo, S_hi, T of this set
+        if (qid < 3) {
+            const XYZZ* p = parts + (size_t)s0 * cta_per_set + (qid == 0 ? 0 : (qid == 1 ? sub_lo : sub_lo + sub_hi));
+            const u32 cnt = qid == 0 ? sub_lo : sub_hi;
+            XYZZ a = XYZZ::load(p);
+            for (u32 i = 1; i < cnt; i++) quad_add(a, XYZZ::load(p + i));
+            if ((threadIdx.x & 3) == 0) a.store(comb + qid);
         }
-        return;
+        __syncthreads();
+        if (qid == 0) {
+            XYZZ v = XYZZ::load(comb + 1);  // S_hi
+            for (int d = 0; d < ml; d++) quad_dbl(v);
+            quad_add(v, XYZZ::load(comb + 0));  // + S_lo
+            quad_add(v, XYZZ::load(comb + 2));  // + T
+            if (threadIdx.x == 0) v.store(vsets + s0);
+        }
+        __syncthreads();
     }
-    __shared__ XYZZ vsets[64];
-    if (threadIdx.x < nsets) v.store(vsets + threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (qid == 0) {
         XYZZ total = XYZZ::load(vsets + nsets - 1);
         for (int s2 = (int)nsets - 2; s2 >= 0; s2--) {
-            for (int d = 0; d < shift; d++) total = xyzz_dbl(total);
-            xyzz_add(total, XYZZ::load(vsets + s2));
+            for (int d = 0; d < shift; d++) quad_dbl(total);
+            quad_add(total, XYZZ::load(vsets + s2));
         }
-        store_jacobian(total, out);
-        *done = 0;
+        if (threadIdx.x == 0) {
+            store_jacobian(total, out);
+            *done = 0;
+        }
     }
 }
 
@@ -442,10 +441,11 @@ __global__ void __launch_bounds__(128) k_precompute_level(const Affine* __restri
 
 // ------------------------------------------------------------------------------------------------ small group ops
 __global__ void __launch_bounds__(256) k_g1_sum(const uint64_t* __restrict__ pts, u32 m, void* __restrict__ out) {
-    __shared__ XYZZ sh[256];
+    __shared__ XYZZ sh[8];
+    const u32 qid = threadIdx.x >> 2;
     XYZZ acc = XYZZ::identity();
-    for (u32 i = threadIdx.x; i < m; i += 256) xyzz_add(acc, xyzz_from_jacobian(pts + 12 * (size_t)i));
-    XYZZ r = block_sum_256(acc, sh);
+    for (u32 i = qid; i < m; i += 64) quad_add(acc, xyzz_from_jacobian(pts + 12 * (size_t)i));
+    XYZZ r = quad_block_sum(acc, sh);
     if (threadIdx.x == 0) store_jacobian(r, out);
 }
 __global__ void __launch_bounds__(128) k_g1_normalize(uint64_t* __restrict__ pts, u32 m) {
@@ -570,13 +570,15 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     const int m = c - 1, ml = (m + 1) / 2, mh = m - ml;
     H2B_REQUIRE(nsets <= 64, "msm: too many bucket sets");
     const u32 per_set = (1u << ml) + (1u << mh);
+    const u32 sub_lo = ((1u << ml) + WQ - 1) / WQ, sub_hi = ((1u << mh) + WQ - 1) / WQ;
+    const u32 cta_per_set = sub_lo + 2 * sub_hi;
     XYZZ* rc = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)nsets * per_set * sizeof(XYZZ));
-    char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)nsets * 3 * sizeof(XYZZ) + 256);
+    char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)nsets * cta_per_set * sizeof(XYZZ) + 256);
     XYZZ* parts = (XYZZ*)rb;
-    u32* done = (u32*)(rb + (size_t)nsets * 3 * sizeof(XYZZ));
+    u32* done = (u32*)(rb + (size_t)nsets * cta_per_set * sizeof(XYZZ));
     H2B_CUDA(cudaMemsetAsync(done, 0, 4, st));
-    H2B_LAUNCH(ctx, k_rowcol_sums, ceil_div((size_t)nsets * per_set * 32, 128), 128, 0, buckets, ml, mh, nsets, rc);
-    H2B_LAUNCH(ctx, k_weighted_final, 3 * nsets, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
+    H2B_LAUNCH(ctx, k_rowcol_sums, nsets * per_set, 128, 0, buckets, ml, mh, nsets, rc);
+    H2B_LAUNCH(ctx, k_weighted_final, nsets * cta_per_set, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
 }
 
 void g1_sum_run(h2b_ctx* ctx, const void* d_points, size_t m, void* d_out) {
