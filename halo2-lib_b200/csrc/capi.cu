@@ -99,6 +99,9 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
         ctx->device = device;
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+        for (auto& row : ctx->pipe_ev)
+            for (auto& e : row) H2B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& ev : ctx->ev) H2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (int l = 0; l < h2b_ctx::NLANES; l++) {
             H2B_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
@@ -147,6 +150,10 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
+    for (auto& row : ctx->pipe_ev)
+        for (auto& e : row)
+            if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -466,6 +473,55 @@ int h2b_coeff_to_extended(h2b_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs,
         H2B_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));
     });
+}
+
+// m transforms of one kind through three rotating device buffers: the upload of column i+1 (copy stream) and the
+// download of column i-1 (second copy stream) overlap the kernels of column i (context stream).
+// mode: 1 lagrange_to_coeff, 2 coeff_to_lagrange, 3 extended_to_coeff (in place, n_in = 2^log_n), 4 coeff_to_extended.
+static void ntt_batch_host(h2b_ctx* ctx, int mode, const uint64_t* const* in, uint64_t* const* out, size_t m, size_t n_in,
+                           uint32_t log_n) {
+    H2B_REQUIRE(in && out, "ntt batch: null pointer");
+    H2B_REQUIRE(log_n <= 28 && n_in <= ((size_t)1 << log_n), "ntt batch: sizes out of range");
+    if (m == 0) return;
+    const size_t n = (size_t)1 << log_n, bytes = n * 32;
+    const int slots[3] = {WS_NTT_A, WS_NTT_C, WS_NTT_D};
+    void* buf[3];
+    for (int b = 0; b < 3; b++) buf[b] = ctx->get(slots[b], bytes);
+    (void)ctx->get(WS_NTT_B, bytes);  // scratch of ntt_run: allocate before anything is in flight
+    uint64_t w[4];
+    int scale = 0, coset = 0;
+    if (mode == 2 || mode == 4) domain_omega(log_n, w, false);
+    else { domain_omega(log_n, w, true); scale = 1; }
+    if (mode == 3) coset = 2;
+    if (mode == 4) coset = 1;
+    cudaStream_t up = ctx->copy_stream, ks = ctx->stream, down = ctx->copy_stream2;
+    H2B_CUDA(cudaEventRecord(ctx->fork_ev, ks));
+    H2B_CUDA(cudaStreamWaitEvent(up, ctx->fork_ev, 0));
+    for (size_t i = 0; i < m; i++) {
+        const int b = (int)(i % 3);
+        H2B_REQUIRE(in[i] && out[i], "ntt batch: null column");
+        if (i >= 3) H2B_CUDA(cudaStreamWaitEvent(up, ctx->pipe_ev[b][2], 0));  // buffer b downloaded
+        H2B_CUDA(cudaMemcpyAsync(buf[b], in[i], n_in * 32, cudaMemcpyHostToDevice, up));
+        H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][0], up));
+        H2B_CUDA(cudaStreamWaitEvent(ks, ctx->pipe_ev[b][0], 0));
+        ntt_run(ctx, buf[b], n_in, buf[b], log_n, w, scale, coset);
+        H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][1], ks));
+        H2B_CUDA(cudaStreamWaitEvent(down, ctx->pipe_ev[b][1], 0));
+        H2B_CUDA(cudaMemcpyAsync(out[i], buf[b], bytes, cudaMemcpyDeviceToHost, down));
+        H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][2], down));
+    }
+    H2B_CUDA(cudaStreamSynchronize(down));
+    H2B_CUDA(cudaStreamSynchronize(ks));
+}
+int h2b_lagrange_to_coeff_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k) {
+    return guarded(ctx, [&] { ntt_batch_host(ctx, 1, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k); });
+}
+int h2b_coeff_to_lagrange_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k) {
+    return guarded(ctx, [&] { ntt_batch_host(ctx, 2, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k); });
+}
+int h2b_coeff_to_extended_batch(h2b_ctx* ctx, const uint64_t* const* coeffs, size_t m, size_t n_coeffs, uint32_t ext_k,
+                                uint64_t* const* out) {
+    return guarded(ctx, [&] { ntt_batch_host(ctx, 4, coeffs, out, m, n_coeffs, ext_k); });
 }
 
 // ------------------------------------------------------------------------------------------------ assignment

@@ -51,6 +51,8 @@ enum WsSlot {
     WS_BASES,         // ad-hoc bases staging
     WS_NTT_A,
     WS_NTT_B,
+    WS_NTT_C,
+    WS_NTT_D,
     WS_ASSIGN_IN,
     WS_ASSIGN_OUT,
     WS_MISC,
@@ -67,6 +69,8 @@ struct h2b_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream2 = nullptr;  // device-to-host leg of the pipelined batch NTT entry points
+    cudaEvent_t pipe_ev[3][3] = {};       // [buffer][uploaded, computed, downloaded]
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     mutable std::mutex mu;

@@ -236,6 +236,21 @@ class EvaluationDomain:
         self.ctx.check(lib.h2b_coeff_to_lagrange(self.ctx.h, _ptr(a), self.k))
         return a
 
+    def lagrange_to_coeff_many(self, cols) -> list:
+        """`cols.iter().map(|c| domain.lagrange_to_coeff(c))`, pipelined over PCIe"""
+        arrs = [_u64(a, 4).copy() for a in cols]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        self.ctx.check(lib.h2b_lagrange_to_coeff_batch(self.ctx.h, ptrs, len(arrs), self.k))
+        return arrs
+
+    def coeff_to_extended_many(self, cols) -> list:
+        arrs = [_u64(a, 4) for a in cols]
+        outs = [np.empty((1 << self.extended_k, 4), dtype=np.uint64) for _ in arrs]
+        pin = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        pout = (C.c_void_p * len(arrs))(*[o.ctypes.data for o in outs])
+        self.ctx.check(lib.h2b_coeff_to_extended_batch(self.ctx.h, pin, len(arrs), self.n, self.extended_k, pout))
+        return outs
+
     def coeff_to_extended(self, a) -> np.ndarray:
         a = _u64(a, 4)
         assert len(a) == self.n

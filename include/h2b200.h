@@ -132,6 +132,14 @@ int h2b_coeff_to_extended_dev(h2b_ctx* ctx, const void* d_coeffs, size_t n_coeff
 int h2b_extended_to_coeff(h2b_ctx* ctx, uint64_t* a, uint32_t ext_k);
 int h2b_extended_to_coeff_dev(h2b_ctx* ctx, void* d_a, uint32_t ext_k);
 
+/* Batched forms (halo2 maps these over all columns of a phase): m transforms pipelined through three device
+ * buffers so that the PCIe upload of column i+1 and the download of column i-1 overlap the kernels of column i.
+ * a[i] / coeffs[i] / out[i] are host pointers (pinned memory makes the copies truly asynchronous). */
+int h2b_lagrange_to_coeff_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k);
+int h2b_coeff_to_lagrange_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k);
+int h2b_coeff_to_extended_batch(h2b_ctx* ctx, const uint64_t* const* coeffs, size_t m, size_t n_coeffs, uint32_t ext_k,
+                                uint64_t* const* out);
+
 /* ---- witness assignment: replaces the per-cell loop of assign_witnesses
  *      (halo2-base/src/gates/flex_gate/threads/single_phase.rs:273-312 -> utils/halo2.rs:20-27) ------ */
 /* vcol = concatenation of ctx.advice over all threads (N x 4 limbs, `Trivial` payloads); break_points =

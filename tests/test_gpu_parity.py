@@ -205,6 +205,18 @@ def test_coset_extended(ctx, h2b, k, j):
     assert np.array_equal(back[:n], A) and not back[n:].any()
 
 
+def test_ntt_batch_pipelined(ctx, h2b):
+    k = 12
+    rng = np.random.default_rng(5150)
+    cols = [mont(rand_ints(rng, 1 << k, R), R) for _ in range(7)]
+    dom = h2b.EvaluationDomain(ctx, 5, k)
+    coeffs = dom.lagrange_to_coeff_many(cols)
+    exts = dom.coeff_to_extended_many(coeffs)
+    for c, co, ex in zip(cols, coeffs, exts):
+        assert np.array_equal(co, orc.lagrange_to_coeff(c, k))
+        assert np.array_equal(ex, orc.coeff_to_extended(co, dom.extended_k))
+
+
 # ------------------------------------------------------------------ L3: KZG identity ties MSM, NTT and SRS layout together
 def test_kzg_commit_identity(ctx, h2b):
     k = 10
