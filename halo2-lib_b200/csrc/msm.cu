@@ -64,11 +64,12 @@ __device__ __forceinline__ void for_each_digit(const Fr& s, int c, int W, F&& f)
     }
 }
 
-// Counter increment with a fast path for warps whose active lanes all hit the SAME counter (constant columns,
-// padding runs): one atomic per warp instead of 32 on one address.  Mixed warps use plain atomics; a hot address
-// then serialises in L2 at about one atomic per clock, which is still far below the accumulation time.
-// All 32 lanes must call; returns the slot of the lane.
-__device__ __forceinline__ u32 warp_agg_add(u32* counters, u32 key, bool active) {
+// Counter increment with two fast paths for hot counters.  (1) all active lanes of the warp hit the SAME counter
+// (constant columns, padding runs): one atomic per warp.  (2) lanes whose digit is tiny (|d| <= 4: bit-valued and
+// small-constant witness cells, the hot buckets of real advice columns) are grouped by __match_any_sync and issue
+// one atomic per distinct counter.  Everything else uses a plain atomic; uniform digits are almost never tiny, so
+// the common case pays nothing for (2).  All 32 lanes must call; returns the slot of the lane.
+__device__ __forceinline__ u32 warp_agg_add(u32* counters, u32 key, bool active, bool tiny) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned mask = __ballot_sync(0xffffffffu, active);
     if (!active) return 0;
@@ -79,6 +80,15 @@ __device__ __forceinline__ u32 warp_agg_add(u32* counters, u32 key, bool active)
         if ((int)lane == leader) base = atomicAdd(counters + key, (u32)__popc(mask));
         base = __shfl_sync(mask, base, leader);
         return base + __popc(mask & ((1u << lane) - 1));
+    }
+    const unsigned tmask = __ballot_sync(mask, tiny);
+    if (tiny) {
+        const unsigned peers = __match_any_sync(tmask, key);
+        const int leader = __ffs(peers) - 1;
+        u32 base = 0;
+        if ((int)lane == leader) base = atomicAdd(counters + key, (u32)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        return base + __popc(peers & ((1u << lane) - 1));
     }
     return atomicAdd(counters + key, 1u);
 }
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint64_t* __restrict__ sca
     for_each_digit(s, c, W, [&](int w, u32 d, bool neg) {
         const bool active = live && d != 0;
         const u32 key = active ? (u32)(w / q) * nbw + (d - 1) : 0;
-        const u32 slot = warp_agg_add(counters, key, active);
+        const u32 slot = warp_agg_add(counters, key, active, d <= 4);
         if (MODE == 1 && active) vals_sorted[slot] = ((u32)(w % q) * n + i) | (neg ? SIGN_BIT : 0u);
     });
 }
@@ -241,39 +251,54 @@ __global__ void __launch_bounds__(128) k_collect(const u32* __restrict__ off, u3
     acc.store(buckets + b);
 }
 
-// block-wide sum of one XYZZ per thread (256 threads); result valid in thread 0
-__device__ __forceinline__ XYZZ block_sum_256(XYZZ v, XYZZ* sh) {
-    const int tid = threadIdx.x;
-    v.store(sh + tid);
-    __syncthreads();
-#pragma unroll 1
-    for (int stride = 128; stride >= 1; stride >>= 1) {
-        if (tid < stride) {
-            XYZZ a = XYZZ::load(sh + tid), b2 = XYZZ::load(sh + tid + stride);
-            xyzz_add(a, b2);
-            a.store(sh + tid);
-        }
-        __syncthreads();
-    }
-    return XYZZ::load(sh);
-}
-
-// hot buckets (e.g. digit 1 of a bit-valued witness column): one CTA per bucket
-__global__ void __launch_bounds__(256) k_collect_big(const u32* __restrict__ off, int L,
-                                                     const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets,
-                                                     const u32* __restrict__ big_list,
-                                                     const u32* __restrict__ big_count) {
-    __shared__ XYZZ sh[256];
+// Hot buckets (e.g. digit 1 of a bit-valued witness column: a quarter of all entries) span thousands of chunks.
+// Stage 1: the partials of every big bucket are cut into segments of 64; one CTA (64 lane-quads) sums a segment.
+// Stage 2: one CTA per big bucket sums its segment sums.  Work lists are walked on the device (counts are only
+// known there); `seg` needs one slot per 64 chunk partials overall.
+static constexpr int BIG_SEG = 64;
+__global__ void __launch_bounds__(256) k_collect_big1(const u32* __restrict__ off, int L, const XYZZ* __restrict__ partials,
+                                                      const u32* __restrict__ big_list, const u32* __restrict__ big_count,
+                                                      XYZZ* __restrict__ seg) {
+    __shared__ XYZZ sh[8];
     const u32 nbig = *big_count;
-    for (u32 j = blockIdx.x; j < nbig; j += gridDim.x) {
+    const u32 qid = threadIdx.x >> 2;
+    u32 seg_base = 0;  // running number of segments of the buckets before j
+    u32 g = blockIdx.x;  // next segment of this CTA (segments are numbered across all big buckets)
+    for (u32 j = 0; j < nbig; j++) {
         const u32 b = big_list[j];
         const u32 s = __ldg(off + b), e = __ldg(off + b + 1);
         const u32 t_lo = s / L, t_hi = (e - 1) / L;
-        XYZZ acc = XYZZ::identity();
-        for (u32 t = t_lo + threadIdx.x; t <= t_hi; t += 256) xyzz_add(acc, XYZZ::load(partial_of(partials, s, t, L)));
-        XYZZ r = block_sum_256(acc, sh);
-        if (threadIdx.x == 0) r.store(buckets + b);
-        __syncthreads();
+        const u32 cnt = t_hi - t_lo + 1, nseg = (cnt + BIG_SEG - 1) / BIG_SEG;
+        for (; g < seg_base + nseg; g += gridDim.x) {
+            const u32 t = t_lo + (g - seg_base) * BIG_SEG + qid;
+            XYZZ v = XYZZ::identity();
+            if (t <= t_hi) v = XYZZ::load(partial_of(partials, s, t, L));
+            v = quad_block_sum(v, sh);
+            if (threadIdx.x == 0) v.store(seg + g);
+            __syncthreads();
+        }
+        seg_base += nseg;
+    }
+}
+__global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ off, int L, const XYZZ* __restrict__ seg,
+                                                      XYZZ* __restrict__ buckets, const u32* __restrict__ big_list,
+                                                      const u32* __restrict__ big_count) {
+    __shared__ XYZZ sh[8];
+    const u32 nbig = *big_count;
+    const u32 qid = threadIdx.x >> 2;
+    u32 seg_base = 0;
+    for (u32 j = 0; j < nbig; j++) {
+        const u32 b = big_list[j];
+        const u32 s = __ldg(off + b), e = __ldg(off + b + 1);
+        const u32 cnt = (e - 1) / L - s / L + 1, nseg = (cnt + BIG_SEG - 1) / BIG_SEG;
+        if (j % gridDim.x == blockIdx.x) {
+            XYZZ acc = XYZZ::identity();
+            for (u32 g = qid; g < nseg; g += 64) quad_add(acc, XYZZ::load(seg + seg_base + g));
+            acc = quad_block_sum(acc, sh);
+            if (threadIdx.x == 0) acc.store(buckets + b);
+            __syncthreads();
+        }
+        seg_base += nseg;
     }
 }
 
@@ -283,41 +308,6 @@ __global__ void __launch_bounds__(256) k_collect_big(const u32* __restrict__ off
 // A running sum over 2^16 buckets is a dependency chain of ~10^5 point additions; this form has depth
 // ~(2^mh / 32 + 5) for the row/column sums (one warp each, shuffle tree), ~2*ml for the small scalar
 // multiplications lo * R_lo / hi * C_hi (one thread each) and ~10 for the block sums and the final doublings.
-__device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
-    XYZZ r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], delta);
-        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], delta);
-        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], delta);
-        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], delta);
-    }
-    return r;
-}
-// sum over the 32 lanes; valid in lane 0
-__device__ __forceinline__ XYZZ warp_sum(XYZZ v) {
-#pragma unroll 1
-    for (int delta = 16; delta >= 1; delta >>= 1) {
-        XYZZ o = shfl_down_xyzz(v, delta);
-        xyzz_add(v, o);
-    }
-    return v;
-}
-// block sum for up to 1024 threads: warp shuffle tree, then the first warp over the per-warp results
-__device__ __forceinline__ XYZZ block_sum(XYZZ v, XYZZ* sh32) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    v = warp_sum(v);
-    __syncthreads();  // sh32 may still be read from a previous call
-    if (lane == 0) v.store(sh32 + wid);
-    __syncthreads();
-    XYZZ r = XYZZ::identity();
-    if (wid == 0) {
-        if (lane < nw) r = XYZZ::load(sh32 + lane);
-        r = warp_sum(r);
-    }
-    return r;  // valid in thread 0
-}
-
 // One CTA of 128 threads (32 lane-quads, quad.cuh) per row sum R_lo / column sum C_hi: every quad adds its
 // stride-32 share of the row (column), then the 32 quads are summed.  rc[set][0 .. 2^ml) = R, rc[set][2^ml ..) = C.
 __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ buckets, int ml, int mh, u32 nsets,
@@ -564,7 +554,9 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     else
         H2B_LAUNCH(ctx, k_accumulate<64>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, (const Affine*)d_table, buckets, partials);
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, ACC_L, partials, buckets, big + 1, big);
-    H2B_LAUNCH(ctx, k_collect_big, 2 * ctx->sm_count, 256, 0, off, ACC_L, partials, buckets, big + 1, big);
+    XYZZ* seg = (XYZZ*)ctx->get(WS_POOL, (2 * (n_chunks / BIG_SEG) + 64) * sizeof(XYZZ));
+    H2B_LAUNCH(ctx, k_collect_big1, 2 * ctx->sm_count, 256, 0, off, ACC_L, partials, big + 1, big, seg);
+    H2B_LAUNCH(ctx, k_collect_big2, 64, 256, 0, off, ACC_L, seg, buckets, big + 1, big);
 
     // bucket reduction: row/column sums of the 2^mh x 2^ml bucket grid, small scalar multiples, final combine
     const int m = c - 1, ml = (m + 1) / 2, mh = m - ml;
