@@ -5,7 +5,7 @@
 // column.  Contract: natural order in, natural order out,
 // out[i] = sum_j a[j] * omega^(i*j).
 //
-// Decomposition: log_n = r_1 + ... + r_p (p <= 3, r_t <= 10).  Pass t transforms digit t of the index
+// Decomposition: log_n = r_1 + ... + r_p (p <= 3, r_t <= 11).  Pass t transforms digit t of the index
 // (decimation in frequency) for a tile of 2^r_t rows x CW adjacent columns held in shared memory (two
 // 128-bit planes per element, conflict-free for unit-stride lanes), multiplies by the inter-pass twiddle
 // omega_t^(i_t * j') taken from a two-level power table of omega, and writes in place; the last pass
@@ -20,7 +20,7 @@ namespace h2b {
 
 static constexpr int NTT_THREADS = 256;
 static constexpr int NTT_TILE_LOG = 11;  // elements per tile (2^11 * 32 B = 64 KB of shared memory)
-static constexpr int NTT_MAX_R = 10;
+static constexpr int NTT_MAX_R = 11;  // one column of the largest digit = 2^11 * 32 B = the whole 64 KB tile
 
 // Fr::ZETA and ZETA^2 in Montgomery form (halo2curves bn256::Fr::ZETA); the same values are
 // emitted as FR_ZETA_U32 by tools/gen_domain_consts.py
@@ -45,7 +45,11 @@ struct NttPlan {
     Fr* tw_hi = nullptr;       // omega^(i << h)
     Fr* wtab[3] = {nullptr, nullptr, nullptr};  // per pass: rho_t^e, e < 2^(r_t - 1), rho_t = omega^(n / 2^r_t)
     Fr* n_inv = nullptr;       // 2^-log_n
+    Fr* tw_full[2] = {nullptr, nullptr};  // per non-last pass: the inter-pass twiddle of every in-place address
+                                          // (times 2^-log_n in the first one when the plan scales)
+    int scaled = 0;
     void* block = nullptr;
+    void* block2 = nullptr;
 };
 
 // out[i] = omega^(i * mult)
@@ -67,6 +71,21 @@ __global__ void k_n_inv(u32 log_n, Fr* out) {
     acc.inv().store(out);
 }
 
+// tw_full[g] = omega_t^(row * j') (times n_inv when given) for every in-place address g of a non-last pass
+__global__ void k_tw_full(const Fr* __restrict__ tw_lo, const Fr* __restrict__ tw_hi, int h, int log_n, int r, int logM,
+                          int tw_shift, const Fr* __restrict__ n_inv, Fr* __restrict__ out) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ((size_t)1 << log_n)) return;
+    u32 jp = (u32)(g & (((size_t)1 << logM) - 1));
+    u32 row = (u32)((g >> logM) & ((1u << r) - 1));
+    uint64_t ex = ((uint64_t)row * jp) << tw_shift;
+    Fr t = Fr::load_nc(tw_lo + (ex & ((1ull << h) - 1)));
+    uint64_t eh = ex >> h;
+    if (eh) t = t * Fr::load_nc(tw_hi + eh);
+    if (n_inv) t = t * Fr::load_nc(n_inv);
+    t.store(out + g);
+}
+
 struct PassArgs {
     const Fr* in;
     Fr* out;
@@ -80,6 +99,7 @@ struct PassArgs {
     int h;
     int tw_shift;    // log2(n / L_t): twiddle exponent = row * j' << tw_shift
     const Fr* n_inv; // non-null: scale by 2^-log_n in the last pass
+    const Fr* tw_full; // non-last passes: precomputed twiddle per in-place address
     int coset;       // 1: in[i] *= zeta^(i mod 3) on load (first pass); 2: out[i] *= zeta^-(i mod 3) on store (last)
 };
 
@@ -176,21 +196,16 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(PassArgs a) {
             }
             v.store(a.out + nat);
         } else {
-            u32 jp = col & ((1u << a.logM) - 1);
-            uint64_t ex = ((uint64_t)row * jp) << a.tw_shift;
-            if (ex) {
-                Fr t = Fr::load_nc(a.tw_lo + (ex & ((1ull << a.h) - 1)));
-                uint64_t eh = ex >> a.h;
-                if (eh) t = t * Fr::load_nc(a.tw_hi + eh);
-                v = v * t;
-            }
-            v.store(a.out + gaddr(row, col));
+            const size_t g = gaddr(row, col);
+            v = v * Fr::load_nc(a.tw_full + g);
+            v.store(a.out + g);
+            continue;
         }
     }
 }
 
-static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4]) {
-    std::array<uint64_t, 5> key = {omega[0], omega[1], omega[2], omega[3], (uint64_t)log_n};
+static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4], int scaled) {
+    std::array<uint64_t, 5> key = {omega[0], omega[1], omega[2], omega[3], (uint64_t)log_n | ((uint64_t)(scaled ? 1 : 0) << 32)};
     auto it = ctx->ntt_plans.find(key);
     if (it != ctx->ntt_plans.end()) return it->second;
     NttPlan* p = new NttPlan();
@@ -225,6 +240,19 @@ static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4]) 
         p->wtab[t] = cur; cur += cnt;
         H2B_LAUNCH(ctx, k_pow_table, ceil_div(cnt, 128), 128, 0, w, (uint64_t)1 << (log_n - p->r[t]), (u32)cnt, p->wtab[t]);
     }
+    p->scaled = scaled ? 1 : 0;
+    if (p->npass > 1) {
+        const size_t n = (size_t)1 << log_n;
+        H2B_CUDA(cudaMalloc(&p->block2, (size_t)(p->npass - 1) * n * sizeof(Fr)));
+        int consumed = 0;
+        for (int t = 0; t < p->npass - 1; t++) {
+            p->tw_full[t] = (Fr*)p->block2 + (size_t)t * n;
+            const int logM = (int)log_n - consumed - p->r[t];
+            H2B_LAUNCH(ctx, k_tw_full, ceil_div(n, 256), 256, 0, p->tw_lo, p->tw_hi, p->h, (int)log_n, p->r[t], logM, consumed,
+                       (t == 0 && scaled) ? p->n_inv : (const Fr*)nullptr, p->tw_full[t]);
+            consumed += p->r[t];
+        }
+    }
     ctx->ntt_plans[key] = p;
     return p;
 }
@@ -232,6 +260,7 @@ static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4]) 
 void ntt_free_plans(h2b_ctx* ctx) {
     for (auto& kv : ctx->ntt_plans) {
         if (kv.second->block) cudaFree(kv.second->block);
+        if (kv.second->block2) cudaFree(kv.second->block2);
         delete kv.second;
     }
     ctx->ntt_plans.clear();
@@ -247,7 +276,7 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
     H2B_REQUIRE(log_n <= 28, "ntt: log_n exceeds the two-adicity of Fr (28)");
     const size_t n = (size_t)1 << log_n;
     H2B_REQUIRE(n_src <= n, "ntt: more input elements than the domain size");
-    NttPlan* p = get_plan(ctx, log_n, omega);
+    NttPlan* p = get_plan(ctx, log_n, omega, inverse_scale);
     static bool attr_set = false;
     if (!attr_set) {
         H2B_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Fr) << NTT_TILE_LOG)));
@@ -279,7 +308,8 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
         a.tw_hi = p->tw_hi;
         a.h = p->h;
         a.tw_shift = consumed;  // n / L_t = 2^consumed
-        a.n_inv = (last && inverse_scale) ? p->n_inv : nullptr;
+        a.n_inv = (last && inverse_scale && p->npass == 1) ? p->n_inv : nullptr;  // multi-pass: folded into tw_full[0]
+        a.tw_full = last ? nullptr : p->tw_full[t];
         a.coset = coset_mode;
         const unsigned grid = 1u << (cols_log - a.cw_log);
         const size_t smem = sizeof(Fr) << (a.r + a.cw_log);
