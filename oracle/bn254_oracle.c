@@ -365,6 +365,78 @@ void orc_ntt(u64 *a, unsigned log_n, const u64 *omega, int threads) {
     }
     free(tw);
 }
+/* serial in-place radix-2 transform with a caller-provided twiddle table tw[i] = root^i, i < n/2 */
+static void ntt_serial(u64 *a, unsigned log_n, const u64 *tw) {
+    const field_t *f = &FR;
+    size_t n = (size_t)1 << log_n;
+    for (size_t i = 0; i < n; i++) {
+        size_t j = bitrev((unsigned)i, log_n);
+        if (i < j) { u64 t[4]; memcpy(t, a + 4 * i, 32); memcpy(a + 4 * i, a + 4 * j, 32); memcpy(a + 4 * j, t, 32); }
+    }
+    for (unsigned s = 0; s < log_n; s++) {
+        size_t half = (size_t)1 << s, step = n / (2 * half);
+        for (size_t grp = 0; grp < n; grp += 2 * half)
+            for (size_t j = 0; j < half; j++) {
+                u64 *u = a + 4 * (grp + j), *v = u + 4 * half, t[4], x[4];
+                f_mul(f, t, v, tw + 4 * (j * step));
+                f_sub(f, x, u, t);
+                f_add(f, u, u, t);
+                memcpy(v, x, 32);
+            }
+    }
+}
+/* Same contract as orc_ntt, organised for many cores the way a tuned CPU prover would (halo2's best_fft splits the
+ * transform into per-thread sub-transforms): n = N1*N2, column transforms + twiddles, row transforms, transpose.
+ * Every thread works on whole cache-resident sub-transforms; 3 parallel regions instead of one per butterfly stage.
+ * Used for the timed CPU baseline; checked against orc_ntt in tests/test_oracle_kat.py. */
+void orc_ntt_fast(u64 *a, unsigned log_n, const u64 *omega, int threads) {
+    const field_t *f = &FR;
+    if (log_n < 10 || threads <= 1) { orc_ntt(a, log_n, omega, threads); return; }
+    unsigned l1 = log_n / 2, l2 = log_n - l1;
+    size_t N1 = (size_t)1 << l1, N2 = (size_t)1 << l2, n = N1 * N2;
+    /* roots: w1 = omega^N2 (order N1), w2 = omega^N1 (order N2) and their half tables */
+    u64 w1[4], w2[4];
+    memcpy(w1, omega, 32); for (unsigned i = 0; i < l2; i++) f_sqr(f, w1, w1);
+    memcpy(w2, omega, 32); for (unsigned i = 0; i < l1; i++) f_sqr(f, w2, w2);
+    u64 *tw1 = (u64 *)malloc((N1 / 2 ? N1 / 2 : 1) * 32), *tw2 = (u64 *)malloc((N2 / 2 ? N2 / 2 : 1) * 32);
+    memcpy(tw1, f->one, 32); for (size_t i = 1; i < N1 / 2; i++) f_mul(f, tw1 + 4 * i, tw1 + 4 * (i - 1), w1);
+    memcpy(tw2, f->one, 32); for (size_t i = 1; i < N2 / 2; i++) f_mul(f, tw2 + 4 * i, tw2 + 4 * (i - 1), w2);
+    u64 *buf = (u64 *)malloc(n * 32);
+#pragma omp parallel num_threads(threads)
+    {
+        u64 *col = (u64 *)malloc(N1 * 32);
+        /* step 1+2: for each column j2: N1-point transform over j1 (stride N2), times omega^(j2*i1) */
+#pragma omp for schedule(static)
+        for (size_t j2 = 0; j2 < N2; j2++) {
+            for (size_t j1 = 0; j1 < N1; j1++) memcpy(col + 4 * j1, a + 4 * (j1 * N2 + j2), 32);
+            ntt_serial(col, l1, tw1);
+            u64 g[4], t[4];
+            /* g = omega^j2 */
+            memcpy(g, f->one, 32);
+            { u64 base[4]; memcpy(base, omega, 32); size_t e = j2; while (e) { if (e & 1) f_mul(f, g, g, base); f_sqr(f, base, base); e >>= 1; } }
+            memcpy(t, f->one, 32);
+            for (size_t i1 = 0; i1 < N1; i1++) {
+                f_mul(f, a + 4 * (i1 * N2 + j2), col + 4 * i1, t);
+                f_mul(f, t, t, g);
+            }
+        }
+        /* step 3: rows i1: N2-point transform over j2 (contiguous) */
+#pragma omp for schedule(static)
+        for (size_t i1 = 0; i1 < N1; i1++) ntt_serial(a + 4 * i1 * N2, l2, tw2);
+        /* step 4: out[i1 + N1*i2] = C[i1][i2] */
+#pragma omp for schedule(static)
+        for (size_t i2 = 0; i2 < N2; i2++)
+            for (size_t i1 = 0; i1 < N1; i1++) memcpy(buf + 4 * (i1 + N1 * i2), a + 4 * (i1 * N2 + i2), 32);
+        free(col);
+    }
+    memcpy(a, buf, n * 32);
+    free(buf); free(tw1); free(tw2);
+}
+static int g_fast_ntt = 0; /* orc_use_fast_ntt(1): EvaluationDomain wrappers below go through orc_ntt_fast */
+void orc_use_fast_ntt(int on) { g_fast_ntt = on; }
+static void ntt_dispatch(u64 *a, unsigned log_n, const u64 *omega, int threads) {
+    if (g_fast_ntt) orc_ntt_fast(a, log_n, omega, threads); else orc_ntt(a, log_n, omega, threads);
+}
 static void fr_from_u64(u64 r[4], u64 v) { u64 t[4] = {v, 0, 0, 0}; f_to_mont(&FR, r, t); }
 /* omega of the 2^k domain: ROOT_OF_UNITY^(2^(28-k)); ROOT_OF_UNITY = 7^((r-1)/2^28). */
 void orc_omega(unsigned k, u64 *out) {
@@ -386,7 +458,7 @@ static void zeta_mont(u64 z[4]) { /* Fr::ZETA = (7^((r-1)/3))^2 ; SURVEY.md §8c
 void orc_lagrange_to_coeff(u64 *a, unsigned k, int threads) {
     u64 w[4], wi[4], n[4], ni[4];
     orc_omega(k, w); f_inv(&FR, wi, w);
-    orc_ntt(a, k, wi, threads);
+    ntt_dispatch(a, k, wi, threads);
     fr_from_u64(n, (u64)1 << k); f_inv(&FR, ni, n);
     size_t N = (size_t)1 << k;
 #pragma omp parallel for num_threads(threads) if (N >= 4096)
@@ -394,7 +466,7 @@ void orc_lagrange_to_coeff(u64 *a, unsigned k, int threads) {
 }
 /* EvaluationDomain::coeff_to_lagrange == best_fft(omega) */
 void orc_coeff_to_lagrange(u64 *a, unsigned k, int threads) {
-    u64 w[4]; orc_omega(k, w); orc_ntt(a, k, w, threads);
+    u64 w[4]; orc_omega(k, w); ntt_dispatch(a, k, w, threads);
 }
 /* EvaluationDomain::coeff_to_extended: a[i] *= zeta^(i mod 3); zero-pad to 2^ext_k; best_fft(extended_omega) */
 void orc_coeff_to_extended(const u64 *coeffs, size_t n_coeffs, unsigned ext_k, u64 *out, int threads) {
@@ -402,8 +474,9 @@ void orc_coeff_to_extended(const u64 *coeffs, size_t n_coeffs, unsigned ext_k, u
     memcpy(z[0], FR.one, 32); zeta_mont(z[1]); f_sqr(&FR, z[2], z[1]);
     size_t N = (size_t)1 << ext_k;
     memset(out, 0, N * 32);
+#pragma omp parallel for num_threads(threads) if (n_coeffs >= 4096)
     for (size_t i = 0; i < n_coeffs; i++) f_mul(&FR, out + 4 * i, coeffs + 4 * i, z[i % 3]);
-    orc_omega(ext_k, w); orc_ntt(out, ext_k, w, threads);
+    orc_omega(ext_k, w); ntt_dispatch(out, ext_k, w, threads);
 }
 /* EvaluationDomain::extended_to_coeff: best_fft(extended_omega^-1), scale 2^-ext_k, a[i] *= zeta^-(i mod 3);
  * caller truncates to n*(d-1). In place on 2^ext_k elements. */
@@ -412,6 +485,7 @@ void orc_extended_to_coeff(u64 *a, unsigned ext_k, int threads) {
     orc_lagrange_to_coeff(a, ext_k, threads);
     memcpy(z[0], FR.one, 32); zeta_mont(z[2]); f_sqr(&FR, z[1], z[2]); /* z[1]=zeta^-1=zeta^2, z[2]=zeta^-2=zeta */
     size_t N = (size_t)1 << ext_k;
+#pragma omp parallel for num_threads(threads) if (N >= 4096)
     for (size_t i = 0; i < N; i++) f_mul(&FR, a + 4 * i, a + 4 * i, z[i % 3]);
 }
 

@@ -136,6 +136,19 @@ def ntt(a, log_n: int, omega_m, threads: int | None = None):
     return a
 
 
+def ntt_fast(a, log_n: int, omega_m, threads: int | None = None):
+    a = np.array(a, dtype=np.uint64).reshape(-1, 4).copy()
+    assert len(a) == 1 << log_n
+    w = np.ascontiguousarray(omega_m, dtype=np.uint64).reshape(4)
+    lib().orc_ntt_fast(_p(a), C.c_uint(log_n), _p(w), C.c_int(threads or max_threads()))
+    return a
+
+
+def use_fast_ntt(on: bool) -> None:
+    """route the EvaluationDomain wrappers through the many-core four-step transform (timed CPU baseline)"""
+    lib().orc_use_fast_ntt(C.c_int(1 if on else 0))
+
+
 def lagrange_to_coeff(a, k, threads=None):
     a = np.array(a, dtype=np.uint64).reshape(-1, 4).copy()
     assert len(a) == 1 << k

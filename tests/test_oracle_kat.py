@@ -100,6 +100,25 @@ def test_ntt_vs_dft(k):
     assert unmont(orc.lagrange_to_coeff(mont(want, R), k), R) == a
 
 
+@pytest.mark.parametrize("k", [10, 13, 15])
+def test_fast_cpu_ntt_equals_radix2(k):
+    rng = np.random.default_rng(50 + k)
+    A = mont(rand_ints(rng, 1 << k, R), R) if k <= 10 else None
+    if A is None:
+        A = rng.integers(0, 1 << 62, size=(1 << k, 4), dtype=np.int64).astype(np.uint64)
+        A[:, 3] &= np.uint64((1 << 60) - 1)
+    w = orc.omega(k)
+    assert np.array_equal(orc.ntt_fast(A, k, w, 4), orc.ntt(A, k, w, 4))
+    orc.use_fast_ntt(True)
+    try:
+        co = orc.lagrange_to_coeff(A, k, 4)
+        ext = orc.coeff_to_extended(co, k + 2, 4)
+    finally:
+        orc.use_fast_ntt(False)
+    assert np.array_equal(co, orc.lagrange_to_coeff(A, k, 4))
+    assert np.array_equal(ext, orc.coeff_to_extended(co, k + 2, 4))
+
+
 def test_coset_extended_round_trip_and_definition():
     rng = np.random.default_rng(20)
     k, ext_k = 4, 6
