@@ -389,6 +389,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    params_windows = (255 + (k - 2) - 1) // (k - 2) if world == 1 else (255 + max(8, k - 2 - (world.bit_length() - 1)) - 1) // max(8, k - 2 - (world.bit_length() - 1))
     ms_step, launches = timed(step_resident, args.steps, args.warmup, prof="k_accumulate")
     acc_ms, acc_cnt = ctx.profile_read("k_accumulate")
     clocks = sampler.stop() if rank == 0 else None
@@ -423,10 +424,18 @@ def run_b200(args):
     peak, peak_src = measured_hbm_peak()
     acc_avg_ms = acc_ms / max(acc_cnt, 1)
     achieved = 96.0 * n_loc / (acc_avg_ms / 1e3) / 1e9  # algorithmic 96 B per pair (32 B scalar + 64 B base), SURVEY.md §8d
+    # field products of the average launch: entries ~= pairs * windows * P(digit != 0); 9 uniform + 3 witness-like columns
+    entries = n_loc * params_windows * (sum(1.0 if c == "uniform" else 0.34 for _, c in MSM_SCHEDULE) / len(MSM_SCHEDULE))
+    products = 10.0 * entries
     roofline = {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch on a uniform column at k=19, single GPU, from the
+                # `ncu --set full` capture summarised in profiles/r01_k_accumulate_final_ncu_full.csv (976.2 + 37.3 MB)
+                "traffic": 1013457920 if (k == 19 and world == 1) else None, "peak_source": peak_src, "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt,
                 "algorithmic_bytes_per_launch": 96 * n_loc,
-                "note": "bucket accumulation is integer-issue-bound (254-bit Montgomery on the IMAD pipe), not HBM-bound: see DESIGN.md"}
+                "integer_multiplier": {"products_per_s": products / (acc_avg_ms / 1e3), "peak_products_per_s": 66.9e9,
+                                       "frac": products / (acc_avg_ms / 1e3) / 66.9e9,
+                                       "note": "10 Montgomery products per XYZZ mixed add; peak = tools/latbench.cu (profiles/r01_pipe_microbench.txt)"},
+                "note": "bucket accumulation is bound by the integer multiplier (IMAD.WIDE), not by HBM: traffic is ~10% of HBM peak; see DESIGN.md 4.1/4.2"}
     h2d = (len(MSM_SCHEDULE) * n_loc * 32 + (N_INTT * n * 32 + N_COSET * n * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n_cells * 32)
     d2h = (len(MSM_SCHEDULE) * 96 + (N_INTT * n * 32 + N_COSET * (1 << ext_k) * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n * 32)
     cpu = cpu_sample(k) if world == 1 and not args.no_cpu else None
