@@ -424,8 +424,9 @@ def run_b200(args):
     peak, peak_src = measured_hbm_peak()
     acc_avg_ms = acc_ms / max(acc_cnt, 1)
     achieved = 96.0 * n_loc / (acc_avg_ms / 1e3) / 1e9  # algorithmic 96 B per pair (32 B scalar + 64 B base), SURVEY.md §8d
-    # field products of the average launch: entries ~= pairs * windows * P(digit != 0); 9 uniform + 3 witness-like columns
-    entries = n_loc * params_windows * (sum(1.0 if c == "uniform" else 0.34 for _, c in MSM_SCHEDULE) / len(MSM_SCHEDULE))
+    # field products of the average launch (estimate): entries = pairs * windows * P(non-zero digit); witness-like columns
+    # keep ~23% of their digits (35% zeros, 25% ones, 30% 88-bit limbs, 10% full width)
+    entries = n_loc * params_windows * (sum(1.0 if c == "uniform" else 0.23 for _, c in MSM_SCHEDULE) / len(MSM_SCHEDULE))
     products = 10.0 * entries
     roofline = {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch on a uniform column at k=19, single GPU, from the
