@@ -568,7 +568,7 @@ int h2b_assign_lookups(h2b_ctx* ctx, const uint64_t* vals, size_t N, uint32_t k,
 int h2b_eval_rational_dev(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out) {
     return guarded(ctx, [&] {
         H2B_REQUIRE((d_num && d_den && d_out) || n == 0, "eval_rational: null pointer");
-        eval_rational_run(ctx, d_num, d_den, n, d_out);
+        eval_rational_batched_run(ctx, d_num, d_den, n, d_out);
     });
 }
 int h2b_eval_rational(h2b_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out) {
@@ -578,8 +578,44 @@ int h2b_eval_rational(h2b_ctx* ctx, const uint64_t* num, const uint64_t* den, si
         char* d = (char*)ctx->get(WS_ASSIGN_IN, 3 * n * 32);
         H2B_CUDA(cudaMemcpyAsync(d, num, n * 32, cudaMemcpyHostToDevice, ctx->stream));
         H2B_CUDA(cudaMemcpyAsync(d + n * 32, den, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-        eval_rational_run(ctx, d, d + n * 32, n, d + 2 * n * 32);
+        eval_rational_batched_run(ctx, d, d + n * 32, n, d + 2 * n * 32);
         H2B_CUDA(cudaMemcpyAsync(out, d + 2 * n * 32, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ grand products
+int h2b_batch_invert_fr_dev(h2b_ctx* ctx, void* d_a, size_t n) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_a || n == 0, "batch_invert: null pointer");
+        batch_invert_run(ctx, d_a, n);
+    });
+}
+int h2b_batch_invert_fr(h2b_ctx* ctx, uint64_t* a, size_t n) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(a || n == 0, "batch_invert: null pointer");
+        if (n == 0) return;
+        void* d = ctx->get(WS_ASSIGN_IN, n * 32);
+        H2B_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        batch_invert_run(ctx, d, n);
+        H2B_CUDA(cudaMemcpyAsync(a, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_grand_product_fr_dev(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(((d_f && d_z) || n == 0) && start, "grand_product: null pointer");
+        grand_product_run(ctx, d_f, start, n, d_z);
+    });
+}
+int h2b_grand_product_fr(h2b_ctx* ctx, const uint64_t* f, const uint64_t start[4], size_t n, uint64_t* z) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(((f && z) || n == 0) && start, "grand_product: null pointer");
+        if (n == 0) return;
+        char* d = (char*)ctx->get(WS_ASSIGN_IN, 2 * n * 32);
+        H2B_CUDA(cudaMemcpyAsync(d, f, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        grand_product_run(ctx, d, start, n, d + n * 32);
+        H2B_CUDA(cudaMemcpyAsync(z, d + n * 32, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }

@@ -170,5 +170,9 @@ void assign_columns_run(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64
                         uint32_t k, size_t ncols, void* d_cols);
 void assign_lookups_run(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols);
 void eval_rational_run(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
+// ---- scan.cu
+void batch_invert_run(h2b_ctx* ctx, void* d_a, size_t n);
+void grand_product_run(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z);
+void eval_rational_batched_run(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
 
 }  // namespace h2b

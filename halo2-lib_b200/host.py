@@ -114,6 +114,20 @@ class Context:
         self.check(lib.h2b_test_field_op(self.h, field, op, _ptr(a), _ptr(bb), len(a), _ptr(out)))
         return out
 
+    def batch_invert(self, a) -> np.ndarray:
+        """ff `BatchInvert::batch_invert` (zeros stay zero); returns the inverted copy"""
+        a = _u64(a, 4).copy()
+        self.check(lib.h2b_batch_invert_fr(self.h, _ptr(a), len(a)))
+        return a
+
+    def grand_product(self, f, start) -> np.ndarray:
+        """z[0] = start, z[i] = z[i-1] * f[i-1] (halo2 permutation / lookup product column)"""
+        f = _u64(f, 4)
+        st = _u64(start, 4)
+        z = np.empty_like(f)
+        self.check(lib.h2b_grand_product_fr(self.h, _ptr(f), _ptr(st), len(f), _ptr(z)))
+        return z
+
     def eval_rational(self, num, den) -> np.ndarray:
         a, b = _u64(num, 4), _u64(den, 4)
         out = np.empty_like(a)

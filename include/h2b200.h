@@ -159,6 +159,15 @@ int h2b_assign_lookups_dev(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t 
 int h2b_eval_rational(h2b_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out);
 int h2b_eval_rational_dev(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
 
+/* ---- grand-product primitives (permutation / lookup arguments of create_proof, §3.3 step 4) */
+/* ff 0.13 `BatchInvert::batch_invert`: a[i] <- a[i]^-1 in place, zeros stay zero. */
+int h2b_batch_invert_fr(h2b_ctx* ctx, uint64_t* a, size_t n);
+int h2b_batch_invert_fr_dev(h2b_ctx* ctx, void* d_a, size_t n);
+/* The product column of halo2's permutation / lookup provers: z[0] = start, z[i] = z[i-1] * f[i-1] for i < n
+ * (`z.push(z[row - 1] * modified_values[row - 1])`; f[n-1] is not used).  f and z hold n elements. */
+int h2b_grand_product_fr(h2b_ctx* ctx, const uint64_t* f, const uint64_t start[4], size_t n, uint64_t* z);
+int h2b_grand_product_fr_dev(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z);
+
 /* ---- test hooks (field arithmetic of the kernels, element-wise on the device) --------------------- */
 /* field: 0 = Fq, 1 = Fr; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 from_mont(a), 5 to_mont(a) */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);

@@ -532,6 +532,32 @@ void orc_eval_rational(const u64 *num, const u64 *den, size_t n, u64 *out) {
         u64 di[4]; f_inv(&FR, di, den + 4 * i); f_mul(&FR, out + 4 * i, num + 4 * i, di);
     }
 }
+/* ff 0.13 BatchInvert::batch_invert semantics on a slice: a[i] <- a[i]^-1, zeros skipped (stay zero);
+ * Montgomery's trick exactly as the trait does it (prefix products, one inversion, backward pass). */
+void orc_batch_invert(u64 *a, size_t n) {
+    u64 *tmp = (u64 *)malloc((n ? n : 1) * 32), acc[4];
+    memcpy(acc, FR.one, 32);
+    for (size_t i = 0; i < n; i++) {
+        memcpy(tmp + 4 * i, acc, 32);
+        if (!f_is_zero(a + 4 * i)) f_mul(&FR, acc, acc, a + 4 * i);
+    }
+    f_inv(&FR, acc, acc);
+    for (size_t i = n; i-- > 0;) {
+        if (f_is_zero(a + 4 * i)) continue;
+        u64 t[4];
+        f_mul(&FR, t, acc, tmp + 4 * i);
+        f_mul(&FR, acc, acc, a + 4 * i);
+        memcpy(a + 4 * i, t, 32);
+    }
+    free(tmp);
+}
+/* halo2 permutation / lookup product column (plonk/permutation/prover.rs, plonk/lookup/prover.rs):
+ * z[0] = start; z[row] = z[row-1] * f[row-1] for row in 1..n. */
+void orc_grand_product(const u64 *f, const u64 *start, size_t n, u64 *z) {
+    if (n == 0) return;
+    memcpy(z, start, 32);
+    for (size_t row = 1; row < n; row++) f_mul(&FR, z + 4 * row, z + 4 * (row - 1), f + 4 * (row - 1));
+}
 void orc_set_threads(int n) {
 #ifdef _OPENMP
     if (n > 0) omp_set_num_threads(n);

@@ -193,6 +193,20 @@ def assign_lookups(vals, k, L):
     return rc, cols
 
 
+def batch_invert(a):
+    a = np.array(a, dtype=np.uint64).reshape(-1, 4).copy()
+    lib().orc_batch_invert(_p(a), C.c_size_t(len(a)))
+    return a
+
+
+def grand_product(f, start):
+    f = np.ascontiguousarray(f, dtype=np.uint64).reshape(-1, 4)
+    st = np.ascontiguousarray(start, dtype=np.uint64).reshape(4)
+    z = np.empty_like(f)
+    lib().orc_grand_product(_p(f), _p(st), C.c_size_t(len(f)), _p(z))
+    return z
+
+
 def eval_rational(num, den):
     a = np.ascontiguousarray(num, dtype=np.uint64).reshape(-1, 4)
     b = np.ascontiguousarray(den, dtype=np.uint64).reshape(-1, 4)

@@ -292,6 +292,22 @@ def test_assign_lookups_and_rational(ctx, h2b):
     assert np.array_equal(ctx.eval_rational(num, den), orc.eval_rational(num, den))
 
 
+@pytest.mark.parametrize("n", [1, 5, 2048, 2049, 70001, 1 << 18])
+def test_batch_invert_and_grand_product(ctx, h2b, n):
+    """the primitives of the permutation / lookup grand products"""
+    rng = np.random.default_rng(900 + n % 97)
+    A = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    A[:, 3] &= np.uint64((1 << 60) - 1)
+    A[::7] = 0  # zeros are skipped by BatchInvert::batch_invert
+    inv = ctx.batch_invert(A)
+    assert np.array_equal(inv, orc.batch_invert(A))
+    assert np.array_equal(orc.f_mul(orc.FR, inv[1:2], A[1:2]), mont([1], R)) if n > 1 else True
+    F = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    F[:, 3] &= np.uint64((1 << 60) - 1)
+    start = mont([3], R)[0]
+    assert np.array_equal(ctx.grand_product(F, start), orc.grand_product(F, start))
+
+
 def test_errors_do_not_cross_the_abi(ctx, h2b):
     with pytest.raises(h2b.H2BError):
         h2b.best_fft(ctx, np.zeros((1, 4), dtype=np.uint64), h2b.omega(0), 0) if False else ctx.check(

@@ -176,3 +176,19 @@ def test_assign_lookups_vs_python():
     assert rc == 0
     for c in range(3):
         assert limbs_to_ints(cols[c]) == want[c]
+
+
+def test_batch_invert_and_grand_product_vs_python():
+    rng = np.random.default_rng(60)
+    a = [0, 1, R - 1] + rand_ints(rng, 97, R)
+    a[50] = 0
+    inv = orc.batch_invert(mont(a, R))
+    assert unmont(inv, R) == [pow(x, -1, R) if x else 0 for x in a]
+    f = rand_ints(rng, 40, R)
+    start = 7
+    z = unmont(orc.grand_product(mont(f, R), mont([start], R)[0]), R)
+    want, cur = [], start
+    for i in range(40):
+        want.append(cur)
+        cur = cur * f[i] % R
+    assert z == want
