@@ -67,6 +67,8 @@ SIGNATURES = {
     "h2b_batch_invert_fr_dev": (_int, [_vp, _vp, _sz]),
     "h2b_grand_product_fr": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "h2b_grand_product_fr_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_flex_gate_fold": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "h2b_flex_gate_fold_dev": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "h2b_test_field_op": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp]),
 }
 

@@ -620,6 +620,29 @@ int h2b_grand_product_fr(h2b_ctx* ctx, const uint64_t* f, const uint64_t start[4
     });
 }
 
+int h2b_flex_gate_fold_dev(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k, uint32_t ext_k,
+                           void* d_acc) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_q_ext && d_a_ext && y && d_acc, "flex_gate: null pointer");
+        flex_gate_fold_run(ctx, d_q_ext, d_a_ext, y, k, ext_k, d_acc);
+    });
+}
+int h2b_flex_gate_fold(h2b_ctx* ctx, const uint64_t* q_ext, const uint64_t* a_ext, const uint64_t y[4], uint32_t k, uint32_t ext_k,
+                       uint64_t* acc) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(q_ext && a_ext && y && acc, "flex_gate: null pointer");
+        H2B_REQUIRE(ext_k >= k && ext_k <= 28, "flex_gate: extended_k out of range");
+        const size_t bytes = ((size_t)1 << ext_k) * 32;
+        char* d = (char*)ctx->get(WS_NTT_A, 3 * bytes);
+        H2B_CUDA(cudaMemcpyAsync(d, q_ext, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        H2B_CUDA(cudaMemcpyAsync(d + bytes, a_ext, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        H2B_CUDA(cudaMemcpyAsync(d + 2 * bytes, acc, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        flex_gate_fold_run(ctx, d, d + bytes, y, k, ext_k, d + 2 * bytes);
+        H2B_CUDA(cudaMemcpyAsync(acc, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
 // ------------------------------------------------------------------------------------------------ test hook
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
     return guarded(ctx, [&] {

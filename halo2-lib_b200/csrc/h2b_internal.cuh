@@ -170,6 +170,9 @@ void assign_columns_run(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64
                         uint32_t k, size_t ncols, void* d_cols);
 void assign_lookups_run(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols);
 void eval_rational_run(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
+// ---- quotient.cu
+void flex_gate_fold_run(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k, uint32_t ext_k,
+                        void* d_acc);
 // ---- scan.cu
 void batch_invert_run(h2b_ctx* ctx, void* d_a, size_t n);
 void grand_product_run(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z);

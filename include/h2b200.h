@@ -168,6 +168,15 @@ int h2b_batch_invert_fr_dev(h2b_ctx* ctx, void* d_a, size_t n);
 int h2b_grand_product_fr(h2b_ctx* ctx, const uint64_t* f, const uint64_t start[4], size_t n, uint64_t* z);
 int h2b_grand_product_fr_dev(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z);
 
+/* ---- quotient evaluation, first slice: the custom-gate term of halo2-base's vertical gate
+ * `q * (a + b*c - out)` (halo2-base/src/gates/flex_gate/mod.rs:80-91) on the extended coset domain, folded as the
+ * prover folds gate terms: acc[i] <- acc[i] * y + q[i] * (a[i] + a[i+s] * a[i+2s] - a[i+3s]), s = 2^(ext_k - k),
+ * indices mod 2^ext_k.  q_ext, a_ext, acc: 2^ext_k elements (coeff_to_extended outputs). */
+int h2b_flex_gate_fold(h2b_ctx* ctx, const uint64_t* q_ext, const uint64_t* a_ext, const uint64_t y[4], uint32_t k,
+                       uint32_t ext_k, uint64_t* acc);
+int h2b_flex_gate_fold_dev(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k,
+                           uint32_t ext_k, void* d_acc);
+
 /* ---- test hooks (field arithmetic of the kernels, element-wise on the device) --------------------- */
 /* field: 0 = Fq, 1 = Fr; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 from_mont(a), 5 to_mont(a) */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);

@@ -558,6 +558,21 @@ void orc_grand_product(const u64 *f, const u64 *start, size_t n, u64 *z) {
     memcpy(z, start, 32);
     for (size_t row = 1; row < n; row++) f_mul(&FR, z + 4 * row, z + 4 * (row - 1), f + 4 * (row - 1));
 }
+/* Custom-gate term of halo2-base's vertical gate q*(a + b*c - out), rotations 0..3 of ONE advice column
+ * (halo2-base/src/gates/flex_gate/mod.rs:80-91), on the extended domain, folded like halo2's evaluate_h folds gate
+ * terms (`value = value * y + gate`): rotation by r rows = index + r * 2^(ext_k - k) mod 2^ext_k. */
+void orc_flex_gate_fold(const u64 *q, const u64 *a, const u64 *y, unsigned k, unsigned ext_k, u64 *acc) {
+    size_t n = (size_t)1 << ext_k, s = (size_t)1 << (ext_k - k), mask = n - 1;
+    for (size_t i = 0; i < n; i++) {
+        u64 t[4], g[4];
+        f_mul(&FR, t, a + 4 * ((i + s) & mask), a + 4 * ((i + 2 * s) & mask));
+        f_add(&FR, t, t, a + 4 * i);
+        f_sub(&FR, t, t, a + 4 * ((i + 3 * s) & mask));
+        f_mul(&FR, g, q + 4 * i, t);
+        f_mul(&FR, t, acc + 4 * i, y);
+        f_add(&FR, acc + 4 * i, t, g);
+    }
+}
 void orc_set_threads(int n) {
 #ifdef _OPENMP
     if (n > 0) omp_set_num_threads(n);

@@ -207,6 +207,15 @@ def grand_product(f, start):
     return z
 
 
+def flex_gate_fold(q, a, y, k, ext_k, acc):
+    q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 4)
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    acc = np.array(acc, dtype=np.uint64).reshape(-1, 4).copy()
+    yy = np.ascontiguousarray(y, dtype=np.uint64).reshape(4)
+    lib().orc_flex_gate_fold(_p(q), _p(a), _p(yy), C.c_uint(k), C.c_uint(ext_k), _p(acc))
+    return acc
+
+
 def eval_rational(num, den):
     a = np.ascontiguousarray(num, dtype=np.uint64).reshape(-1, 4)
     b = np.ascontiguousarray(den, dtype=np.uint64).reshape(-1, 4)

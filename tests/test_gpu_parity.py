@@ -308,6 +308,48 @@ def test_batch_invert_and_grand_product(ctx, h2b, n):
     assert np.array_equal(ctx.grand_product(F, start), orc.grand_product(F, start))
 
 
+def test_flex_gate_fold_and_vanishing(ctx, h2b):
+    """SURVEY.md §8(f) rank 1, first slice.  (1) parity with the oracle on random data.  (2) end-to-end meaning: for a
+    witness column that satisfies q*(a + b*c - out) on every row of the 2^k domain, the folded term evaluated on the
+    extended coset is divisible by the vanishing polynomial X^n - 1; a broken witness is not."""
+    rng = np.random.default_rng(62)
+    k, j = 8, 5
+    dom = h2b.EvaluationDomain(ctx, j, k)
+    n, ek = 1 << k, dom.extended_k
+    ne = 1 << ek
+
+    def rnd(m):
+        x = rng.integers(0, 1 << 62, size=(m, 4), dtype=np.int64).astype(np.uint64)
+        x[:, 3] &= np.uint64((1 << 60) - 1)
+        return x
+    Q, A, ACC, y = rnd(ne), rnd(ne), rnd(ne), rnd(1)[0]
+    assert np.array_equal(ctx.flex_gate_fold(Q, A, y, k, ek, ACC), orc.flex_gate_fold(Q, A, y, k, ek, ACC))
+    # satisfied witness: gates at rows 0, 4, 8, ... (out = a + b*c), selector 1 there
+    vals = rand_ints(rng, n, R)
+    sel = [0] * n
+    for r in range(0, n - 4, 4):
+        vals[r + 3] = (vals[r] + vals[r + 1] * vals[r + 2]) % R
+        sel[r] = 1
+    q_ext = dom.coeff_to_extended(dom.lagrange_to_coeff(mont(sel, R)))
+    zero = np.zeros((ne, 4), dtype=np.uint64)
+    # 1 / t(X), t = X^n - 1, on the coset zeta*<w_ext>: t(zeta w^i) = zeta^n w^(n i) - 1 has period 2^(ek - k)
+    we, zeta, per = pyref.omega_for(ek), pyref.ZETA, ne >> k
+    tinv = [pow((pow(zeta, n, R) * pow(we, n * i, R) - 1) % R, -1, R) for i in range(per)]
+    TI = mont([tinv[i % per] for i in range(ne)], R)
+
+    def quotient_coeffs(values):
+        a_ext = dom.coeff_to_extended(dom.lagrange_to_coeff(mont(values, R)))
+        term = ctx.flex_gate_fold(q_ext, a_ext, y, k, ek, zero)
+        full = h2b.EvaluationDomain(ctx, j, k)
+        full.quotient_poly_degree = ne >> k  # keep all 2^ek coefficients
+        return unmont(full.extended_to_coeff(orc.f_mul(orc.FR, term, TI)), R)
+    hc = quotient_coeffs(vals)
+    # deg(q * a * a) <= 3(n-1): exact division leaves deg(h) <= 2n - 3, everything above must be zero
+    assert any(hc[: 2 * n]) and not any(hc[2 * n:])
+    vals[3] = (vals[3] + 1) % R  # break one gate: no longer divisible, the high coefficients are non-zero
+    assert any(quotient_coeffs(vals)[2 * n:])
+
+
 def test_errors_do_not_cross_the_abi(ctx, h2b):
     with pytest.raises(h2b.H2BError):
         h2b.best_fft(ctx, np.zeros((1, 4), dtype=np.uint64), h2b.omega(0), 0) if False else ctx.check(

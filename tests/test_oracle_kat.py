@@ -192,3 +192,13 @@ def test_batch_invert_and_grand_product_vs_python():
         want.append(cur)
         cur = cur * f[i] % R
     assert z == want
+
+
+def test_flex_gate_fold_vs_python():
+    rng = np.random.default_rng(61)
+    k, ext_k = 3, 5
+    ne, s = 1 << ext_k, 1 << (ext_k - k)
+    q = rand_ints(rng, ne, R); a = rand_ints(rng, ne, R); acc = rand_ints(rng, ne, R); y = rand_ints(rng, 1, R)[0]
+    got = unmont(orc.flex_gate_fold(mont(q, R), mont(a, R), mont([y], R)[0], k, ext_k, mont(acc, R)), R)
+    want = [(acc[i] * y + q[i] * (a[i] + a[(i + s) % ne] * a[(i + 2 * s) % ne] - a[(i + 3 * s) % ne])) % R for i in range(ne)]
+    assert got == want
