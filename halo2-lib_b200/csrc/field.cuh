@@ -175,11 +175,14 @@ struct __align__(16) Fp {
     // into X[i], the carry of that add entering the Y chain at position i+1 — exactly where it belongs.
     // Bounds: running total < 2p before a row and < 2^288 * 2^(32 i) after the products, so the chains
     // that would carry into position i+9 cannot, and the final sum is < 2p.
-#ifdef H2B_MUL_NOINLINE
-    __device__ __noinline__ friend Fp operator*(const Fp& a, const Fp& b) {
-#else
     __device__ __forceinline__ friend Fp operator*(const Fp& a, const Fp& b) {
+#ifdef H2B_MUL_KARATSUBA  // measured slower on B200 (see the note at mul_karatsuba): kept for reference only
+        return mul_karatsuba(a, b);
+#else
+        return mul_cios(a, b);
 #endif
+    }
+    __device__ __forceinline__ static Fp mul_cios(const Fp& a, const Fp& b) {
         u32 E[17], O[17];
 #pragma unroll
         for (int k = 0; k < 17; k++) { E[k] = 0; O[k] = 0; }
@@ -231,6 +234,126 @@ struct __align__(16) Fp {
 #pragma unroll
         for (int k = 1; k < 7; k++) addc_cc(s.l[k], E[8 + k], O[8 + k]);
         addc(s.l[7], E[15], O[15]);
+        return reduce_once(s);
+    }
+
+    // ---- Karatsuba variant: 48 + 64 = 112 wide multiplies instead of 128 (NOT the default) ------------------------
+    // Measured on B200 (tools/latbench.cu, 8 warps per sub-partition): 599 cycles per warp-product against 556 for
+    // the CIOS form above, and k_accumulate 1.86 ms against 1.31 ms: ptxas needs 303 instructions (incl. IMAD.MOV /
+    // IMAD.X on the multiplier pipe) instead of 185 and the kernel becomes issue- and register-bound.
+    // The integer multiplier is the scarce resource on this part (IMAD.WIDE / IMAD.HI issue every ~4.2 cycles per
+    // sub-partition, plain adds run on the otherwise idle ALU pipe), so one Karatsuba level on the 8x8-limb product
+    // trades 16 wide multiplies for ~100 additions:  a = a0 + a1 X, b = b0 + b1 X, X = 2^128,
+    //     a*b = z0 + (z0 + z2 - (a0 - a1)(b0 - b1)) X + z2 X^2,   z0 = a0 b0, z2 = a1 b1.
+    // 4x4-limb product r[0..8) = x * y.  E / O are position-indexed accumulators for products that start at even /
+    // odd limb positions; every chain ends in a carry limb that so far holds only carry counts (see operator*).
+    __device__ __forceinline__ static void mul4(const u32* x, const u32* y, u32* r) {
+        u32 E[10], O[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u32 yi = y[i];
+            // products x[j]*y[i] at position i+j; j and j+2 share parity: one carry chain per parity
+            u32* A = (i & 1) ? O : E;  // gets j = 0, 2 (positions i, i+2)
+            u32* B = (i & 1) ? E : O;  // gets j = 1, 3 (positions i+1, i+3)
+            mad_lo_cc(A[i], x[0], yi);      madc_hi_cc(A[i + 1], x[0], yi);
+            madc_lo_cc(A[i + 2], x[2], yi); madc_hi_cc(A[i + 3], x[2], yi);
+            addc(A[i + 4], A[i + 4], 0);
+            mad_lo_cc(B[i + 1], x[1], yi);  madc_hi_cc(B[i + 2], x[1], yi);
+            madc_lo_cc(B[i + 3], x[3], yi); madc_hi_cc(B[i + 4], x[3], yi);
+            addc(B[i + 5], B[i + 5], 0);
+        }
+        add_cc(r[0], E[0], O[0]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) addc_cc(r[k], E[k], O[k]);
+        addc(r[7], E[7], O[7]);
+    }
+    // |x - y| over 4 limbs; returns all-ones if x < y
+    __device__ __forceinline__ static u32 absdiff4(const u32* x, const u32* y, u32* d) {
+        u32 t[4], borrow;
+        sub_cc(t[0], x[0], y[0]);
+        subc_cc(t[1], x[1], y[1]);
+        subc_cc(t[2], x[2], y[2]);
+        subc_cc(t[3], x[3], y[3]);
+        subc(borrow, 0, 0);
+        // negate when negative: (t ^ borrow) - borrow
+        sub_cc(d[0], t[0] ^ borrow, borrow);
+        subc_cc(d[1], t[1] ^ borrow, borrow);
+        subc_cc(d[2], t[2] ^ borrow, borrow);
+        subc(d[3], t[3] ^ borrow, borrow);
+        return borrow;
+    }
+    __device__ __forceinline__ static Fp mul_karatsuba(const Fp& a, const Fp& b) {
+        u32 z0[8], z2[8], zm[8], da[4], db[4];
+        mul4(a.l, b.l, z0);
+        mul4(a.l + 4, b.l + 4, z2);
+        const u32 sa = absdiff4(a.l, a.l + 4, da), sb = absdiff4(b.l, b.l + 4, db);
+        mul4(da, db, zm);
+        // mid = z0 + z2 -+ zm  (9 limbs).  neg = all-ones when (a0-a1)(b0-b1) > 0, i.e. zm is SUBTRACTED
+        const u32 neg = ~(sa ^ sb);
+        u32 mid[9];
+        add_cc(mid[0], z0[0], z2[0]);
+#pragma unroll
+        for (int k = 1; k < 8; k++) addc_cc(mid[k], z0[k], z2[k]);
+        addc(mid[8], 0, 0);
+        // mid += (zm ^ neg) + (neg & 1), top limb += neg  (two's complement subtraction when neg)
+        add_cc(mid[0], mid[0], neg & 1u);
+#pragma unroll
+        for (int k = 1; k < 8; k++) addc_cc(mid[k], mid[k], 0);
+        addc(mid[8], mid[8], 0);
+        add_cc(mid[0], mid[0], zm[0] ^ neg);
+#pragma unroll
+        for (int k = 1; k < 8; k++) addc_cc(mid[k], mid[k], zm[k] ^ neg);
+        addc(mid[8], mid[8], neg);
+        // T = z0 + mid * 2^128 + z2 * 2^256  (16 limbs: lo = T[0..8), hi = T[8..16))
+        u32 lo[8], hi[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) lo[k] = z0[k];
+        add_cc(lo[4], z0[4], mid[0]);
+        addc_cc(lo[5], z0[5], mid[1]);
+        addc_cc(lo[6], z0[6], mid[2]);
+        addc_cc(lo[7], z0[7], mid[3]);
+        addc_cc(hi[0], z2[0], mid[4]);
+        addc_cc(hi[1], z2[1], mid[5]);
+        addc_cc(hi[2], z2[2], mid[6]);
+        addc_cc(hi[3], z2[3], mid[7]);
+        addc_cc(hi[4], z2[4], mid[8]);
+        addc_cc(hi[5], z2[5], 0);
+        addc_cc(hi[6], z2[6], 0);
+        addc(hi[7], z2[7], 0);
+        // Montgomery reduction of the low half (8 rows, same even/odd accumulators as operator*), then + hi
+        u32 E[17], O[17];
+#pragma unroll
+        for (int k = 0; k < 17; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) E[k] = lo[k];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            u32* X = (i & 1) ? O : E;
+            u32* Y = (i & 1) ? E : O;
+            if (i > 0) add_cc(X[i], X[i], Y[i]);  // fold Y's live limb; the carry enters the Y chain below
+            const u32 m = X[i] * P::INV;
+            if (i > 0) { madc_lo_cc(Y[i + 1], m, P::MOD(1)); } else { mad_lo_cc(Y[i + 1], m, P::MOD(1)); }
+            madc_hi_cc(Y[i + 2], m, P::MOD(1));
+            madc_lo_cc(Y[i + 3], m, P::MOD(3)); madc_hi_cc(Y[i + 4], m, P::MOD(3));
+            madc_lo_cc(Y[i + 5], m, P::MOD(5)); madc_hi_cc(Y[i + 6], m, P::MOD(5));
+            madc_lo_cc(Y[i + 7], m, P::MOD(7)); madc_hi(Y[i + 8], m, P::MOD(7));
+            mad_lo_cc(X[i], m, P::MOD(0));      madc_hi_cc(X[i + 1], m, P::MOD(0));
+            madc_lo_cc(X[i + 2], m, P::MOD(2)); madc_hi_cc(X[i + 3], m, P::MOD(2));
+            madc_lo_cc(X[i + 4], m, P::MOD(4)); madc_hi_cc(X[i + 5], m, P::MOD(4));
+            madc_lo_cc(X[i + 6], m, P::MOD(6)); madc_hi_cc(X[i + 7], m, P::MOD(6));
+            addc(X[i + 8], X[i + 8], 0);
+        }
+        Fp s;
+        add_cc(s.l[0], E[8], O[8]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) addc_cc(s.l[k], E[8 + k], O[8 + k]);
+        addc(s.l[7], E[15], O[15]);
+        add_cc(s.l[0], s.l[0], hi[0]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) addc_cc(s.l[k], s.l[k], hi[k]);
+        addc(s.l[7], s.l[7], hi[7]);
         return reduce_once(s);
     }
     __device__ __forceinline__ Fp sqr() const { return (*this) * (*this); }
