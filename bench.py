@@ -255,6 +255,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would precede the JSON line
         dist.init_process_group("nccl", device_id=dev)
     k = args.k
     n = 1 << k
