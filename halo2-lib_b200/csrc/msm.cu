@@ -13,9 +13,10 @@
 //                     scalar distribution, witness columns are dominated by 0/1/88-bit limbs), gathers the
 //                     64-byte affine points with 128-bit loads, XYZZ mixed adds; buckets that end inside
 //                     the chunk are written directly, runs cut by a chunk border go to a partial array
-//   k_collect(_big)   per bucket: add the partials of the chunks it spans
-//   k_rowcol_sums     bucket grid 2^mh x 2^ml: one warp per row sum / column sum (shuffle tree)
-//   k_weighted_final  lo * R_lo and hi * C_hi by small double-and-add, block sums, Horner over bucket sets
+//   k_collect         per bucket: add the partials of the chunks it spans; buckets spanning > 64 chunks are
+//   k_collect_big1/2  cut into segments summed by whole CTAs
+//   k_rowcol_sums     bucket grid 2^mh x 2^ml: one CTA of 32 lane-quads per row sum / column sum (quad.cuh)
+//   k_weighted_final  lo * R_lo and hi * C_hi by 4-lane double-and-add, block sums, Horner over bucket sets
 //
 // Fixed bases (the SRS): `table[w*n + i] = 2^(c*w) * P_i` is built once per SRS (k_precompute_level), so all
 // windows of a scalar fall into ONE bucket set: no per-window reduction and no final doublings.

@@ -8,10 +8,11 @@
 // Decomposition: log_n = r_1 + ... + r_p (p <= 3, r_t <= 11).  Pass t transforms digit t of the index
 // (decimation in frequency) for a tile of 2^r_t rows x CW adjacent columns held in shared memory (two
 // 128-bit planes per element, conflict-free for unit-stride lanes), multiplies by the inter-pass twiddle
-// omega_t^(i_t * j') taken from a two-level power table of omega, and writes in place; the last pass
+// omega_t^(i_t * j') (one precomputed table entry per in-place address, built once per domain from a two-level
+// power table of omega, with 2^-k folded in for inverse transforms), and writes in place; the last pass
 // writes through the digit-reversal so the result is in natural order with >= 64-byte contiguous stores.
 // Every pass reads and writes each element once: 64 B of HBM traffic per element per pass.
-// Coset scaling (zeta^(i mod 3)), zero padding and the 2^-k scaling are fused into the first / last pass.
+// Coset scaling (zeta^(i mod 3)) and zero padding are fused into the first pass, zeta^-(i mod 3) into the last.
 #include "h2b_internal.cuh"
 #include "field.cuh"
 #include "fr_domain_consts.inc"
@@ -94,10 +95,6 @@ struct PassArgs {
     int first, last;
     int logN1, logBrest;   // last pass: natural index = i1 + N1 * (rest + Brest * row)
     const Fr* wtab;
-    const Fr* tw_lo;
-    const Fr* tw_hi;
-    int h;
-    int tw_shift;    // log2(n / L_t): twiddle exponent = row * j' << tw_shift
     const Fr* n_inv; // non-null: scale by 2^-log_n in the last pass
     const Fr* tw_full; // non-last passes: precomputed twiddle per in-place address
     int coset;       // 1: in[i] *= zeta^(i mod 3) on load (first pass); 2: out[i] *= zeta^-(i mod 3) on store (last)
@@ -199,7 +196,6 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(PassArgs a) {
             const size_t g = gaddr(row, col);
             v = v * Fr::load_nc(a.tw_full + g);
             v.store(a.out + g);
-            continue;
         }
     }
 }
@@ -304,10 +300,6 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
         a.logN1 = p->npass > 1 ? p->r[0] : 0;
         a.logBrest = cols_log - a.logN1;
         a.wtab = p->wtab[t];
-        a.tw_lo = p->tw_lo;
-        a.tw_hi = p->tw_hi;
-        a.h = p->h;
-        a.tw_shift = consumed;  // n / L_t = 2^consumed
         a.n_inv = (last && inverse_scale && p->npass == 1) ? p->n_inv : nullptr;  // multi-pass: folded into tw_full[0]
         a.tw_full = last ? nullptr : p->tw_full[t];
         a.coset = coset_mode;
