@@ -27,7 +27,7 @@
 namespace h2b {
 
 static constexpr u32 SIGN_BIT = 0x80000000u;
-static constexpr int ACC_L_DEFAULT = 32;  // sorted entries per accumulate thread (H2B_ACC_L overrides: 16/32/64)
+static constexpr int ACC_L_DEFAULT = 32;  // upper bound of the sorted entries per accumulate thread (see k_accumulate)
 static constexpr int BIG_PARTIALS = 64;  // buckets spanning more chunks than this are summed by a whole CTA
 
 // ------------------------------------------------------------------------------------------------ digits + counting sort
@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ hist
     if (t == 255) tile_sums[blockIdx.x] = run;
 }
 __global__ void __launch_bounds__(256) k_scan_apply(u32 nb, u32 ntiles, const u32* __restrict__ tile_sums,
-                                                    u32* __restrict__ off, u32* __restrict__ cursor) {
+                                                    u32* __restrict__ off, u32* __restrict__ cursor, u32 slots,
+                                                    u32 l_min, u32 l_max, u32* __restrict__ d_L) {
     __shared__ u32 red[256];
     const u32 t = threadIdx.x;
     u32 s = 0;
@@ -164,7 +165,17 @@ __global__ void __launch_bounds__(256) k_scan_apply(u32 nb, u32 ntiles, const u3
             off[base + e] = o;
             cursor[base + e] = o;
         }
-    if (blockIdx.x == ntiles - 1 && t == 0) off[nb] = add + tile_sums[ntiles - 1];
+    if (blockIdx.x == ntiles - 1 && t == 0) {
+        const u32 mv = add + tile_sums[ntiles - 1];
+        off[nb] = mv;
+        // chunk length for k_accumulate: whole waves of equally long chunks (see k_accumulate)
+        u32 L = l_max;
+        if (mv < l_max * slots) {  // less than one full wave of l_max-chunks: spread the entries over every slot
+            L = (mv + slots - 1) / slots;
+            if (L < l_min) L = l_min;
+        }
+        *d_L = L;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
@@ -184,11 +195,17 @@ __device__ __forceinline__ u32 bucket_of(const u32* __restrict__ off, u32 lo, u3
     return lo;
 }
 
-template <int L>
+// Chunk length L is chosen ON THE DEVICE by k_scan_apply once the number of entries is known (zero digits are
+// dropped, so it depends on the scalars): 32 normally; when the entries would not even fill one wave of
+// 32-entry chunks (sparse witness columns, small shards) L = ceil(entries / slots), slots = resident threads of
+// this kernel, so that every SM is busy.  (Whole-wave balancing of dense columns was measured: no gain, the
+// kernel is multiplier-bound and a partially filled last wave simply runs faster.)
 __global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ vals, const u32* __restrict__ off,
-                                                       u32 nb_total, const Affine* __restrict__ table,
+                                                       u32 nb_total, const u32* __restrict__ d_L,
+                                                       const Affine* __restrict__ table,
                                                        XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 L = __ldg(d_L);
     const u32 mv = __ldg(off + nb_total);  // number of (non-zero-digit) entries
     const u64 cs64 = (u64)t * L;
     if (cs64 >= mv) return;
@@ -226,16 +243,17 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ v
     }
 }
 
-__device__ __forceinline__ const XYZZ* partial_of(const XYZZ* partials, u32 s, u32 t, int L) {
-    return (s <= t * (u32)L) ? partials + 2 * (size_t)t : partials + 2 * (size_t)t + 1;
+__device__ __forceinline__ const XYZZ* partial_of(const XYZZ* partials, u32 s, u32 t, u32 L) {
+    return (s <= t * L) ? partials + 2 * (size_t)t : partials + 2 * (size_t)t + 1;
 }
 
 // one thread per bucket: empty -> identity; spans several chunks -> add their partials
-__global__ void __launch_bounds__(128) k_collect(const u32* __restrict__ off, u32 nb_total, int L,
+__global__ void __launch_bounds__(128) k_collect(const u32* __restrict__ off, u32 nb_total, const u32* __restrict__ d_L,
                                                  const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets,
                                                  u32* __restrict__ big_list, u32* __restrict__ big_count) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb_total) return;
+    const u32 L = __ldg(d_L);
     const u32 s = __ldg(off + b), e = __ldg(off + b + 1);
     if (s == e) {
         XYZZ::identity().store(buckets + b);
@@ -257,11 +275,12 @@ __global__ void __launch_bounds__(128) k_collect(const u32* __restrict__ off, u3
 // Stage 2: one CTA per big bucket sums its segment sums.  Work lists are walked on the device (counts are only
 // known there); `seg` needs one slot per 64 chunk partials overall.
 static constexpr int BIG_SEG = 64;
-__global__ void __launch_bounds__(256) k_collect_big1(const u32* __restrict__ off, int L, const XYZZ* __restrict__ partials,
+__global__ void __launch_bounds__(256) k_collect_big1(const u32* __restrict__ off, const u32* __restrict__ d_L, const XYZZ* __restrict__ partials,
                                                       const u32* __restrict__ big_list, const u32* __restrict__ big_count,
                                                       XYZZ* __restrict__ seg) {
     __shared__ XYZZ sh[8];
     const u32 nbig = *big_count;
+    const u32 L = __ldg(d_L);
     const u32 qid = threadIdx.x >> 2;
     u32 seg_base = 0;  // running number of segments of the buckets before j
     u32 g = blockIdx.x;  // next segment of this CTA (segments are numbered across all big buckets)
@@ -281,11 +300,12 @@ __global__ void __launch_bounds__(256) k_collect_big1(const u32* __restrict__ of
         seg_base += nseg;
     }
 }
-__global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ off, int L, const XYZZ* __restrict__ seg,
+__global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ off, const u32* __restrict__ d_L, const XYZZ* __restrict__ seg,
                                                       XYZZ* __restrict__ buckets, const u32* __restrict__ big_list,
                                                       const u32* __restrict__ big_count) {
     __shared__ XYZZ sh[8];
     const u32 nbig = *big_count;
+    const u32 L = __ldg(d_L);
     const u32 qid = threadIdx.x >> 2;
     u32 seg_base = 0;
     for (u32 j = 0; j < nbig; j++) {
@@ -523,17 +543,18 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     cudaStream_t st = ctx->stream;
 
     u32* vals = (u32*)ctx->get(WS_VALS_A, M * 4);
-    u32* cnt = (u32*)ctx->get(WS_KEYS_A, (2 * ((size_t)nb_total + 2) + nb_total / SCAN_TILE + 2) * 4);  // histogram, cursors, tile sums
+    u32* cnt = (u32*)ctx->get(WS_KEYS_A, (2 * ((size_t)nb_total + 2) + nb_total / SCAN_TILE + 4) * 4);  // histogram, cursors, tile sums, L
     u32* hist = cnt;
     u32* cursor = cnt + nb_total + 2;
     u32* off = (u32*)ctx->get(WS_OFFSETS, ((size_t)nb_total + 2) * 4);
     XYZZ* buckets = (XYZZ*)ctx->get(WS_BUCKETS, (size_t)nb_total * sizeof(XYZZ));
-    static const int ACC_L = [] {
+    static const int L_MAX = [] {  // H2B_ACC_L pins the chunk length (experiments); default: device-chosen in [12, 32]
         const char* e = getenv("H2B_ACC_L");
-        int v = e ? atoi(e) : ACC_L_DEFAULT;
-        return (v == 16 || v == 32 || v == 64) ? v : ACC_L_DEFAULT;
+        int v = e ? atoi(e) : 0;
+        return (v >= 8 && v <= 64) ? v : 0;
     }();
-    const size_t n_chunks = (M + ACC_L - 1) / ACC_L;
+    const u32 l_min = L_MAX ? (u32)L_MAX : 12u, l_max = L_MAX ? (u32)L_MAX : (u32)ACC_L_DEFAULT;
+    const size_t n_chunks = (M + l_min - 1) / l_min;  // worst case; threads beyond the entries exit at once
     XYZZ* partials = (XYZZ*)ctx->get(WS_PARTIALS, 2 * n_chunks * sizeof(XYZZ));
     u32* big = (u32*)ctx->get(WS_BIGLIST, ((size_t)nb_total + 1) * 4);  // [0] = counter, list follows
 
@@ -543,21 +564,18 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     const u32 ntiles = (nb_total + SCAN_TILE - 1) / SCAN_TILE;
     u32* tile_sums = cursor + nb_total + 2;
     H2B_LAUNCH(ctx, k_scan_tiles, ntiles, 256, 0, hist, nb_total, off, tile_sums);
-    H2B_LAUNCH(ctx, k_scan_apply, ntiles, 256, 0, nb_total, ntiles, tile_sums, off, cursor);
+    u32* d_L = tile_sums + ntiles + 1;
+    const u32 slots = (u32)ctx->sm_count * 512u;  // k_accumulate: 128 registers -> 4 CTAs x 128 threads per SM
+    H2B_LAUNCH(ctx, k_scan_apply, ntiles, 256, 0, nb_total, ntiles, tile_sums, off, cursor, slots, l_min, l_max, d_L);
     H2B_LAUNCH(ctx, k_digits<1>, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, cursor, vals);
     if (after_digits) H2B_CUDA(cudaEventRecord(after_digits, st));
 
     H2B_CUDA(cudaMemsetAsync(big, 0, 4, st));
-    if (ACC_L == 16)
-        H2B_LAUNCH(ctx, k_accumulate<16>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, (const Affine*)d_table, buckets, partials);
-    else if (ACC_L == 32)
-        H2B_LAUNCH(ctx, k_accumulate<32>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, (const Affine*)d_table, buckets, partials);
-    else
-        H2B_LAUNCH(ctx, k_accumulate<64>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, (const Affine*)d_table, buckets, partials);
-    H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, ACC_L, partials, buckets, big + 1, big);
+    H2B_LAUNCH(ctx, k_accumulate, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, d_L, (const Affine*)d_table, buckets, partials);
+    H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, d_L, partials, buckets, big + 1, big);
     XYZZ* seg = (XYZZ*)ctx->get(WS_POOL, (2 * (n_chunks / BIG_SEG) + 64) * sizeof(XYZZ));
-    H2B_LAUNCH(ctx, k_collect_big1, 2 * ctx->sm_count, 256, 0, off, ACC_L, partials, big + 1, big, seg);
-    H2B_LAUNCH(ctx, k_collect_big2, 64, 256, 0, off, ACC_L, seg, buckets, big + 1, big);
+    H2B_LAUNCH(ctx, k_collect_big1, 2 * ctx->sm_count, 256, 0, off, d_L, partials, big + 1, big, seg);
+    H2B_LAUNCH(ctx, k_collect_big2, 64, 256, 0, off, d_L, seg, buckets, big + 1, big);
 
     // bucket reduction: row/column sums of the 2^mh x 2^ml bucket grid, small scalar multiples, final combine
     const int m = c - 1, ml = (m + 1) / 2, mh = m - ml;
