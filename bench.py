@@ -235,7 +235,7 @@ def workload_config(k, gpus):
         "k": k, "columns": "1 advice / q_lookup / 1 fixed", "msm": f"{len(MSM_SCHEDULE)} x 2^{k} ({sum(1 for b, _ in MSM_SCHEDULE if b == 'lagrange')} lagrange + {sum(1 for b, _ in MSM_SCHEDULE if b == 'monomial')} monomial basis)",
         "ntt": f"{N_INTT} x iNTT(2^{k}) + {N_COSET} x coeff_to_extended(2^{k + 2}) + {N_COSET_INV} x extended_to_coeff(2^{k + 2})",
         "assignment": f"1 column x 2^{k} rows", "scalars": "3 witness-like + 9 uniform columns (SURVEY.md §8d)",
-        "parallelism": f"msm point-range sharded x{gpus} + all-gather of partial sums; NTT one polynomial per device" if gpus > 1 else "single GPU",
+        "parallelism": f"msm point-range sharded x{gpus} + fused NVLink peer all-reduce of the partial sums (one kernel per phase); NTT one polynomial per device" if gpus > 1 else "single GPU",
         "l2_policy": "inputs larger than L2: 12 distinct scalar columns + two 15-level base tables (~1 GB) + NTT buffers (~0.5 GB) per step vs 126 MB L2",
     }
 
@@ -287,6 +287,8 @@ def run_b200(args):
         ctx.check(lib.h2b_g1_fixed_base_mul_dev(ctx.h, C.c_void_p(gbase.ctypes.data), C.c_void_p(d_sc.data_ptr()), n_loc, C.c_void_p(d_pts.data_ptr())))
         tables[name] = d_pts
     torch.cuda.synchronize()
+    if world > 1:
+        h.connect_peers(ctx)  # NVLink mailboxes for the fused all-reduce of partial commitments (csrc/peer.cu)
     params = h.ParamsKZG(ctx, k, g=tables["monomial"].data_ptr(), g_lagrange=tables["lagrange"].data_ptr(), begin=begin, count=n_loc, device_ptrs=True)
     del tables
     # ---- inputs: 12 scalar columns (host pinned + device resident), NTT polynomials, the virtual witness column
@@ -318,11 +320,8 @@ def run_b200(args):
         for phase in MSM_PHASES:
             j0 = phase[0]
             params.commit_batch_dev([basis_id[j] for j in phase], [cols_dev[j].data_ptr() for j in phase], n_loc, outs_dev[j0].data_ptr())
-            if world > 1:  # all-reduce under EC addition = all-gather of the 96-byte partials + local adds
-                npts = len(phase)
-                gt = h.all_gather_points(outs_dev[j0:j0 + npts])  # npts x world x 12
-                for jj in range(npts):
-                    ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(gt[jj].data_ptr()), world, vp(outs_dev[j0 + jj].data_ptr())))
+            if world > 1:  # all-reduce under EC addition: one fused kernel over NVLink peer memory, no NCCL call
+                h.allreduce_points(ctx, outs_dev[j0].data_ptr(), len(phase))
         for i in range(N_INTT):
             if my_ntt(i):
                 ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(polys_dev[i].data_ptr()), k))

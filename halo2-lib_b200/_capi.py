@@ -43,6 +43,9 @@ SIGNATURES = {
     "h2b_g1_normalize": (_int, [_vp, _vp, _sz]),
     "h2b_g1_fixed_base_mul": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "h2b_g1_fixed_base_mul_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_peer_create": (_int, [_vp, _int, _int, _vp]),
+    "h2b_peer_connect": (_int, [_vp, _vp]),
+    "h2b_g1_allreduce_dev": (_int, [_vp, _vp, _sz]),
     "h2b_ntt_fr": (_int, [_vp, _vp, _u32, _vp, _int]),
     "h2b_ntt_fr_dev": (_int, [_vp, _vp, _u32, _vp, _int]),
     "h2b_domain_omega": (_int, [_u32, _vp]),

@@ -132,6 +132,7 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ntt_free_plans(ctx);
+    peer_destroy(ctx);
     for (auto& lane : ctx->ws)
         for (auto& b : lane)
             if (b.p) cudaFree(b.p);
@@ -408,6 +409,26 @@ int h2b_g1_fixed_base_mul(h2b_ctx* ctx, const uint64_t base_xy[8], const uint64_
         g1_fixed_base_mul_run(ctx, base_xy, d_s, n, d_o);
         H2B_CUDA(cudaMemcpyAsync(out_xy, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ peer all-reduce
+int h2b_peer_create(h2b_ctx* ctx, int rank, int nranks, uint8_t handle_out[64]) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(handle_out, "peer: null pointer");
+        peer_create(ctx, rank, nranks, handle_out);
+    });
+}
+int h2b_peer_connect(h2b_ctx* ctx, const uint8_t* handles) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(handles, "peer: null pointer");
+        peer_connect(ctx, handles);
+    });
+}
+int h2b_g1_allreduce_dev(h2b_ctx* ctx, void* d_points_xyz, size_t m) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_points_xyz, "peer: null pointer");
+        peer_allreduce(ctx, d_points_xyz, m);
     });
 }
 

@@ -146,7 +146,7 @@ __device__ __forceinline__ void xyzz_add(XYZZ& acc, const XYZZ& q) {
 
 // XYZZ -> canonical Jacobian written as 12 x u64: identity -> (0, R, 0) (halo2curves G1::identity()),
 // otherwise the affine-normalised representative (x, y, R).  One field inversion; cold path.
-__device__ __noinline__ void xyzz_store_jacobian_normalised(const XYZZ& p, void* out) {
+static __device__ __noinline__ void xyzz_store_jacobian_normalised(const XYZZ& p, void* out) {
     char* c = reinterpret_cast<char*>(out);
     if (p.is_identity()) {
         Fq::zero().store(c);
@@ -161,7 +161,7 @@ __device__ __noinline__ void xyzz_store_jacobian_normalised(const XYZZ& p, void*
     (p.y * izzz).store(c + 32);
     Fq::one().store(c + 64);
 }
-__device__ __noinline__ Affine xyzz_to_affine(const XYZZ& p) {
+static __device__ __noinline__ Affine xyzz_to_affine(const XYZZ& p) {
     Affine a;
     if (p.is_identity()) { a.x = Fq::zero(); a.y = Fq::zero(); return a; }
     Fq t = (p.zz * p.zzz).inv();

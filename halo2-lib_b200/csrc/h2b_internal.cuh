@@ -76,6 +76,7 @@ struct h2b_ctx {
     mutable std::mutex mu;
     std::string err;
     uint64_t launches = 0;
+    void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
     bool reduce_counter_zeroed = false;
     void* reduce_counter_ptr = nullptr;
     struct Buf {
@@ -170,6 +171,11 @@ void assign_columns_run(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64
                         uint32_t k, size_t ncols, void* d_cols);
 void assign_lookups_run(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols);
 void eval_rational_run(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
+// ---- peer.cu
+void peer_create(h2b_ctx* ctx, int rank, int nranks, uint8_t* handle_out);
+void peer_connect(h2b_ctx* ctx, const uint8_t* handles);
+void peer_allreduce(h2b_ctx* ctx, void* d_points, size_t m);
+void peer_destroy(h2b_ctx* ctx);
 // ---- quotient.cu
 void flex_gate_fold_run(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k, uint32_t ext_k,
                         void* d_acc);

@@ -1,0 +1,150 @@
+// peer.cu — all-reduce of G1 partial sums over NVLink peer memory, fused into ONE kernel per prover phase.
+//
+// Point-range sharded MSM leaves one 96-byte Jacobian partial per GPU and commitment.  EC addition is
+// not an NCCL reduction op, and the payload is tiny, so instead of an NCCL all-gather plus a separate summation
+// kernel every rank runs k_g1_allreduce: it STORES its partials straight into every peer's mailbox through the
+// NVLink-mapped (CUDA IPC) address, publishes a flag, waits for the flags of all peers in its own mailbox and adds
+// the points with the 4-lane group law of quad.cuh.  One launch, no host round trip, no NCCL call on the data path.
+#include "h2b_internal.cuh"
+#include "quad.cuh"
+
+namespace h2b {
+
+static constexpr int PEER_MAX_RANKS = 16;
+static constexpr int PEER_MAX_POINTS = 16;  // commitments per call (a prover phase has <= 4)
+
+struct PeerMailbox {
+    uint64_t data[2][PEER_MAX_RANKS][PEER_MAX_POINTS][12];  // [epoch parity][source rank][point][limb]
+    uint64_t flags[2][PEER_MAX_RANKS];                      // epoch number published by each source rank
+};
+
+struct PeerPtrs {
+    PeerMailbox* box[PEER_MAX_RANKS];
+};
+
+__device__ __forceinline__ void store_jacobian_xyzz(const XYZZ& p, uint64_t* out) {
+    char* o = reinterpret_cast<char*>(out);
+    if (p.is_identity()) {
+        Fq::zero().store(o);
+        Fq::one().store(o + 32);
+        Fq::zero().store(o + 64);
+        return;
+    }
+    Fq z = p.zz * p.zzz;
+    Fq a = p.zz * p.zzz.sqr();
+    (p.x * a).store(o);
+    (p.y * a * p.zz.sqr()).store(o + 32);
+    z.store(o + 64);
+}
+
+// Parity slots: epoch e uses slot e & 1.  A rank can only start epoch e+2 after it passed the wait of epoch e+1, and a
+// peer publishes epoch e+1 only after its own kernel of epoch e has finished (stream order), so the data of epoch e
+// is never overwritten while somebody still reads it.
+__global__ void __launch_bounds__(256) k_g1_allreduce(PeerPtrs peers, int rank, int nranks, uint64_t epoch,
+                                                      uint64_t* __restrict__ pts, int m) {
+    const int par = (int)(epoch & 1);
+    const int t = threadIdx.x;
+    // 1. scatter my partials into every rank's mailbox (own one included), slot [parity][rank]
+    const int words = m * 12;
+    for (int idx = t; idx < words * nranks; idx += blockDim.x) {
+        const int r = idx / words, w = idx % words;
+        volatile uint64_t* dst = &peers.box[r]->data[par][rank][0][0];
+        dst[w] = pts[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < nranks) {
+        volatile uint64_t* f = &peers.box[t]->flags[par][rank];
+        *f = epoch;
+    }
+    // 2. wait until every rank has published this epoch in MY mailbox
+    if (t < nranks) {
+        volatile uint64_t* f = &peers.box[rank]->flags[par][t];
+        while (*f != epoch) { }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 3. one lane-quad per commitment: sum over the source ranks
+    const int q = t >> 2;
+    if (q < m) {
+        XYZZ acc = XYZZ::identity();
+        for (int r = 0; r < nranks; r++) {
+            const uint64_t* src = &peers.box[rank]->data[par][r][q][0];
+            uint64_t tmp[12];
+#pragma unroll
+            for (int l = 0; l < 12; l++) tmp[l] = __ldcg(src + l);
+            XYZZ p;  // Jacobian -> XYZZ
+            Fq z;
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                p.x.l[2 * l] = (u32)tmp[l]; p.x.l[2 * l + 1] = (u32)(tmp[l] >> 32);
+                p.y.l[2 * l] = (u32)tmp[4 + l]; p.y.l[2 * l + 1] = (u32)(tmp[4 + l] >> 32);
+                z.l[2 * l] = (u32)tmp[8 + l]; z.l[2 * l + 1] = (u32)(tmp[8 + l] >> 32);
+            }
+            if (z.is_zero()) continue;
+            p.zz = z.sqr();
+            p.zzz = p.zz * z;
+            quad_add(acc, p);
+        }
+        if ((t & 3) == 0) store_jacobian_xyzz(acc, pts + 12 * q);
+    }
+}
+
+struct PeerState {
+    int rank = -1, nranks = 0;
+    PeerMailbox* own = nullptr;
+    PeerPtrs ptrs{};
+    bool opened[PEER_MAX_RANKS] = {};
+    bool connected = false;
+    uint64_t epoch = 0;
+};
+
+void peer_create(h2b_ctx* ctx, int rank, int nranks, uint8_t* handle_out) {
+    H2B_REQUIRE(nranks >= 1 && nranks <= PEER_MAX_RANKS && rank >= 0 && rank < nranks, "peer: bad rank / nranks");
+    H2B_REQUIRE(!ctx->peer, "peer: mailbox already created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    PeerState* st = new PeerState();
+    st->rank = rank;
+    st->nranks = nranks;
+    ctx->peer = st;
+    H2B_CUDA(cudaMalloc((void**)&st->own, sizeof(PeerMailbox)));
+    H2B_CUDA(cudaMemset(st->own, 0, sizeof(PeerMailbox)));
+    cudaIpcMemHandle_t h;
+    H2B_CUDA(cudaIpcGetMemHandle(&h, st->own));
+    memcpy(handle_out, &h, 64);
+}
+
+void peer_connect(h2b_ctx* ctx, const uint8_t* handles) {
+    PeerState* st = (PeerState*)ctx->peer;
+    H2B_REQUIRE(st, "peer: call h2b_peer_create first");
+    for (int r = 0; r < st->nranks; r++) {
+        if (r == st->rank) { st->ptrs.box[r] = st->own; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        H2B_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        st->ptrs.box[r] = (PeerMailbox*)p;
+        st->opened[r] = true;
+    }
+    st->connected = true;
+}
+
+void peer_allreduce(h2b_ctx* ctx, void* d_points, size_t m) {
+    PeerState* st = (PeerState*)ctx->peer;
+    H2B_REQUIRE(st && st->connected, "peer: mailboxes are not connected");
+    H2B_REQUIRE(m >= 1 && m <= (size_t)PEER_MAX_POINTS, "peer: 1..16 points per call");
+    st->epoch++;
+    H2B_LAUNCH(ctx, k_g1_allreduce, 1, 256, 0, st->ptrs, st->rank, st->nranks, st->epoch, (uint64_t*)d_points, (int)m);
+}
+
+void peer_destroy(h2b_ctx* ctx) {
+    PeerState* st = (PeerState*)ctx->peer;
+    if (!st) return;
+    for (int r = 0; r < st->nranks; r++)
+        if (st->opened[r]) cudaIpcCloseMemHandle(st->ptrs.box[r]);
+    if (st->own) cudaFree(st->own);
+    delete st;
+    ctx->peer = nullptr;
+}
+
+}  // namespace h2b

@@ -32,3 +32,31 @@ def all_gather_points(partials, group=None):
     out = torch.empty((world * m,) + tuple(partials.shape[1:]), dtype=partials.dtype, device=partials.device)
     dist.all_gather_into_tensor(out, partials.contiguous(), group=group)  # concatenation along dim 0 (gloo and nccl)
     return out.view((world, m) + tuple(partials.shape[1:])).transpose(0, 1).contiguous()
+
+
+def connect_peers(ctx, group=None):
+    """Creates this rank's NVLink mailbox, exchanges the CUDA IPC handles of all ranks through torch.distributed and
+    connects them (h2b_peer_create / h2b_peer_connect).  After this `allreduce_points` needs no NCCL call."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from ._capi import lib
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = (C.c_uint8 * 64)()
+    ctx.check(lib.h2b_peer_create(ctx.h, rank, world, mine))
+    dev = torch.device("cuda", ctx.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+    out = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, t, group=group)
+    blob = bytes(out.cpu().tolist())
+    ctx.check(lib.h2b_peer_connect(ctx.h, C.c_char_p(blob)))
+    dist.barrier(group)
+
+
+def allreduce_points(ctx, d_points_ptr: int, m: int):
+    """in place: m Jacobian partials (device, m x 12 limbs) -> the m sums over all ranks; one fused kernel"""
+    import ctypes as C
+    from ._capi import lib
+
+    ctx.check(lib.h2b_g1_allreduce_dev(ctx.h, C.c_void_p(d_points_ptr), m))

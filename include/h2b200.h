@@ -111,6 +111,17 @@ int h2b_g1_fixed_base_mul(h2b_ctx* ctx, const uint64_t base_xy[8], const uint64_
 int h2b_g1_fixed_base_mul_dev(h2b_ctx* ctx, const uint64_t base_xy[8], const void* d_scalars, size_t n,
                               void* d_out_xy);
 
+/* ---- multi-GPU: all-reduce of partial commitments over NVLink peer memory (one process per GPU) ------------------
+ * Every rank creates a mailbox and exports its 64-byte CUDA IPC handle; the handles of all ranks (rank order) are
+ * exchanged by the caller's process layer (e.g. one torch.distributed all_gather at start-up) and connected once.
+ * h2b_g1_allreduce_dev then replaces `all-gather + h2b_g1_sum` by ONE kernel: each rank stores its m partial points
+ * (m x 12 limbs, Jacobian) straight into every peer's mailbox through the NVLink-mapped address, publishes a flag,
+ * waits for its peers' flags and adds the points; on return (stream order) d_points_xyz holds the m full sums on
+ * every rank.  All ranks must call it the same number of times, with the same m.  m <= 16. */
+int h2b_peer_create(h2b_ctx* ctx, int rank, int nranks, uint8_t handle_out[64]);
+int h2b_peer_connect(h2b_ctx* ctx, const uint8_t* handles /* nranks x 64 bytes */);
+int h2b_g1_allreduce_dev(h2b_ctx* ctx, void* d_points_xyz, size_t m);
+
 /* ---- NTT: replaces halo2-axiom 0.5.3 arithmetic::best_fft and poly::EvaluationDomain -- */
 /* best_fft(a, omega, log_n): in place, natural order in and out, out[i] = sum_j a[j] * omega^(i*j).
  * scale_by_n_inv != 0 additionally multiplies by 2^-log_n (EvaluationDomain::ifft). */
