@@ -76,6 +76,7 @@ struct h2b_ctx {
     mutable std::mutex mu;
     std::string err;
     uint64_t launches = 0;
+    bool ntt_attr_set = false;
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
     bool reduce_counter_zeroed = false;
     void* reduce_counter_ptr = nullptr;

@@ -205,6 +205,15 @@ static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4], 
     auto it = ctx->ntt_plans.find(key);
     if (it != ctx->ntt_plans.end()) return it->second;
     NttPlan* p = new NttPlan();
+    struct Guard {  // a failed allocation / launch must not leak the half-built plan
+        NttPlan* p;
+        ~Guard() {
+            if (!p) return;
+            if (p->block) cudaFree(p->block);
+            if (p->block2) cudaFree(p->block2);
+            delete p;
+        }
+    } guard{p};
     p->log_n = log_n;
     p->npass = log_n <= NTT_MAX_R ? 1 : (log_n <= 2 * NTT_MAX_R ? 2 : 3);
     {
@@ -250,6 +259,7 @@ static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4], 
         }
     }
     ctx->ntt_plans[key] = p;
+    guard.p = nullptr;
     return p;
 }
 
@@ -273,11 +283,10 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
     const size_t n = (size_t)1 << log_n;
     H2B_REQUIRE(n_src <= n, "ntt: more input elements than the domain size");
     NttPlan* p = get_plan(ctx, log_n, omega, inverse_scale);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->ntt_attr_set) {  // per context: the attribute belongs to the device the context is bound to
         H2B_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Fr) << NTT_TILE_LOG)));
         H2B_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Fr) << NTT_TILE_LOG)));
-        attr_set = true;
+        ctx->ntt_attr_set = true;
     }
     Fr* scratch = nullptr;
     if (p->npass > 1) scratch = (Fr*)ctx->get(WS_NTT_B, n * sizeof(Fr));
