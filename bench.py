@@ -415,6 +415,15 @@ def run_b200(args):
         "coset_intt": time_op(lambda: ctx.check(lib.h2b_extended_to_coeff_dev(ctx.h, vp(ext_dev[0].data_ptr()), ext_k))),
         "assign": time_op(lambda: ctx.check(lib.h2b_assign_columns_dev(ctx.h, vp(vcol_dev.data_ptr()), n_cells, None, 0, k, 1, vp(acol_dev.data_ptr())))),
     }
+
+    # the same 12 columns once more, one MSM at a time (no lane overlap): k_accumulate timed alone
+    ctx.profile_reset()
+    ctx.profile_enable("k_accumulate")
+    for j in range(len(MSM_SCHEDULE)):
+        params.commit_dev(basis_id[j], cols_dev[j].data_ptr(), n_loc, outs_dev[j].data_ptr())
+    torch.cuda.synchronize()
+    iso_ms, iso_cnt = ctx.profile_read("k_accumulate")
+    ctx.profile_enable(None)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -424,19 +433,23 @@ def run_b200(args):
     value = pairs / (ms_step / 1e3)
     peak, peak_src = measured_hbm_peak()
     acc_avg_ms = acc_ms / max(acc_cnt, 1)
+    iso_avg_ms = iso_ms / max(iso_cnt, 1)
     achieved = 96.0 * n_loc / (acc_avg_ms / 1e3) / 1e9  # algorithmic 96 B per pair (32 B scalar + 64 B base), SURVEY.md §8d
+    achieved_iso = 96.0 * n_loc / (iso_avg_ms / 1e3) / 1e9
     # field products of the average launch (estimate): entries = pairs * windows * P(non-zero digit); witness-like columns
     # keep ~23% of their digits (35% zeros, 25% ones, 30% 88-bit limbs, 10% full width)
     entries = n_loc * params_windows * (sum(1.0 if c == "uniform" else 0.23 for _, c in MSM_SCHEDULE) / len(MSM_SCHEDULE))
     products = 10.0 * entries
     roofline = {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch on a uniform column at k=19, single GPU, from the
-                # `ncu --set full` capture summarised in profiles/r01_k_accumulate_final_ncu_full.csv (976.2 + 37.3 MB)
-                "traffic": 1013457920 if (k == 19 and world == 1) else None, "peak_source": peak_src, "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt,
-                "algorithmic_bytes_per_launch": 96 * n_loc,
-                "integer_multiplier": {"products_per_s": products / (acc_avg_ms / 1e3), "peak_products_per_s": 66.9e9,
-                                       "frac": products / (acc_avg_ms / 1e3) / 66.9e9,
-                                       "note": "10 Montgomery products per XYZZ mixed add; peak = tools/latbench.cu (profiles/r01_pipe_microbench.txt)"},
+                # `ncu --set full` capture summarised in profiles/ (976.2 + 37.3 MB)
+                "traffic": 1013457920 if (k == 19 and world == 1) else None, "peak_source": peak_src,
+                "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt, "algorithmic_bytes_per_launch": 96 * n_loc,
+                "timed_region_note": "launches of the timed region overlap with the kernels of the other two MSM lanes, which stretches each launch",
+                "isolated": {"avg_launch_ms": iso_avg_ms, "launches": iso_cnt, "achieved": achieved_iso, "frac": achieved_iso / peak,
+                             "integer_multiplier": {"products_per_s": products / (iso_avg_ms / 1e3), "peak_products_per_s": 66.9e9,
+                                                    "frac": products / (iso_avg_ms / 1e3) / 66.9e9,
+                                                    "note": "estimate: 10 Montgomery products per XYZZ mixed add x non-zero digits; peak = tools/latbench.cu (profiles/r01_pipe_microbench.txt)"}},
                 "note": "bucket accumulation is bound by the integer multiplier (IMAD.WIDE), not by HBM: traffic is ~10% of HBM peak; see DESIGN.md 4.1/4.2"}
     h2d = (len(MSM_SCHEDULE) * n_loc * 32 + (N_INTT * n * 32 + N_COSET * n * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n_cells * 32)
     d2h = (len(MSM_SCHEDULE) * 96 + (N_INTT * n * 32 + N_COSET * (1 << ext_k) * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n * 32)
