@@ -67,7 +67,8 @@ __device__ __forceinline__ void for_each_digit(const Fr& s, int c, int W, F&& f)
 
 // Counter increment with two fast paths for hot counters.  (1) all active lanes of the warp hit the SAME counter
 // (constant columns, padding runs): one atomic per warp.  (2) lanes whose digit is tiny (|d| <= 4: bit-valued and
-// small-constant witness cells, the hot buckets of real advice columns) are grouped by __match_any_sync and issue
+// small-constant witness cells, the hot buckets of real advice columns) or in the top window (its digit only spans the
+// few leading bits of the scalar) are grouped by __match_any_sync and issue
 // one atomic per distinct counter.  Everything else uses a plain atomic; uniform digits are almost never tiny, so
 // the common case pays nothing for (2).  All 32 lanes must call; returns the slot of the lane.
 __device__ __forceinline__ u32 warp_agg_add(u32* counters, u32 key, bool active, bool tiny) {
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(256) k_digits(const uint64_t* __restrict__ sca
     for_each_digit(s, c, W, [&](int w, u32 d, bool neg) {
         const bool active = live && d != 0;
         const u32 key = active ? (u32)(w / q) * nbw + (d - 1) : 0;
-        const u32 slot = warp_agg_add(counters, key, active, d <= 4);
+        // tiny digits and the (narrow) top window are where hot buckets come from: group them before the atomic
+        const u32 slot = warp_agg_add(counters, key, active, d <= 4 || w == W - 1);
         if (MODE == 1 && active) vals_sorted[slot] = ((u32)(w % q) * n + i) | (neg ? SIGN_BIT : 0u);
     });
 }
@@ -510,10 +512,14 @@ int msm_choose_c_fixed(size_t n) {
         int v = atoi(e);
         if (v >= 4 && v <= 24) return v;
     }
+    // W = ceil(255 / c) only drops at c = 13, 14, 15, 16, 17, 19, 20, 22; measured on B200 (tools/prof_ops.py):
+    // 2^19: c = 17 (W = 15) beats 16 / 19 / 20; 2^21 and 2^23: c = 20 (W = 13) beats 17 / 19 / 21 / 22
+    // (the bucket-side work grows 2^c while the additions only shrink with W).
     int lg = ceil_log2(n ? n : 1);
     int c = lg - 2;
     if (c < 8) c = 8;
-    if (c > 22) c = 22;
+    if (lg >= 21) c = 20;
+    else if (c > 17) c = 17;
     return c;
 }
 static int msm_choose_c_adhoc(size_t n) {
