@@ -390,7 +390,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    params_windows = (255 + (k - 2) - 1) // (k - 2) if world == 1 else (255 + max(8, k - 2 - (world.bit_length() - 1)) - 1) // max(8, k - 2 - (world.bit_length() - 1))
+    params_windows = params.windows
     ms_step, launches = timed(step_resident, args.steps, args.warmup, prof="k_accumulate")
     acc_ms, acc_cnt = ctx.profile_read("k_accumulate")
     clocks = sampler.stop() if rank == 0 else None

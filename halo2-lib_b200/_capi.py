@@ -31,6 +31,7 @@ SIGNATURES = {
     "h2b_profile_read": (_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "h2b_srs_upload": (_int, [_vp, _vp, _vp, _u32, _sz, _sz, C.POINTER(_vp)]),
     "h2b_srs_upload_dev": (_int, [_vp, _vp, _vp, _u32, _sz, _sz, C.POINTER(_vp)]),
+    "h2b_srs_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
     "h2b_srs_destroy": (None, [_vp, _vp]),
     "h2b_msm_g1": (_int, [_vp, _vp, _int, _vp, _sz, _vp]),
     "h2b_msm_g1_batch": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_vp), _sz, _sz, _vp]),

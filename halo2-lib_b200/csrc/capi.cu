@@ -244,6 +244,12 @@ int h2b_srs_upload_dev(h2b_ctx* ctx, const void* d_g, const void* d_g_lagrange, 
                        h2b_srs** out) {
     return guarded(ctx, [&] { srs_build(ctx, d_g, d_g_lagrange, k, begin, count, out); });
 }
+int h2b_srs_info(const h2b_srs* srs, int* window_bits, int* windows) {
+    if (!srs || !window_bits || !windows) return H2B_ERR_ARG;
+    *window_bits = srs->c;
+    *windows = srs->W;
+    return H2B_OK;
+}
 void h2b_srs_destroy(h2b_ctx* ctx, h2b_srs* srs) {
     if (!srs) return;
     if (ctx) {

@@ -186,6 +186,9 @@ class ParamsKZG:
             rc = lib.h2b_srs_upload(ctx.h, _ptr(gg), _ptr(gl), k, begin, self.count, C.byref(h))
         ctx.check(rc)
         self.h = h
+        cb, w = C.c_int(), C.c_int()
+        lib.h2b_srs_info(self.h, C.byref(cb), C.byref(w))
+        self.window_bits, self.windows = cb.value, w.value
 
     def _commit(self, basis: int, poly) -> np.ndarray:
         s = _u64(poly, 4)

@@ -73,6 +73,8 @@ int h2b_srs_upload(h2b_ctx* ctx, const uint64_t* g, const uint64_t* g_lagrange, 
 /* Same, bases already on the device (count x 8 limbs each, the shard only). */
 int h2b_srs_upload_dev(h2b_ctx* ctx, const void* d_g, const void* d_g_lagrange, uint32_t k, size_t begin,
                        size_t count, h2b_srs** out);
+/* Window size c (bits) and number of table levels W = ceil(255 / c) chosen for this shard. */
+int h2b_srs_info(const h2b_srs* srs, int* window_bits, int* windows);
 void h2b_srs_destroy(h2b_ctx* ctx, h2b_srs* srs);
 
 /* ---- MSM: replaces halo2curves-axiom 0.7.3 msm::best_multiexp(coeffs, bases) -> G1, as reached from
