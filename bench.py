@@ -235,6 +235,7 @@ def workload_config(k, gpus):
         "k": k, "columns": "1 advice / q_lookup / 1 fixed", "msm": f"{len(MSM_SCHEDULE)} x 2^{k} ({sum(1 for b, _ in MSM_SCHEDULE if b == 'lagrange')} lagrange + {sum(1 for b, _ in MSM_SCHEDULE if b == 'monomial')} monomial basis)",
         "ntt": f"{N_INTT} x iNTT(2^{k}) + {N_COSET} x coeff_to_extended(2^{k + 2}) + {N_COSET_INV} x extended_to_coeff(2^{k + 2})",
         "assignment": f"1 column x 2^{k} rows", "scalars": "3 witness-like + 9 uniform columns (SURVEY.md §8d)",
+        "overlap": "MSMs of a transcript phase run on 3 lanes; the iNTT + coset NTT of a polynomial run on a side stream from the moment the polynomial exists and are joined before extended_to_coeff / the h(X) commitments",
         "parallelism": f"msm point-range sharded x{gpus} + fused NVLink peer all-reduce of the partial sums (one kernel per phase); NTT one polynomial per device" if gpus > 1 else "single GPU",
         "l2_policy": "inputs larger than L2: 12 distinct scalar columns + two 15-level base tables (~1 GB) + NTT buffers (~0.5 GB) per step vs 126 MB L2",
     }
@@ -269,6 +270,11 @@ def run_b200(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
+    # second context + stream on the same GPU: the polynomial transforms of a column run beside the commitment phases
+    # that do not depend on them (see step_resident)
+    ctx_ntt = h.Context(local_rank)
+    stream_ntt = torch.cuda.Stream(device=dev)
+    ctx_ntt.set_stream(stream_ntt.cuda_stream)
     rng = np.random.default_rng(0xB2000000 + k)
 
     def dev_u64(arr):
@@ -314,22 +320,46 @@ def run_b200(args):
     outs_host = np.zeros((len(MSM_SCHEDULE), 12), dtype=np.uint64)
     vp = C.c_void_p
 
-    def step_resident():
+    # which polynomials exist when a commitment phase starts (their iNTT + coset NTT may then run on the side stream):
+    # the advice column after the assignment, the two permuted lookup columns with phase 1, the two grand products with
+    # phase 2.  Everything must be back before h(X) is formed (extended_to_coeff, then the h-piece commitments).
+    NTT_READY = {0: [0], 1: [1, 2], 2: [3, 4]}
+    ev_fork = [torch.cuda.Event() for _ in range(4)]
+    ev_join = torch.cuda.Event()
+
+    def ntt_side(polys):
+        for i in polys:
+            if my_ntt(i):
+                ctx_ntt.check(lib.h2b_lagrange_to_coeff_dev(ctx_ntt.h, vp(polys_dev[i].data_ptr()), k))
+            if my_ntt(N_INTT + i):
+                ctx_ntt.check(lib.h2b_coeff_to_extended_dev(ctx_ntt.h, vp(polys_dev[i].data_ptr()), n, ext_k, vp(ext_dev[i].data_ptr())))
+
+    def step_resident(overlap=True):
         if rank == 0:
             ctx.check(lib.h2b_assign_columns_dev(ctx.h, vp(vcol_dev.data_ptr()), n_cells, None, 0, k, 1, vp(acol_dev.data_ptr())))
-        for phase in MSM_PHASES:
+        for pi, phase in enumerate(MSM_PHASES):
+            if pi in NTT_READY:
+                if overlap:
+                    ev_fork[pi].record(stream)
+                    stream_ntt.wait_event(ev_fork[pi])
+                    ntt_side(NTT_READY[pi])
+            elif pi == 3:
+                if overlap:
+                    ev_join.record(stream_ntt)
+                    stream.wait_event(ev_join)
+                else:
+                    for q in (0, 1, 2):
+                        for i in NTT_READY[q]:
+                            if my_ntt(i):
+                                ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(polys_dev[i].data_ptr()), k))
+                            if my_ntt(N_INTT + i):
+                                ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(polys_dev[i].data_ptr()), n, ext_k, vp(ext_dev[i].data_ptr())))
+                if my_ntt(N_INTT + N_COSET):
+                    ctx.check(lib.h2b_extended_to_coeff_dev(ctx.h, vp(ext_dev[0].data_ptr()), ext_k))
             j0 = phase[0]
             params.commit_batch_dev([basis_id[j] for j in phase], [cols_dev[j].data_ptr() for j in phase], n_loc, outs_dev[j0].data_ptr())
             if world > 1:  # all-reduce under EC addition: one fused kernel over NVLink peer memory, no NCCL call
                 h.allreduce_points(ctx, outs_dev[j0].data_ptr(), len(phase))
-        for i in range(N_INTT):
-            if my_ntt(i):
-                ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(polys_dev[i].data_ptr()), k))
-        for i in range(N_COSET):
-            if my_ntt(i):
-                ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(polys_dev[i % N_INTT].data_ptr()), n, ext_k, vp(ext_dev[i].data_ptr())))
-        if my_ntt(N_COSET):
-            ctx.check(lib.h2b_extended_to_coeff_dev(ctx.h, vp(ext_dev[0].data_ptr()), ext_k))
 
     def step_e2e():
         """the same step through the host-pointer C ABI: pinned host buffers in, host buffers out"""
@@ -352,12 +382,12 @@ def run_b200(args):
         if mine:
             ptrs = (C.c_void_p * len(mine))(*[polys_host[i].data_ptr() for i in mine])
             ctx.check(lib.h2b_lagrange_to_coeff_batch(ctx.h, ptrs, len(mine), k))
-        mine = [i for i in range(N_COSET) if my_ntt(i)]
+        mine = [i for i in range(N_COSET) if my_ntt(N_INTT + i)]
         if mine:
             pin = (C.c_void_p * len(mine))(*[polys_host[i % N_INTT].data_ptr() for i in mine])
             pout = (C.c_void_p * len(mine))(*[ext_host[i].data_ptr() for i in mine])
             ctx.check(lib.h2b_coeff_to_extended_batch(ctx.h, pin, len(mine), n, ext_k, pout))
-        if my_ntt(N_COSET):
+        if my_ntt(N_INTT + N_COSET):
             ctx.check(lib.h2b_extended_to_coeff(ctx.h, vp(ext_host[0].data_ptr()), ext_k))
 
     def barrier():
@@ -372,7 +402,7 @@ def run_b200(args):
         if prof:
             ctx.profile_reset()
             ctx.profile_enable(prof)
-        l0 = ctx.kernel_launches
+        l0 = ctx.kernel_launches + ctx_ntt.kernel_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -385,13 +415,14 @@ def run_b200(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps, ctx.kernel_launches - l0
+        return float(t.item()) / steps, ctx.kernel_launches + ctx_ntt.kernel_launches - l0
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     params_windows = params.windows
     ms_step, launches = timed(step_resident, args.steps, args.warmup, prof="k_accumulate")
+    ms_step_seq, _ = timed(lambda: step_resident(False), max(1, min(args.steps, 5)), 1)
     acc_ms, acc_cnt = ctx.profile_read("k_accumulate")
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 5)), 1)
@@ -460,6 +491,7 @@ def run_b200(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
         "config": workload_config(k, world),
         "create_proof_schedule_ms": ms_step,
+        "create_proof_schedule_ms_no_ntt_overlap": ms_step_seq,
         "ntt_fr_elements_per_s": (1 << ext_k) / (op_ms["coset_ntt"] / 1e3),
         "msm_only_pairs_per_s": n / (op_ms["msm_uniform"] / 1e3),
         "op_ms": op_ms,
