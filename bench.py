@@ -256,9 +256,18 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would precede the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the communicator is created: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     k = args.k
     n = 1 << k
     ext_k = k + 2
