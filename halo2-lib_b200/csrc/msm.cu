@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ of
         const u32 cnt = (e - 1) / L - s / L + 1, nseg = (cnt + BIG_SEG - 1) / BIG_SEG;
         if (j % gridDim.x == blockIdx.x) {
             XYZZ acc = XYZZ::identity();
-            for (u32 g = qid; g < nseg; g += 64) quad_add(acc, XYZZ::load(seg + seg_base + g));
+            for (u32 g = qid; g < nseg; g += 64) quad_add_nl(acc, XYZZ::load(seg + seg_base + g));
             acc = quad_block_sum(acc, sh);
             if (threadIdx.x == 0) acc.store(buckets + b);
             __syncthreads();
@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ of
 // ~(2^mh / 32 + 5) for the row/column sums (one warp each, shuffle tree), ~2*ml for the small scalar
 // multiplications lo * R_lo / hi * C_hi (one thread each) and ~10 for the block sums and the final doublings.
 // One CTA of 128 threads (32 lane-quads, quad.cuh) per row sum R_lo / column sum C_hi: every quad adds its
-// stride-32 share of the row (column), then the 32 quads are summed.  rc[set][0 .. 2^ml) = R, rc[set][2^ml ..) = C.
+// stride-32 share of the row (column), then the 32 quads are summed and the result is multiplied by its weight.
+// rc[set] = [ lo * R_lo (2^ml) | hi * C_hi (2^mh) | C_hi (2^mh) ].
 __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ buckets, int ml, int mh, u32 nsets,
                                                      XYZZ* __restrict__ rc) {
     __shared__ XYZZ sh[4];
@@ -348,7 +349,16 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ bu
         for (u32 lo = qid; lo < (1u << ml); lo += 32) quad_add(acc, XYZZ::load(base + ((size_t)hi << ml) + lo));
     }
     acc = quad_block_sum(acc, sh);
-    if (threadIdx.x == 0) acc.store(rc + (size_t)set * per_set + idx);
+    // quad 0 of warp 0 holds the sum: store it already multiplied by its weight (lo for a row, hi for a column) so
+    // that the final kernel only has plain sums left; the plain column sums are kept too (T = sum of all buckets)
+    if (threadIdx.x < 4) {
+        const bool is_row = idx < (1u << ml);
+        const u32 weight = is_row ? idx : idx - (1u << ml);
+        XYZZ* out = rc + (size_t)set * ((1u << ml) + 2 * (1u << mh));
+        if (!is_row && threadIdx.x == 0) acc.store(out + (1u << ml) + (1u << mh) + weight);
+        XYZZ w = quad_small_mul(acc, weight, is_row ? ml : mh);
+        if (threadIdx.x == 0) w.store(out + idx);
+    }
 }
 
 __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
@@ -367,12 +377,12 @@ __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
     z.store(o + 64);
 }
 
-// Weighted sums S_lo = sum_lo lo * R_lo, S_hi = sum_hi hi * C_hi and T = sum_hi C_hi, 64 points (one per lane-quad)
-// per CTA.  CTAs of a set: [0, sub_lo) -> kind 0 (lo, weighted), then sub_hi CTAs kind 1 (hi, weighted), then sub_hi
-// CTAs kind 2 (hi, plain).  The last CTA to finish adds the CTA partials, forms V_set = T + S_lo + 2^ml * S_hi, runs
-// Horner over the sets (`shift` doublings between consecutive sets; one set when the bases are tabulated) and
-// stores the Jacobian result.
-static constexpr int WQ = 64;  // quads (points) per CTA of k_weighted_final
+// S_lo = sum of rc[0 .. 2^ml), S_hi = sum of rc[2^ml .. 2^ml + 2^mh), T = sum of the plain column sums: plain sums of
+// 64 x 4 points per CTA (one lane-quad adds 4 of them).  CTAs of a set: [0, sub_lo) -> S_lo, then sub_hi CTAs S_hi, then
+// sub_hi CTAs T.  The last CTA to finish adds the CTA partials, forms V_set = T + S_lo + 2^ml * S_hi, runs Horner over
+// the sets (`shift` doublings between consecutive sets; one set when the bases are tabulated) and stores the
+// Jacobian result.
+static constexpr int WQ = 256;  // points per CTA of k_weighted_final (64 quads x 4)
 __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__ rc, int ml, int mh, u32 nsets, int shift,
                                                         XYZZ* __restrict__ parts, u32* __restrict__ done,
                                                         void* __restrict__ out) {
@@ -385,16 +395,12 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
     const u32 set = blockIdx.x / cta_per_set, c = blockIdx.x % cta_per_set;
     const u32 kind = c < sub_lo ? 0 : (c < sub_lo + sub_hi ? 1 : 2);
     const u32 sub = kind == 0 ? c : (kind == 1 ? c - sub_lo : c - sub_lo - sub_hi);
-    const u32 per_set = (1u << ml) + (1u << mh);
-    const XYZZ* src = rc + (size_t)set * per_set + (kind ? (1u << ml) : 0);
-    const int bits = kind ? mh : ml;
+    const u32 per_set = (1u << ml) + 2 * (1u << mh);
+    const XYZZ* src = rc + (size_t)set * per_set + (kind == 0 ? 0 : (kind == 1 ? (1u << ml) : (1u << ml) + (1u << mh)));
+    const u32 cnt = 1u << (kind ? mh : ml);
     const u32 qid = threadIdx.x >> 2;
-    const u32 j = sub * WQ + qid;
     XYZZ w = XYZZ::identity();
-    if (j < (1u << bits)) {
-        XYZZ p = XYZZ::load(src + j);
-        w = (kind == 2) ? p : quad_small_mul(p, j, bits);
-    }
+    for (u32 j = sub * WQ + qid; j < cnt && j < (sub + 1) * WQ; j += 64) quad_add_nl(w, XYZZ::load(src + j));
     w = quad_block_sum(w, sh);
     if (threadIdx.x == 0) w.store(parts + (size_t)set * cta_per_set + c);
     __threadfence();
@@ -410,15 +416,15 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
             const XYZZ* p = parts + (size_t)s0 * cta_per_set + (qid == 0 ? 0 : (qid == 1 ? sub_lo : sub_lo + sub_hi));
             const u32 cnt = qid == 0 ? sub_lo : sub_hi;
             XYZZ a = XYZZ::load(p);
-            for (u32 i = 1; i < cnt; i++) quad_add(a, XYZZ::load(p + i));
+            for (u32 i = 1; i < cnt; i++) quad_add_nl(a, XYZZ::load(p + i));
             if ((threadIdx.x & 3) == 0) a.store(comb + qid);
         }
         __syncthreads();
         if (qid == 0) {
             XYZZ v = XYZZ::load(comb + 1);  // S_hi
-            for (int d = 0; d < ml; d++) quad_dbl(v);
-            quad_add(v, XYZZ::load(comb + 0));  // + S_lo
-            quad_add(v, XYZZ::load(comb + 2));  // + T
+            for (int d = 0; d < ml; d++) quad_dbl_nl(v);
+            quad_add_nl(v, XYZZ::load(comb + 0));  // + S_lo
+            quad_add_nl(v, XYZZ::load(comb + 2));  // + T
             if (threadIdx.x == 0) v.store(vsets + s0);
         }
         __syncthreads();
@@ -426,8 +432,8 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
     if (qid == 0) {
         XYZZ total = XYZZ::load(vsets + nsets - 1);
         for (int s2 = (int)nsets - 2; s2 >= 0; s2--) {
-            for (int d = 0; d < shift; d++) quad_dbl(total);
-            quad_add(total, XYZZ::load(vsets + s2));
+            for (int d = 0; d < shift; d++) quad_dbl_nl(total);
+            quad_add_nl(total, XYZZ::load(vsets + s2));
         }
         if (threadIdx.x == 0) {
             store_jacobian(total, out);
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(256) k_g1_sum(const uint64_t* __restrict__ pts
     __shared__ XYZZ sh[8];
     const u32 qid = threadIdx.x >> 2;
     XYZZ acc = XYZZ::identity();
-    for (u32 i = qid; i < m; i += 64) quad_add(acc, xyzz_from_jacobian(pts + 12 * (size_t)i));
+    for (u32 i = qid; i < m; i += 64) quad_add_nl(acc, xyzz_from_jacobian(pts + 12 * (size_t)i));
     XYZZ r = quad_block_sum(acc, sh);
     if (threadIdx.x == 0) store_jacobian(r, out);
 }
@@ -586,10 +592,10 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     // bucket reduction: row/column sums of the 2^mh x 2^ml bucket grid, small scalar multiples, final combine
     const int m = c - 1, ml = (m + 1) / 2, mh = m - ml;
     H2B_REQUIRE(nsets <= 64, "msm: too many bucket sets");
-    const u32 per_set = (1u << ml) + (1u << mh);
+    const u32 per_set = (1u << ml) + (1u << mh);  // row + column sums (one CTA each)
     const u32 sub_lo = ((1u << ml) + WQ - 1) / WQ, sub_hi = ((1u << mh) + WQ - 1) / WQ;
     const u32 cta_per_set = sub_lo + 2 * sub_hi;
-    XYZZ* rc = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)nsets * per_set * sizeof(XYZZ));
+    XYZZ* rc = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)nsets * (per_set + (1u << mh)) * sizeof(XYZZ));
     char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)nsets * cta_per_set * sizeof(XYZZ) + 256);
     XYZZ* parts = (XYZZ*)rb;
     u32* done = (u32*)(rb + (size_t)nsets * cta_per_set * sizeof(XYZZ));

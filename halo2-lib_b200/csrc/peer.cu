@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_g1_allreduce(PeerPtrs peers, int rank, 
             if (z.is_zero()) continue;
             p.zz = z.sqr();
             p.zzz = p.zz * z;
-            quad_add(acc, p);
+            quad_add_nl(acc, p);
         }
         if ((t & 3) == 0) store_jacobian_xyzz(acc, pts + 12 * q);
     }

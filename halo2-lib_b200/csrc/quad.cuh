@@ -98,6 +98,12 @@ __device__ __forceinline__ void quad_add(XYZZ& acc, const XYZZ& q) {
     acc.y = t0 - t1;
 }
 
+// Out-of-line copies for code that runs only a handful of times per launch (block sums, the final combine): every
+// inlined call site would be ~1200 cold instructions that a lone warp has to pull through the instruction cache
+// (k_weighted_final: 123 us inlined, 87 us with these); hot loops keep the inlined forms above.
+static __device__ __noinline__ void quad_add_nl(XYZZ& acc, const XYZZ& q) { quad_add(acc, q); }
+static __device__ __noinline__ void quad_dbl_nl(XYZZ& p) { quad_dbl(p); }
+
 // value of the quad `delta` quads further up the warp (all 32 lanes must call; operands replicated per quad)
 __device__ __forceinline__ XYZZ quad_shfl_down(const XYZZ& v, int delta_quads) {
     XYZZ r;
@@ -117,7 +123,7 @@ __device__ __forceinline__ XYZZ quad_warp_sum(XYZZ v) {
     for (int dq = 4; dq >= 1; dq >>= 1) {
         __syncwarp();
         XYZZ o = quad_shfl_down(v, dq);
-        quad_add(v, o);
+        quad_add_nl(v, o);
     }
     __syncwarp();
     return v;
@@ -134,7 +140,7 @@ __device__ __forceinline__ XYZZ quad_block_sum(XYZZ v, XYZZ* sh) {
     if (wid == 0) {
         // quad k of warp 0 takes the results of warps k, k+8, k+16, k+24 (serial), then the 8 quads are summed
         const int qid = lane >> 2;
-        for (int w = qid; w < nw; w += 8) quad_add(r, XYZZ::load(sh + w));
+        for (int w = qid; w < nw; w += 8) quad_add_nl(r, XYZZ::load(sh + w));
         r = quad_warp_sum(r);
     }
     return r;
@@ -145,8 +151,8 @@ __device__ __forceinline__ XYZZ quad_small_mul(const XYZZ& p, u32 k, int bits) {
     XYZZ acc = XYZZ::identity();
 #pragma unroll 1
     for (int b = bits - 1; b >= 0; b--) {
-        quad_dbl(acc);
-        if ((k >> b) & 1) quad_add(acc, p);
+        quad_dbl_nl(acc);
+        if ((k >> b) & 1) quad_add_nl(acc, p);
     }
     return acc;
 }
