@@ -146,6 +146,24 @@ def test_msm_hot_bucket_and_sharded(ctx, h2b):
     assert np.array_equal(norm(ctx, ctx.g1_sum(np.stack(parts))), want)
 
 
+def test_msm_odd_shard_and_long_batch(ctx, h2b):
+    """a shard that is not a power of two (begin/count arbitrary) and a batch longer than twice the number of lanes"""
+    k = 10
+    n = 1 << k
+    rng = np.random.default_rng(77)
+    B = _bases(ctx, n, a0=9, delta=4)
+    begin, count = 100, 777
+    p = h2b.ParamsKZG(ctx, k, g=B, g_lagrange=B, begin=begin, count=count)
+    cols = [mont(rand_ints(rng, count, R) if j % 2 == 0 else witness_like_ints(rng, count), R) for j in range(7)]
+    outs = p.commit_batch([j % 2 for j in range(7)], cols)
+    for j in range(7):
+        assert np.array_equal(norm(ctx, outs[j]), orc.msm_pippenger(cols[j], B[begin:begin + count]))
+    # wrong length is rejected, not mis-indexed
+    with pytest.raises(h2b.H2BError):
+        p.commit(cols[0][:-1])
+    p.close()
+
+
 def test_msm_closed_form_large(ctx, h2b):
     # size-independent property at 2^17: bases a_i*G (a_i = a0 + i*delta) => MSM == (sum s_i a_i mod r)*G
     k = 17
