@@ -117,7 +117,7 @@ struct SmemFr {  // two 128-bit planes
 };
 
 template <bool LAST>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(PassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
     extern __shared__ uint4 smem_raw[];
     const int r = a.r, cwl = a.cw_log;
     const u32 R = 1u << r, CW = 1u << cwl, TILE = R << cwl;
@@ -157,9 +157,39 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(PassArgs a) {
     }
     __syncthreads();
 
-    // ---- r radix-2 DIF stages inside the tile
+    // ---- r radix-2 DIF stages inside the tile, two at a time: a thread takes the 4 elements u, u+q, u+2q, u+3q
+    // (q = quarter of the current block), does the stage-s butterflies (u, u+2q), (u+q, u+3q) and the stage-(s+1)
+    // butterflies (u, u+q), (u+2q, u+3q) in registers: half the shared-memory round trips and barriers.
     const u32 NBF = TILE >> 1;
-    for (int s = 0; s < r; s++) {
+    int s = 0;
+    for (; s + 1 < r; s += 2) {
+        const u32 half = 1u << (r - 1 - s), quarter = half >> 1;
+        for (u32 q4 = tid; q4 < (NBF >> 1); q4 += NTT_THREADS) {
+            u32 c, pi;
+            if (LAST) { pi = q4 & ((R >> 2) - 1); c = q4 >> (r - 2); } else { c = q4 & (CW - 1); pi = q4 >> cwl; }
+            const u32 j = pi & (quarter - 1), grp = pi >> (r - 2 - s);
+            const u32 u = (grp << (r - s)) + j;
+            const u32 i0 = sidx(u, c), i1 = sidx(u + quarter, c), i2 = sidx(u + half, c), i3 = sidx(u + half + quarter, c);
+            Fr x0 = sm.ld(i0), x1 = sm.ld(i1), x2 = sm.ld(i2), x3 = sm.ld(i3);
+            // stage s: (x0, x2) twiddle index j, (x1, x3) twiddle index j + quarter
+            Fr d02 = x0 - x2, d13 = (x1 - x3) * Fr::load_nc(a.wtab + ((size_t)(j + quarter) << s));
+            if (j) d02 = d02 * Fr::load_nc(a.wtab + ((size_t)j << s));
+            Fr s02 = x0 + x2, s13 = x1 + x3;
+            // stage s+1: (s02, s13) and (d02, d13), both with twiddle index j
+            Fr e = s02 - s13, f = d02 - d13;
+            if (j) {
+                const Fr w2 = Fr::load_nc(a.wtab + ((size_t)j << (s + 1)));
+                e = e * w2;
+                f = f * w2;
+            }
+            sm.st(i0, s02 + s13);
+            sm.st(i1, e);
+            sm.st(i2, d02 + d13);
+            sm.st(i3, f);
+        }
+        __syncthreads();
+    }
+    for (; s < r; s++) {
         const u32 half = 1u << (r - 1 - s);
         for (u32 q = tid; q < NBF; q += NTT_THREADS) {
             u32 c, pi;
