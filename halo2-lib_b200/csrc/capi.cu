@@ -673,7 +673,7 @@ int h2b_flex_gate_fold(h2b_ctx* ctx, const uint64_t* q_ext, const uint64_t* a_ex
 // ------------------------------------------------------------------------------------------------ test hook
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
     return guarded(ctx, [&] {
-        H2B_REQUIRE(a && out && (b || op > 2) && (field == 0 || field == 1) && op >= 0 && op <= 5, "field_op: bad argument");
+        H2B_REQUIRE(a && out && (b || op > 2) && (field == 0 || field == 1) && op >= 0 && op <= 6, "field_op: bad argument");
         if (n == 0) return;
         char* d = (char*)ctx->get(WS_ASSIGN_IN, 3 * n * 32);
         H2B_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));

@@ -506,6 +506,7 @@ __global__ void __launch_bounds__(128) k_field_op(int op, const uint64_t* __rest
         case 2: r = x - y; break;
         case 3: r = x.inv(); break;
         case 4: r = x.from_mont(); break;
+        case 6: r = x.sqr(); break;
         default: r = x.to_mont(); break;
     }
     r.store(out + 4 * (size_t)i);

@@ -38,6 +38,8 @@ def test_field_ops(ctx, which, m):
     assert np.array_equal(ctx.field_op(which, 1, A, B), orc.f_add(which, A, B))
     assert np.array_equal(ctx.field_op(which, 2, A, B), orc.f_sub(which, A, B))
     assert np.array_equal(ctx.field_op(which, 4, A), orc.from_mont(which, A))
+    assert np.array_equal(ctx.field_op(which, 6, A), orc.f_mul(which, A, A))  # dedicated squaring
+    assert np.array_equal(ctx.field_op(which, 6, B), orc.f_mul(which, B, B))
     assert np.array_equal(ctx.field_op(which, 5, ints_to_limbs(a)), A)
     assert np.array_equal(ctx.field_op(which, 3, A[:300]), orc.f_inv(which, A[:300]))
     # products of edge x edge (carry patterns)
