@@ -15,3 +15,13 @@ from .host import (  # noqa: F401
     assign_lookups,
     omega,
 )
+from .evaluation import (  # noqa: F401,E402
+    GraphEvaluator,
+    BoundGraph,
+    quotient_graph,
+    permutation_fold,
+    lookup_fold,
+    eval_polynomial,
+    kate_division,
+    poly_lincomb,
+)

@@ -17,6 +17,26 @@ BASIS_MONOMIAL, BASIS_LAGRANGE = 0, 1
 _vp, _sz, _u32, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
 _u64p = C.POINTER(C.c_uint64)
 
+
+
+class Graph(C.Structure):
+    """h2b_graph (include/h2b200.h): a GraphEvaluator program plus its column tables and challenges."""
+    _fields_ = [
+        ("program", C.POINTER(C.c_uint32)), ("program_words", C.c_size_t),
+        ("n_calculations", C.c_uint32), ("result", C.c_uint32),
+        ("constants", C.c_void_p), ("n_constants", C.c_size_t),
+        ("rotations", C.POINTER(C.c_int32)), ("n_rotations", C.c_size_t),
+        ("fixed", C.POINTER(C.c_void_p)), ("n_fixed", C.c_size_t),
+        ("advice", C.POINTER(C.c_void_p)), ("n_advice", C.c_size_t),
+        ("instance", C.POINTER(C.c_void_p)), ("n_instance", C.c_size_t),
+        ("challenges", C.c_void_p), ("n_challenges", C.c_size_t),
+        ("beta", C.c_uint64 * 4), ("gamma", C.c_uint64 * 4), ("theta", C.c_uint64 * 4), ("y", C.c_uint64 * 4),
+    ]
+
+
+_gp = C.POINTER(Graph)
+_vpp = C.POINTER(C.c_void_p)
+
 # name -> (restype, argtypes)
 SIGNATURES = {
     "h2b_version": (C.c_char_p, []),
@@ -73,6 +93,18 @@ SIGNATURES = {
     "h2b_grand_product_fr_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "h2b_flex_gate_fold": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "h2b_flex_gate_fold_dev": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "h2b_quotient_graph": (_int, [_vp, _gp, _u32, _u32, _vp]),
+    "h2b_quotient_graph_dev": (_int, [_vp, _gp, _u32, _u32, _vp]),
+    "h2b_permutation_fold": (_int, [_vp, _vpp, _sz, _vpp, _vpp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
+    "h2b_permutation_fold_dev": (_int, [_vp, _vpp, _sz, _vpp, _vpp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
+    "h2b_lookup_fold": (_int, [_vp, _gp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "h2b_lookup_fold_dev": (_int, [_vp, _gp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "h2b_eval_polynomial": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "h2b_eval_polynomial_dev": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "h2b_kate_division": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "h2b_kate_division_dev": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "h2b_poly_lincomb": (_int, [_vp, _vpp, _vp, _sz, _sz, _vp]),
+    "h2b_poly_lincomb_dev": (_int, [_vp, _vpp, _vp, _sz, _sz, _vp]),
     "h2b_test_field_op": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp]),
 }
 

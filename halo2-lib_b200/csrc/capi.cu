@@ -670,6 +670,184 @@ int h2b_flex_gate_fold(h2b_ctx* ctx, const uint64_t* q_ext, const uint64_t* a_ex
     });
 }
 
+// ------------------------------------------------------------------------------------------------ quotient (general)
+namespace {
+// stages host columns of `bytes` bytes each, back to back, in one workspace slot
+struct ColumnStager {
+    h2b_ctx* ctx;
+    char* base;
+    size_t bytes, used = 0, cap;
+    ColumnStager(h2b_ctx* c, int slot, size_t count, size_t col_bytes) : ctx(c), bytes(col_bytes), cap(count) {
+        base = (char*)c->get(slot, count * col_bytes);
+    }
+    void* put(const void* host) {
+        H2B_REQUIRE(host, "quotient: null column");
+        H2B_REQUIRE(used < cap, "quotient: staging overflow");
+        char* d = base + (used++) * bytes;
+        H2B_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return d;
+    }
+};
+struct StagedGraph {
+    h2b_graph g;
+    std::vector<const void*> fixed, advice, instance;
+    StagedGraph(const h2b_graph* src, ColumnStager& st) : g(*src) {
+        H2B_REQUIRE((src->fixed || !src->n_fixed) && (src->advice || !src->n_advice) && (src->instance || !src->n_instance), "graph: null table");
+        for (size_t i = 0; i < src->n_fixed; i++) fixed.push_back(st.put(src->fixed[i]));
+        for (size_t i = 0; i < src->n_advice; i++) advice.push_back(st.put(src->advice[i]));
+        for (size_t i = 0; i < src->n_instance; i++) instance.push_back(st.put(src->instance[i]));
+        g.fixed = fixed.data();
+        g.advice = advice.data();
+        g.instance = instance.data();
+    }
+};
+size_t graph_columns(const h2b_graph* g) {
+    H2B_REQUIRE(g, "graph: null pointer");
+    return g->n_fixed + g->n_advice + g->n_instance;
+}
+}  // namespace
+
+int h2b_quotient_graph_dev(h2b_ctx* ctx, const h2b_graph* graph, uint32_t k, uint32_t ext_k, void* d_values) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(graph && d_values, "quotient_graph: null pointer");
+        quotient_graph_run(ctx, graph, k, ext_k, d_values);
+    });
+}
+int h2b_quotient_graph(h2b_ctx* ctx, const h2b_graph* graph, uint32_t k, uint32_t ext_k, uint64_t* values) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(graph && values, "quotient_graph: null pointer");
+        H2B_REQUIRE(ext_k >= k && ext_k <= 28, "quotient: extended_k out of range");
+        const size_t bytes = ((size_t)1 << ext_k) * 32;
+        ColumnStager st(ctx, WS_NTT_A, graph_columns(graph) + 1, bytes);
+        StagedGraph sg(graph, st);
+        void* d_values = st.put(values);
+        quotient_graph_run(ctx, &sg.g, k, ext_k, d_values);
+        H2B_CUDA(cudaMemcpyAsync(values, d_values, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_lookup_fold_dev(h2b_ctx* ctx, const h2b_graph* graph, const void* d_z, const void* d_permuted_input,
+                        const void* d_permuted_table, const void* d_l0, const void* d_l_last, const void* d_l_active, uint32_t k,
+                        uint32_t ext_k, void* d_values) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(graph && d_z && d_permuted_input && d_permuted_table && d_l0 && d_l_last && d_l_active && d_values, "lookup_fold: null pointer");
+        lookup_fold_run(ctx, graph, d_z, d_permuted_input, d_permuted_table, d_l0, d_l_last, d_l_active, k, ext_k, d_values);
+    });
+}
+int h2b_lookup_fold(h2b_ctx* ctx, const h2b_graph* graph, const uint64_t* z, const uint64_t* permuted_input,
+                    const uint64_t* permuted_table, const uint64_t* l0, const uint64_t* l_last, const uint64_t* l_active, uint32_t k,
+                    uint32_t ext_k, uint64_t* values) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(graph && values, "lookup_fold: null pointer");
+        H2B_REQUIRE(ext_k >= k && ext_k <= 28, "quotient: extended_k out of range");
+        const size_t bytes = ((size_t)1 << ext_k) * 32;
+        ColumnStager st(ctx, WS_NTT_A, graph_columns(graph) + 7, bytes);
+        StagedGraph sg(graph, st);
+        void *dz = st.put(z), *dpi = st.put(permuted_input), *dpt = st.put(permuted_table), *d0 = st.put(l0), *dl = st.put(l_last),
+             *da = st.put(l_active), *dv = st.put(values);
+        lookup_fold_run(ctx, &sg.g, dz, dpi, dpt, d0, dl, da, k, ext_k, dv);
+        H2B_CUDA(cudaMemcpyAsync(values, dv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_permutation_fold_dev(h2b_ctx* ctx, const void* const* d_z, size_t n_sets, const void* const* d_columns, const void* const* d_sigma,
+                             size_t n_cols, size_t chunk_len, const void* d_l0, const void* d_l_last, const void* d_l_active,
+                             const uint64_t beta[4], const uint64_t gamma[4], const uint64_t y[4], uint32_t blinding_factors, uint32_t k,
+                             uint32_t ext_k, void* d_values) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(n_sets == 0 || (d_z && d_columns && d_sigma && d_l0 && d_l_last && d_l_active && d_values), "permutation_fold: null pointer");
+        H2B_REQUIRE(beta && gamma && y, "permutation_fold: null challenge");
+        permutation_fold_run(ctx, d_z, n_sets, d_columns, d_sigma, n_cols, chunk_len, d_l0, d_l_last, d_l_active, beta, gamma, y,
+                             blinding_factors, k, ext_k, d_values);
+    });
+}
+int h2b_permutation_fold(h2b_ctx* ctx, const uint64_t* const* z, size_t n_sets, const uint64_t* const* columns, const uint64_t* const* sigma,
+                         size_t n_cols, size_t chunk_len, const uint64_t* l0, const uint64_t* l_last, const uint64_t* l_active,
+                         const uint64_t beta[4], const uint64_t gamma[4], const uint64_t y[4], uint32_t blinding_factors, uint32_t k,
+                         uint32_t ext_k, uint64_t* values) {
+    return guarded(ctx, [&] {
+        if (n_sets == 0) return;
+        H2B_REQUIRE(z && columns && sigma && values && beta && gamma && y, "permutation_fold: null pointer");
+        H2B_REQUIRE(ext_k >= k && ext_k <= 28, "quotient: extended_k out of range");
+        const size_t bytes = ((size_t)1 << ext_k) * 32;
+        ColumnStager st(ctx, WS_NTT_A, n_sets + 2 * n_cols + 4, bytes);
+        std::vector<const void*> dz, dc, ds;
+        for (size_t i = 0; i < n_sets; i++) dz.push_back(st.put(z[i]));
+        for (size_t i = 0; i < n_cols; i++) dc.push_back(st.put(columns[i]));
+        for (size_t i = 0; i < n_cols; i++) ds.push_back(st.put(sigma[i]));
+        void *d0 = st.put(l0), *dl = st.put(l_last), *da = st.put(l_active), *dv = st.put(values);
+        permutation_fold_run(ctx, dz.data(), n_sets, dc.data(), ds.data(), n_cols, chunk_len, d0, dl, da, beta, gamma, y, blinding_factors,
+                             k, ext_k, dv);
+        H2B_CUDA(cudaMemcpyAsync(values, dv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ opening arithmetic
+int h2b_eval_polynomial_dev(h2b_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t x[4], uint64_t out[4]) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((d_coeffs || n == 0) && x && out, "eval_polynomial: null pointer");
+        void* d_out = ctx->get(WS_OUT, 32);
+        eval_polynomial_run(ctx, d_coeffs, n, x, d_out);
+        uint64_t* bounce = (uint64_t*)ctx->get_pinned(0, 4096);
+        H2B_CUDA(cudaMemcpyAsync(bounce, d_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(out, bounce, 32);
+    });
+}
+int h2b_eval_polynomial(h2b_ctx* ctx, const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((coeffs || n == 0) && x && out, "eval_polynomial: null pointer");
+        void* d = ctx->get(WS_ASSIGN_IN, n * 32);
+        if (n) H2B_CUDA(cudaMemcpyAsync(d, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        void* d_out = ctx->get(WS_OUT, 32);
+        eval_polynomial_run(ctx, d, n, x, d_out);
+        uint64_t* bounce = (uint64_t*)ctx->get_pinned(0, 4096);
+        H2B_CUDA(cudaMemcpyAsync(bounce, d_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(out, bounce, 32);
+    });
+}
+int h2b_kate_division_dev(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t z[4], void* d_q) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_a && z && (d_q || n <= 1), "kate_division: null pointer");
+        H2B_REQUIRE(d_a != d_q, "kate_division: q must not alias a");
+        kate_division_run(ctx, d_a, n, z, d_q);
+    });
+}
+int h2b_kate_division(h2b_ctx* ctx, const uint64_t* a, size_t n, const uint64_t z[4], uint64_t* q) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(a && z && (q || n <= 1), "kate_division: null pointer");
+        H2B_REQUIRE(n >= 1, "kate_division: empty polynomial");
+        if (n == 1) return;
+        char* d = (char*)ctx->get(WS_ASSIGN_IN, 2 * n * 32);
+        H2B_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        kate_division_run(ctx, d, n, z, d + n * 32);
+        H2B_CUDA(cudaMemcpyAsync(q, d + n * 32, (n - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_poly_lincomb_dev(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* scalars, size_t m, size_t n, void* d_out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_polys && scalars && (d_out || n == 0), "poly_lincomb: null pointer");
+        poly_lincomb_run(ctx, d_polys, scalars, m, n, d_out);
+    });
+}
+int h2b_poly_lincomb(h2b_ctx* ctx, const uint64_t* const* polys, const uint64_t* scalars, size_t m, size_t n, uint64_t* out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(polys && scalars && (out || n == 0), "poly_lincomb: null pointer");
+        H2B_REQUIRE(m >= 1 && m <= 32, "poly_lincomb: 1..32 polynomials per call");
+        if (n == 0) return;
+        ColumnStager st(ctx, WS_NTT_A, m + 1, n * 32);
+        std::vector<const void*> dp;
+        for (size_t j = 0; j < m; j++) dp.push_back(st.put(polys[j]));
+        char* d_out = st.base + m * st.bytes;
+        poly_lincomb_run(ctx, dp.data(), scalars, m, n, d_out);
+        H2B_CUDA(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
 // ------------------------------------------------------------------------------------------------ test hook
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
     return guarded(ctx, [&] {

@@ -130,8 +130,8 @@ class Context:
 
     def flex_gate_fold(self, q_ext, a_ext, y, k: int, ext_k: int, acc) -> np.ndarray:
         """acc*y + q*(a + a(w X)*a(w^2 X) - a(w^3 X)) on the extended domain (halo2-base flex_gate/mod.rs:80-91)"""
-        q, a, acc = _u64(q_ext, 4), _u64(a_ext, 4), _u64(acc, 4).copy()
-        self.check(lib.h2b_flex_gate_fold(self.h, _ptr(q), _ptr(a), _ptr(_u64(y, 4)), k, ext_k, _ptr(acc)))
+        q, a, acc, yy = _u64(q_ext, 4), _u64(a_ext, 4), _u64(acc, 4).copy(), _u64(y, 4)
+        self.check(lib.h2b_flex_gate_fold(self.h, _ptr(q), _ptr(a), _ptr(yy), k, ext_k, _ptr(acc)))
         return acc
 
     def eval_rational(self, num, den) -> np.ndarray:

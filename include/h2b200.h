@@ -190,6 +190,98 @@ int h2b_flex_gate_fold(h2b_ctx* ctx, const uint64_t* q_ext, const uint64_t* a_ex
 int h2b_flex_gate_fold_dev(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k,
                            uint32_t ext_k, void* d_acc);
 
+/* ---- quotient evaluation, general form: halo2-axiom 0.5.3 `plonk/evaluation.rs`
+ * (`Evaluator::evaluate_h`; not vendored — restated from the upstream algorithm, parity unpinned like the rest of L0).
+ * All columns are evaluations on the extended coset domain (2^ext_k x [u64;4], outputs of coeff_to_extended); a
+ * rotation by r rows of the 2^k domain is the index (i + r * 2^(ext_k-k)) mod 2^ext_k (`get_rotation_idx`).
+ *
+ * h2b_graph mirrors `GraphEvaluator`: a straight-line program whose calculation number t writes intermediate t.
+ *   value source word:  kind | index << 4 | rotation_slot << 20
+ *   program:            H2B_CALC_* opcode followed by its value-source words;
+ *                       H2B_CALC_HORNER: start, factor, n_parts, parts[n_parts]  ->  ((start*f + p0)*f + p1)...
+ * The `_dev` entry points take column tables that are HOST arrays of DEVICE pointers; the host-pointer forms take
+ * host columns and stage them (use them for tests / small circuits — the prover keeps these columns resident). */
+#define H2B_SRC_CONSTANT 0u
+#define H2B_SRC_INTERMEDIATE 1u
+#define H2B_SRC_FIXED 2u
+#define H2B_SRC_ADVICE 3u
+#define H2B_SRC_INSTANCE 4u
+#define H2B_SRC_CHALLENGE 5u
+#define H2B_SRC_BETA 6u
+#define H2B_SRC_GAMMA 7u
+#define H2B_SRC_THETA 8u
+#define H2B_SRC_Y 9u
+#define H2B_SRC_PREVIOUS 10u
+#define H2B_SRC(kind, index, rot_slot) ((uint32_t)(kind) | ((uint32_t)(index) << 4) | ((uint32_t)(rot_slot) << 20))
+#define H2B_CALC_ADD 0u
+#define H2B_CALC_SUB 1u
+#define H2B_CALC_MUL 2u
+#define H2B_CALC_SQUARE 3u
+#define H2B_CALC_DOUBLE 4u
+#define H2B_CALC_NEGATE 5u
+#define H2B_CALC_HORNER 6u
+#define H2B_CALC_STORE 7u
+#define H2B_GRAPH_MAX_CALCULATIONS 64
+typedef struct h2b_graph {
+    const uint32_t* program;     /* host memory */
+    size_t program_words;
+    uint32_t n_calculations;     /* <= H2B_GRAPH_MAX_CALCULATIONS */
+    uint32_t result;             /* value source word of the result */
+    const uint64_t* constants;   /* host, n_constants x 4 (Montgomery) */
+    size_t n_constants;
+    const int32_t* rotations;    /* host, rotation of each rotation slot, in rows of the 2^k domain */
+    size_t n_rotations;
+    const void* const* fixed;    /* column tables: n_* pointers to 2^ext_k x 4 u64 */
+    size_t n_fixed;
+    const void* const* advice;
+    size_t n_advice;
+    const void* const* instance;
+    size_t n_instance;
+    const uint64_t* challenges;  /* host, n_challenges x 4 */
+    size_t n_challenges;
+    uint64_t beta[4], gamma[4], theta[4], y[4];
+} h2b_graph;
+/* custom gates: values[i] <- graph(previous = values[i]) for every row of the extended domain */
+int h2b_quotient_graph(h2b_ctx* ctx, const h2b_graph* graph, uint32_t k, uint32_t ext_k, uint64_t* values);
+int h2b_quotient_graph_dev(h2b_ctx* ctx, const h2b_graph* graph, uint32_t k, uint32_t ext_k, void* d_values);
+/* permutation argument terms of evaluate_h, folded with y in halo2's order:
+ *   l_0 (1 - z_0);  l_last (z_last^2 - z_last);  l_0 (z_s - z_{s-1}(omega^last X)) for s >= 1;
+ *   l_active (z_s(omega X) prod_j (v_j + beta sigma_j + gamma) - z_s prod_j (v_j + delta^j beta X + gamma)) per set,
+ * sets = chunks of `chunk_len` (= degree - 2) permutation columns; last = -(blinding_factors + 1).
+ * z: n_sets product cosets; columns / sigma: n_cols value cosets and permutation-polynomial cosets in the
+ * permutation's column order.  No-op when n_sets == 0, as in halo2. */
+int h2b_permutation_fold(h2b_ctx* ctx, const uint64_t* const* z, size_t n_sets, const uint64_t* const* columns,
+                         const uint64_t* const* sigma, size_t n_cols, size_t chunk_len, const uint64_t* l0,
+                         const uint64_t* l_last, const uint64_t* l_active, const uint64_t beta[4], const uint64_t gamma[4],
+                         const uint64_t y[4], uint32_t blinding_factors, uint32_t k, uint32_t ext_k, uint64_t* values);
+int h2b_permutation_fold_dev(h2b_ctx* ctx, const void* const* d_z, size_t n_sets, const void* const* d_columns,
+                             const void* const* d_sigma, size_t n_cols, size_t chunk_len, const void* d_l0,
+                             const void* d_l_last, const void* d_l_active, const uint64_t beta[4], const uint64_t gamma[4],
+                             const uint64_t y[4], uint32_t blinding_factors, uint32_t k, uint32_t ext_k, void* d_values);
+/* one lookup argument's five terms; `graph` yields (compressed input + beta)(compressed table + gamma) per row
+ * (its beta / gamma / theta / y are the ones used for the fold):
+ *   l_0 (1 - z); l_last (z^2 - z); l_active (z(omega X)(a' + beta)(s' + gamma) - z * graph); l_0 (a' - s');
+ *   l_active (a' - s')(a' - a'(omega^-1 X)) */
+int h2b_lookup_fold(h2b_ctx* ctx, const h2b_graph* graph, const uint64_t* z, const uint64_t* permuted_input,
+                    const uint64_t* permuted_table, const uint64_t* l0, const uint64_t* l_last, const uint64_t* l_active,
+                    uint32_t k, uint32_t ext_k, uint64_t* values);
+int h2b_lookup_fold_dev(h2b_ctx* ctx, const h2b_graph* graph, const void* d_z, const void* d_permuted_input,
+                        const void* d_permuted_table, const void* d_l0, const void* d_l_last, const void* d_l_active,
+                        uint32_t k, uint32_t ext_k, void* d_values);
+
+/* ---- opening arithmetic: halo2-axiom 0.5.3 `arithmetic::{eval_polynomial, kate_division}`
+ * and the polynomial linear combinations of `poly/kzg/multiopen/shplonk/prover.rs` ------------------------------- */
+/* out = sum_i coeffs[i] * x^i */
+int h2b_eval_polynomial(h2b_ctx* ctx, const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
+int h2b_eval_polynomial_dev(h2b_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
+/* quotient of a(X) (n coefficients, n >= 1) by (X - z): q has n - 1 coefficients, the remainder a(z) is dropped,
+ * as `kate_division(a, z)` does. */
+int h2b_kate_division(h2b_ctx* ctx, const uint64_t* a, size_t n, const uint64_t z[4], uint64_t* q);
+int h2b_kate_division_dev(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t z[4], void* d_q);
+/* out[i] = sum_j scalars[j] * polys[j][i], i < n, j < m (1 <= m <= 32); out may alias one of the inputs */
+int h2b_poly_lincomb(h2b_ctx* ctx, const uint64_t* const* polys, const uint64_t* scalars, size_t m, size_t n, uint64_t* out);
+int h2b_poly_lincomb_dev(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* scalars, size_t m, size_t n, void* d_out);
+
 /* ---- test hooks (field arithmetic of the kernels, element-wise on the device) --------------------- */
 /* field: 0 = Fq, 1 = Fr; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 from_mont(a), 5 to_mont(a), 6 sqr(a) */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);

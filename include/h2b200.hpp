@@ -197,4 +197,20 @@ inline std::vector<std::vector<Fr>> assign_lookups(const Context& ctx, const std
     return cols;
 }
 
+// arithmetic::eval_polynomial(poly, point)
+inline Fr eval_polynomial(const Context& ctx, const std::vector<Fr>& poly, const Fr& point) {
+    Fr out{};
+    ctx.check(h2b_eval_polynomial(ctx.raw(), reinterpret_cast<const uint64_t*>(poly.data()), poly.size(),
+                                  reinterpret_cast<const uint64_t*>(&point), reinterpret_cast<uint64_t*>(&out)));
+    return out;
+}
+
+// arithmetic::kate_division(a, b): quotient of a(X) by (X - b), remainder dropped
+inline std::vector<Fr> kate_division(const Context& ctx, const std::vector<Fr>& a, const Fr& b) {
+    std::vector<Fr> q(a.empty() ? 0 : a.size() - 1);
+    ctx.check(h2b_kate_division(ctx.raw(), reinterpret_cast<const uint64_t*>(a.data()), a.size(), reinterpret_cast<const uint64_t*>(&b),
+                                reinterpret_cast<uint64_t*>(q.data())));
+    return q;
+}
+
 }  // namespace h2b

@@ -573,6 +573,189 @@ void orc_flex_gate_fold(const u64 *q, const u64 *a, const u64 *y, unsigned k, un
         f_add(&FR, acc + 4 * i, t, g);
     }
 }
+/* ---- general quotient evaluation: halo2-axiom 0.5.3 plonk/evaluation.rs (`GraphEvaluator::evaluate`, `Evaluator::evaluate_h`;
+ * not vendored — restated from the upstream algorithm; the single gate and lookup halo2-lib feeds it are
+ * halo2-base/src/gates/flex_gate/mod.rs:80-91 and gates/range/mod.rs:131-140).  Row loops are written the way the
+ * Rust code walks them (running `beta_term`, sequential Horner), not the way the CUDA kernels do. */
+typedef struct {
+    const uint32_t *program; size_t program_words; uint32_t n_calculations; uint32_t result;
+    const u64 *constants; size_t n_constants;
+    const int32_t *rotations; size_t n_rotations;
+    const u64 *const *fixed; size_t n_fixed;
+    const u64 *const *advice; size_t n_advice;
+    const u64 *const *instance; size_t n_instance;
+    const u64 *challenges; size_t n_challenges;
+    u64 beta[4], gamma[4], theta[4], y[4];
+} orc_graph; /* same field order as h2b_graph, so tests can pass one ctypes structure to both sides */
+
+static size_t rotation_idx(size_t idx, int rot, unsigned rot_scale_log, size_t isize) { /* get_rotation_idx */
+    long long v = (long long)idx + (long long)rot * ((long long)1 << rot_scale_log);
+    long long m = (long long)isize;
+    v %= m; if (v < 0) v += m;
+    return (size_t)v;
+}
+static void graph_source(const orc_graph *g, uint32_t src, size_t idx, unsigned rs, size_t isize, const u64 *prev, const u64 *inter, u64 out[4]) {
+    uint32_t kind = src & 15u, index = (src >> 4) & 0xffffu, slot = src >> 20;
+    const u64 *p;
+    switch (kind) {
+        case 0: p = g->constants + 4 * (size_t)index; break;
+        case 1: p = inter + 4 * (size_t)index; break;
+        case 2: p = g->fixed[index] + 4 * rotation_idx(idx, g->rotations[slot], rs, isize); break;
+        case 3: p = g->advice[index] + 4 * rotation_idx(idx, g->rotations[slot], rs, isize); break;
+        case 4: p = g->instance[index] + 4 * rotation_idx(idx, g->rotations[slot], rs, isize); break;
+        case 5: p = g->challenges + 4 * (size_t)index; break;
+        case 6: p = g->beta; break;
+        case 7: p = g->gamma; break;
+        case 8: p = g->theta; break;
+        case 9: p = g->y; break;
+        default: p = prev; break;
+    }
+    memcpy(out, p, 32);
+}
+static void graph_row(const orc_graph *g, size_t idx, unsigned rs, size_t isize, const u64 *prev, u64 *inter, u64 out[4]) {
+    const uint32_t *pc = g->program;
+    for (uint32_t t = 0; t < g->n_calculations; t++) {
+        uint32_t op = *pc++;
+        u64 a[4], b[4], r[4];
+        if (op == 6) { /* Horner(start, parts, factor) */
+            graph_source(g, pc[0], idx, rs, isize, prev, inter, r);
+            graph_source(g, pc[1], idx, rs, isize, prev, inter, b);
+            uint32_t np = pc[2];
+            pc += 3;
+            for (uint32_t j = 0; j < np; j++) {
+                graph_source(g, *pc++, idx, rs, isize, prev, inter, a);
+                f_mul(&FR, r, r, b);
+                f_add(&FR, r, r, a);
+            }
+        } else {
+            graph_source(g, *pc++, idx, rs, isize, prev, inter, a);
+            if (op <= 2) graph_source(g, *pc++, idx, rs, isize, prev, inter, b);
+            switch (op) {
+                case 0: f_add(&FR, r, a, b); break;
+                case 1: f_sub(&FR, r, a, b); break;
+                case 2: f_mul(&FR, r, a, b); break;
+                case 3: f_mul(&FR, r, a, a); break;
+                case 4: f_add(&FR, r, a, a); break;
+                case 5: f_neg(&FR, r, a); break;
+                default: memcpy(r, a, 32); break;
+            }
+        }
+        memcpy(inter + 4 * (size_t)t, r, 32);
+    }
+    graph_source(g, g->result, idx, rs, isize, prev, inter, out);
+}
+void orc_quotient_graph(const orc_graph *g, unsigned k, unsigned ext_k, u64 *values) {
+    size_t isize = (size_t)1 << ext_k;
+#pragma omp parallel
+    {
+        u64 *inter = (u64 *)malloc(32 * (size_t)(g->n_calculations + 1));
+#pragma omp for schedule(static)
+        for (size_t idx = 0; idx < isize; idx++) {
+            u64 prev[4], out[4];
+            memcpy(prev, values + 4 * idx, 32);
+            graph_row(g, idx, ext_k - k, isize, prev, inter, out);
+            memcpy(values + 4 * idx, out, 32);
+        }
+        free(inter);
+    }
+}
+static void fold(u64 *value, const u64 *y, const u64 *term) { /* *value = *value * y + term */
+    u64 t[4];
+    f_mul(&FR, t, value, y);
+    f_add(&FR, value, t, term);
+}
+void orc_lookup_fold(const orc_graph *g, const u64 *z, const u64 *pin, const u64 *ptab, const u64 *l0, const u64 *l_last,
+                     const u64 *l_active, unsigned k, unsigned ext_k, u64 *values) {
+    size_t isize = (size_t)1 << ext_k;
+    unsigned rs = ext_k - k;
+    u64 *inter = (u64 *)malloc(32 * (size_t)(g->n_calculations + 1));
+    u64 zero[4] = {0, 0, 0, 0};
+    for (size_t idx = 0; idx < isize; idx++) {
+        u64 table_value[4], t[4], u[4], w[4], a_minus_s[4];
+        graph_row(g, idx, rs, isize, zero, inter, table_value);
+        size_t r_next = rotation_idx(idx, 1, rs, isize), r_prev = rotation_idx(idx, -1, rs, isize);
+        u64 *value = values + 4 * idx;
+        const u64 *zc = z + 4 * idx, *a = pin + 4 * idx, *s = ptab + 4 * idx;
+        f_sub(&FR, a_minus_s, a, s);
+        f_sub(&FR, t, FR.one, zc); f_mul(&FR, t, t, l0 + 4 * idx); fold(value, g->y, t);                 /* l_0 (1 - z) */
+        f_mul(&FR, t, zc, zc); f_sub(&FR, t, t, zc); f_mul(&FR, t, t, l_last + 4 * idx); fold(value, g->y, t); /* l_last (z^2 - z) */
+        f_add(&FR, t, a, g->beta); f_add(&FR, u, s, g->gamma); f_mul(&FR, t, t, u); f_mul(&FR, t, z + 4 * r_next, t);
+        f_mul(&FR, w, zc, table_value); f_sub(&FR, t, t, w); f_mul(&FR, t, t, l_active + 4 * idx); fold(value, g->y, t);
+        f_mul(&FR, t, a_minus_s, l0 + 4 * idx); fold(value, g->y, t);                                    /* l_0 (a' - s') */
+        f_sub(&FR, t, a, pin + 4 * r_prev); f_mul(&FR, t, a_minus_s, t); f_mul(&FR, t, t, l_active + 4 * idx); fold(value, g->y, t);
+    }
+    free(inter);
+}
+/* Fr::ZETA (cube root of unity) and Fr::DELTA = 7^(2^28), recomputed here from their definitions */
+static void delta_mont(u64 d[4]) {
+    u64 g[4]; fr_from_u64(g, 7);
+    memcpy(d, g, 32);
+    for (int i = 0; i < 28; i++) f_mul(&FR, d, d, d);
+}
+void orc_permutation_fold(const u64 *const *z, size_t n_sets, const u64 *const *columns, const u64 *const *sigma, size_t n_cols,
+                          size_t chunk_len, const u64 *l0, const u64 *l_last, const u64 *l_active, const u64 *beta, const u64 *gamma,
+                          const u64 *y, unsigned blinding_factors, unsigned k, unsigned ext_k, u64 *values) {
+    if (n_sets == 0) return;
+    size_t isize = (size_t)1 << ext_k;
+    unsigned rs = ext_k - k;
+    int last_rotation = -((int)blinding_factors + 1);
+    u64 zeta[4], delta[4], ext_omega[4], delta_start[4], beta_term[4];
+    zeta_mont(zeta); delta_mont(delta); orc_omega(ext_k, ext_omega);
+    f_mul(&FR, delta_start, beta, zeta);
+    memcpy(beta_term, FR.one, 32); /* extended_omega^start, start = 0 */
+    for (size_t idx = 0; idx < isize; idx++) {
+        size_t r_next = rotation_idx(idx, 1, rs, isize), r_last = rotation_idx(idx, last_rotation, rs, isize);
+        u64 *value = values + 4 * idx, t[4], u[4];
+        const u64 *first = z[0] + 4 * idx, *last = z[n_sets - 1] + 4 * idx;
+        f_sub(&FR, t, FR.one, first); f_mul(&FR, t, t, l0 + 4 * idx); fold(value, y, t);
+        f_mul(&FR, t, last, last); f_sub(&FR, t, t, last); f_mul(&FR, t, t, l_last + 4 * idx); fold(value, y, t);
+        for (size_t s = 1; s < n_sets; s++) {
+            f_sub(&FR, t, z[s] + 4 * idx, z[s - 1] + 4 * r_last); f_mul(&FR, t, t, l0 + 4 * idx); fold(value, y, t);
+        }
+        u64 current_delta[4];
+        f_mul(&FR, current_delta, delta_start, beta_term);
+        for (size_t s = 0; s < n_sets; s++) {
+            size_t c0 = s * chunk_len, c1 = c0 + chunk_len < n_cols ? c0 + chunk_len : n_cols;
+            u64 left[4], right[4];
+            memcpy(left, z[s] + 4 * r_next, 32);
+            for (size_t c = c0; c < c1; c++) {
+                f_mul(&FR, t, beta, sigma[c] + 4 * idx); f_add(&FR, t, t, columns[c] + 4 * idx); f_add(&FR, t, t, gamma);
+                f_mul(&FR, left, left, t);
+            }
+            memcpy(right, z[s] + 4 * idx, 32);
+            for (size_t c = c0; c < c1; c++) {
+                f_add(&FR, u, columns[c] + 4 * idx, current_delta); f_add(&FR, u, u, gamma);
+                f_mul(&FR, right, right, u);
+                f_mul(&FR, current_delta, current_delta, delta);
+            }
+            f_sub(&FR, t, left, right); f_mul(&FR, t, t, l_active + 4 * idx); fold(value, y, t);
+        }
+        f_mul(&FR, beta_term, beta_term, ext_omega);
+    }
+}
+/* ---- opening arithmetic: halo2-axiom 0.5.3 arithmetic.rs `eval_polynomial` (Horner) and `kate_division` */
+void orc_eval_polynomial(const u64 *coeffs, size_t n, const u64 *x, u64 *out) {
+    u64 acc[4] = {0, 0, 0, 0};
+    for (size_t i = n; i-- > 0;) { f_mul(&FR, acc, acc, x); f_add(&FR, acc, acc, coeffs + 4 * i); }
+    memcpy(out, acc, 32);
+}
+void orc_kate_division(const u64 *a, size_t n, const u64 *z, u64 *q) { /* b = -z; q_i = a_{i+1} - tmp; tmp = q_i * b */
+    u64 b[4], tmp[4] = {0, 0, 0, 0};
+    f_neg(&FR, b, z);
+    for (size_t i = n - 1; i >= 1; i--) {
+        u64 lead[4];
+        f_sub(&FR, lead, a + 4 * i, tmp);
+        memcpy(q + 4 * (i - 1), lead, 32);
+        f_mul(&FR, tmp, lead, b);
+    }
+}
+void orc_poly_lincomb(const u64 *const *polys, const u64 *scalars, size_t m, size_t n, u64 *out) {
+    for (size_t i = 0; i < n; i++) {
+        u64 acc[4] = {0, 0, 0, 0}, t[4];
+        for (size_t j = 0; j < m; j++) { f_mul(&FR, t, polys[j] + 4 * i, scalars + 4 * j); f_add(&FR, acc, acc, t); }
+        memcpy(out + 4 * i, acc, 32);
+    }
+}
 void orc_set_threads(int n) {
 #ifdef _OPENMP
     if (n > 0) omp_set_num_threads(n);

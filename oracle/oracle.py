@@ -222,3 +222,59 @@ def eval_rational(num, den):
     r = np.empty_like(a)
     lib().orc_eval_rational(_p(a), _p(b), C.c_size_t(len(a)), _p(r))
     return r
+
+
+# ---- general quotient evaluation / opening arithmetic -----------------------------
+# `graph` is a ctypes structure with the field order of orc_graph (== h2b_graph); tests pass the very structure they
+# hand to the CUDA library, with HOST column pointers.
+def quotient_graph(graph, k, ext_k, values):
+    v = np.array(values, dtype=np.uint64).reshape(-1, 4).copy()
+    lib().orc_quotient_graph(C.byref(graph), C.c_uint(k), C.c_uint(ext_k), _p(v))
+    return v
+
+
+def lookup_fold(graph, z, permuted_input, permuted_table, l0, l_last, l_active, k, ext_k, values):
+    a = [np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4) for x in (z, permuted_input, permuted_table, l0, l_last, l_active)]
+    v = np.array(values, dtype=np.uint64).reshape(-1, 4).copy()
+    lib().orc_lookup_fold(C.byref(graph), *[_p(x) for x in a], C.c_uint(k), C.c_uint(ext_k), _p(v))
+    return v
+
+
+def _ptr_table(cols):
+    return (C.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+
+
+def permutation_fold(z_sets, columns, sigma, chunk_len, l0, l_last, l_active, beta, gamma, y, blinding_factors, k, ext_k, values):
+    conv = lambda xs: [np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4) for x in xs]
+    zs, cs, ss, ls, ch = conv(z_sets), conv(columns), conv(sigma), conv([l0, l_last, l_active]), conv([beta, gamma, y])
+    v = np.array(values, dtype=np.uint64).reshape(-1, 4).copy()
+    lib().orc_permutation_fold(_ptr_table(zs), C.c_size_t(len(zs)), _ptr_table(cs), _ptr_table(ss), C.c_size_t(len(cs)),
+                               C.c_size_t(chunk_len), *[_p(x) for x in ls], *[_p(x) for x in ch], C.c_uint(blinding_factors),
+                               C.c_uint(k), C.c_uint(ext_k), _p(v))
+    return v
+
+
+def eval_polynomial(coeffs, x):
+    a = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    xx = np.ascontiguousarray(x, dtype=np.uint64).reshape(4)
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_eval_polynomial(_p(a) if len(a) else None, C.c_size_t(len(a)), _p(xx), _p(out))
+    return out
+
+
+def kate_division(a, z):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    assert len(a) >= 1
+    zz = np.ascontiguousarray(z, dtype=np.uint64).reshape(4)
+    q = np.empty((len(a) - 1, 4), dtype=np.uint64)
+    if len(a) > 1:
+        lib().orc_kate_division(_p(a), C.c_size_t(len(a)), _p(zz), _p(q))
+    return q
+
+
+def poly_lincomb(polys, scalars):
+    ps = [np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4) for x in polys]
+    s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty_like(ps[0])
+    lib().orc_poly_lincomb(_ptr_table(ps), _p(s), C.c_size_t(len(ps)), C.c_size_t(len(ps[0])), _p(out))
+    return out

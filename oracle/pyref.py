@@ -208,3 +208,106 @@ def assign_lookups(values, num_lookup_cols, n_rows):
     for j, v in enumerate(values):
         cols[j % num_lookup_cols][j // num_lookup_cols] = v
     return cols
+
+
+# ---- quotient h(X) terms and opening arithmetic on plain integers (pins oracle/bn254_oracle.c on small sizes) -------
+# halo2-axiom 0.5.3 plonk/evaluation.rs / arithmetic.rs are not vendored; these are the textbook formulas the Rust
+# code implements (comments there quote them), written with no regard for speed.
+ZETA = pow(pow(7, (R - 1) // 3, R), 2, R)  # Fr::ZETA
+DELTA = pow(7, 1 << 28, R)                 # Fr::DELTA = GENERATOR^(2^S)
+
+
+def eval_polynomial(coeffs, x):
+    return sum(c * pow(x, i, R) for i, c in enumerate(coeffs)) % R
+
+
+def kate_division(a, z):
+    """quotient of a(X) by (X - z) by schoolbook long division; remainder dropped"""
+    a = list(a)
+    q = [0] * (len(a) - 1)
+    for i in range(len(a) - 1, 0, -1):
+        q[i - 1] = a[i] % R
+        a[i - 1] = (a[i - 1] + z * a[i]) % R
+    return q
+
+
+def rotate(col, idx, rot, k, ext_k):
+    n = 1 << ext_k
+    return col[(idx + rot * (1 << (ext_k - k))) % n]
+
+
+def permutation_terms(z_sets, columns, sigma, chunk_len, l0, l_last, l_active, beta, gamma, y, blinding_factors, k, ext_k, values):
+    n = 1 << ext_k
+    w = omega_for(ext_k)
+    out = []
+    for i in range(n):
+        x = ZETA * pow(w, i, R) % R  # the point of the extended coset this row evaluates at
+        v = values[i]
+        v = (v * y + (1 - z_sets[0][i]) * l0[i]) % R
+        zl = z_sets[-1][i]
+        v = (v * y + (zl * zl - zl) * l_last[i]) % R
+        for s in range(1, len(z_sets)):
+            v = (v * y + (z_sets[s][i] - rotate(z_sets[s - 1], i, -(blinding_factors + 1), k, ext_k)) * l0[i]) % R
+        for s in range(len(z_sets)):
+            left, right = rotate(z_sets[s], i, 1, k, ext_k), z_sets[s][i]
+            for c in range(s * chunk_len, min((s + 1) * chunk_len, len(columns))):
+                left = left * (columns[c][i] + beta * sigma[c][i] + gamma) % R
+                right = right * (columns[c][i] + pow(DELTA, c, R) * beta * x + gamma) % R
+            v = (v * y + (left - right) * l_active[i]) % R
+        out.append(v)
+    return out
+
+
+def lookup_terms(table_values, z, a, s, l0, l_last, l_active, beta, gamma, y, k, ext_k, values):
+    """table_values[i] = (compressed input + beta)(compressed table + gamma) at row i"""
+    out = []
+    for i in range(1 << ext_k):
+        v = values[i]
+        v = (v * y + (1 - z[i]) * l0[i]) % R
+        v = (v * y + (z[i] * z[i] - z[i]) * l_last[i]) % R
+        v = (v * y + (rotate(z, i, 1, k, ext_k) * (a[i] + beta) * (s[i] + gamma) - z[i] * table_values[i]) * l_active[i]) % R
+        v = (v * y + (a[i] - s[i]) * l0[i]) % R
+        v = (v * y + (a[i] - s[i]) * (a[i] - rotate(a, i, -1, k, ext_k)) * l_active[i]) % R
+        out.append(v)
+    return out
+
+
+def graph_row(program, n_calc, result, constants, rotations, fixed, advice, instance, challenges, beta, gamma, theta, y, prev, idx, k,
+              ext_k):
+    """GraphEvaluator::evaluate for one row on plain integers; program / value-source encoding of include/h2b200.h"""
+    inter = []
+
+    def fetch(src):
+        kind, index, slot = src & 15, (src >> 4) & 0xFFFF, src >> 20
+        if kind == 0:
+            return constants[index]
+        if kind == 1:
+            return inter[index]
+        if kind in (2, 3, 4):
+            return rotate((fixed, advice, instance)[kind - 2][index], idx, rotations[slot], k, ext_k)
+        if kind == 5:
+            return challenges[index]
+        return {6: beta, 7: gamma, 8: theta, 9: y, 10: prev}[kind]
+
+    pc = 0
+    for _ in range(n_calc):
+        op = program[pc]
+        pc += 1
+        if op == 6:
+            r, f, np_ = fetch(program[pc]), fetch(program[pc + 1]), program[pc + 2]
+            pc += 3
+            for _j in range(np_):
+                r = (r * f + fetch(program[pc])) % R
+                pc += 1
+        else:
+            a = fetch(program[pc])
+            pc += 1
+            if op <= 2:
+                b = fetch(program[pc])
+                pc += 1
+                r = (a + b) % R if op == 0 else (a - b) % R if op == 1 else a * b % R
+            else:
+                r = {3: a * a % R, 4: 2 * a % R, 5: (-a) % R, 7: a}[op]
+        inter.append(r)
+    assert pc == len(program)
+    return fetch(result)

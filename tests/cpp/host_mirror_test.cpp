@@ -79,6 +79,13 @@ int main() {
     auto lk = assign_lookups(ctx, std::vector<Fr>(s.begin(), s.begin() + 10), k, 3);
     CHECK(lk[0][0] == s[0] && lk[1][0] == s[1] && lk[2][0] == s[2] && lk[0][1] == s[3] && lk[0][3] == s[9]);
 
+    // opening arithmetic: dividing by X (b = 0) shifts the coefficients, and then q(0) = a_1, a(0) = a_0
+    Fr zero{0, 0, 0, 0};
+    auto qd = kate_division(ctx, a, zero);
+    CHECK(qd.size() == a.size() - 1 && qd[0] == a[1] && qd.back() == a.back());
+    CHECK(eval_polynomial(ctx, a, zero) == a[0]);
+    CHECK(eval_polynomial(ctx, qd, zero) == a[1]);
+
     printf(fails ? "host mirror: %d FAILED\n" : "host mirror: all checks passed\n", fails);
     return fails ? 1 : 0;
 }
