@@ -6,6 +6,7 @@ from .parallel import shard_range, ntt_owner, all_gather_points, connect_peers, 
 from .host import (  # noqa: F401
     H2BError,
     LayoutError,
+    ConstraintSystemFailure,
     Context,
     ParamsKZG,
     EvaluationDomain,
@@ -24,4 +25,5 @@ from .evaluation import (  # noqa: F401,E402
     eval_polynomial,
     kate_division,
     poly_lincomb,
+    permute_expression_pair,
 )

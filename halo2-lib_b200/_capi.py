@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libh2b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "h2b200.h")
 
-H2B_OK, H2B_ERR_ARG, H2B_ERR_CUDA, H2B_ERR_OOM, H2B_ERR_LAYOUT = 0, -1, -2, -3, -4
+H2B_OK, H2B_ERR_ARG, H2B_ERR_CUDA, H2B_ERR_OOM, H2B_ERR_LAYOUT, H2B_ERR_UNSATISFIED = 0, -1, -2, -3, -4, -5
 BASIS_MONOMIAL, BASIS_LAGRANGE = 0, 1
 
 _vp, _sz, _u32, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
@@ -93,6 +93,15 @@ SIGNATURES = {
     "h2b_grand_product_fr_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "h2b_flex_gate_fold": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "h2b_flex_gate_fold_dev": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "h2b_g_to_lagrange": (_int, [_vp, _vp, _u32, _vp]),
+    "h2b_g_to_lagrange_dev": (_int, [_vp, _vp, _u32, _vp]),
+    "h2b_srs_setup": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
+    "h2b_srs_setup_dev": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
+    "h2b_g1_check_on_curve": (_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "h2b_g1_check_on_curve_dev": (_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "h2b_params_raw_view": (_int, [_vp, _sz, C.POINTER(_u32), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "h2b_permute_expression_pair": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "h2b_permute_expression_pair_dev": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "h2b_quotient_graph": (_int, [_vp, _gp, _u32, _u32, _vp]),
     "h2b_quotient_graph_dev": (_int, [_vp, _gp, _u32, _u32, _vp]),
     "h2b_permutation_fold": (_int, [_vp, _vpp, _sz, _vpp, _vpp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),

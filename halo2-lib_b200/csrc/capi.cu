@@ -670,6 +670,100 @@ int h2b_flex_gate_fold(h2b_ctx* ctx, const uint64_t* q_ext, const uint64_t* a_ex
     });
 }
 
+// ------------------------------------------------------------------------------------------------ keygen-side SRS utilities
+int h2b_g_to_lagrange_dev(h2b_ctx* ctx, const void* d_g, uint32_t k, void* d_g_lagrange) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_g && d_g_lagrange, "g_to_lagrange: null pointer");
+        g_to_lagrange_run(ctx, d_g, k, d_g_lagrange);
+    });
+}
+int h2b_g_to_lagrange(h2b_ctx* ctx, const uint64_t* g, uint32_t k, uint64_t* g_lagrange) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(g && g_lagrange, "g_to_lagrange: null pointer");
+        H2B_REQUIRE(k <= 28, "g_to_lagrange: k out of range");
+        const size_t bytes = ((size_t)1 << k) * 64;
+        char* d = (char*)ctx->get(WS_BASES, 2 * bytes);
+        H2B_CUDA(cudaMemcpyAsync(d, g, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        g_to_lagrange_run(ctx, d, k, d + bytes);
+        H2B_CUDA(cudaMemcpyAsync(g_lagrange, d + bytes, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_srs_setup_dev(h2b_ctx* ctx, const uint64_t tau[4], const uint64_t base_xy[8], uint32_t k, void* d_g, void* d_g_lagrange) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(tau && base_xy, "srs_setup: null pointer");
+        srs_setup_run(ctx, tau, base_xy, k, d_g, d_g_lagrange);
+    });
+}
+int h2b_srs_setup(h2b_ctx* ctx, const uint64_t tau[4], const uint64_t base_xy[8], uint32_t k, uint64_t* g, uint64_t* g_lagrange) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(tau && base_xy, "srs_setup: null pointer");
+        H2B_REQUIRE(k <= 28, "srs_setup: k out of range");
+        const size_t bytes = ((size_t)1 << k) * 64;
+        char* d = (char*)ctx->get(WS_BASES, 2 * bytes);
+        srs_setup_run(ctx, tau, base_xy, k, g ? d : nullptr, g_lagrange ? d + bytes : nullptr);
+        if (g) H2B_CUDA(cudaMemcpyAsync(g, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (g_lagrange) H2B_CUDA(cudaMemcpyAsync(g_lagrange, d + bytes, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_g1_check_on_curve_dev(h2b_ctx* ctx, const void* d_points_xy, size_t n, size_t* off_curve) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((d_points_xy || n == 0) && off_curve, "check_on_curve: null pointer");
+        *off_curve = g1_count_off_curve_run(ctx, d_points_xy, n);
+    });
+}
+int h2b_g1_check_on_curve(h2b_ctx* ctx, const uint64_t* points_xy, size_t n, size_t* off_curve) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((points_xy || n == 0) && off_curve, "check_on_curve: null pointer");
+        void* d = ctx->get(WS_BASES, n * 64);
+        if (n) H2B_CUDA(cudaMemcpyAsync(d, points_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+        *off_curve = g1_count_off_curve_run(ctx, d, n);
+    });
+}
+int h2b_params_raw_view(const uint8_t* bytes, size_t len, uint32_t* k, size_t* g_offset, size_t* g_lagrange_offset, size_t* g2_offset,
+                        size_t* s_g2_offset) {
+    if (!bytes || !k || len < 4) return H2B_ERR_ARG;
+    const uint32_t kk = (uint32_t)bytes[0] | ((uint32_t)bytes[1] << 8) | ((uint32_t)bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
+    if (kk > 28) return H2B_ERR_ARG;
+    const size_t n = (size_t)1 << kk;
+    if (len < 4 + 2 * n * 64 + 2 * 128) return H2B_ERR_ARG;
+    *k = kk;
+    if (g_offset) *g_offset = 4;
+    if (g_lagrange_offset) *g_lagrange_offset = 4 + n * 64;
+    if (g2_offset) *g2_offset = 4 + 2 * n * 64;
+    if (s_g2_offset) *s_g2_offset = 4 + 2 * n * 64 + 128;
+    return H2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ lookup permutation
+int h2b_permute_expression_pair_dev(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
+                                    void* d_permuted_input, void* d_permuted_table) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_input && d_table && d_permuted_input && d_permuted_table, "permute_expression_pair: null pointer");
+        H2B_REQUIRE(d_input != d_permuted_input && d_table != d_permuted_table && d_input != d_permuted_table && d_table != d_permuted_input,
+                    "permute_expression_pair: outputs must not alias inputs");
+        if (permute_expression_pair_run(ctx, d_input, d_table, k, blinding_factors, d_permuted_input, d_permuted_table))
+            throw StatusError{H2B_ERR_UNSATISFIED, "permute_expression_pair: an input value is not in the table (ConstraintSystemFailure)"};
+    });
+}
+int h2b_permute_expression_pair(h2b_ctx* ctx, const uint64_t* input, const uint64_t* table, uint32_t k, uint32_t blinding_factors,
+                                uint64_t* permuted_input, uint64_t* permuted_table) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(input && table && permuted_input && permuted_table, "permute_expression_pair: null pointer");
+        H2B_REQUIRE(k <= 28 && (size_t)blinding_factors + 1 < ((size_t)1 << k), "permute_expression_pair: no usable rows");
+        const size_t u = ((size_t)1 << k) - (blinding_factors + 1), bytes = u * 32;
+        char* d = (char*)ctx->get(WS_ASSIGN_IN, 4 * bytes);
+        H2B_CUDA(cudaMemcpyAsync(d, input, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        H2B_CUDA(cudaMemcpyAsync(d + bytes, table, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        const bool missing = permute_expression_pair_run(ctx, d, d + bytes, k, blinding_factors, d + 2 * bytes, d + 3 * bytes);
+        if (missing) throw StatusError{H2B_ERR_UNSATISFIED, "permute_expression_pair: an input value is not in the table (ConstraintSystemFailure)"};
+        H2B_CUDA(cudaMemcpyAsync(permuted_input, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaMemcpyAsync(permuted_table, d + 3 * bytes, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
 // ------------------------------------------------------------------------------------------------ quotient (general)
 namespace {
 // stages host columns of `bytes` bytes each, back to back, in one workspace slot

@@ -187,6 +187,13 @@ void permutation_fold_run(h2b_ctx* ctx, const void* const* d_z, size_t n_sets, c
                           size_t n_cols, size_t chunk_len, const void* d_l0, const void* d_l_last, const void* d_l_active,
                           const uint64_t beta[4], const uint64_t gamma[4], const uint64_t y[4], uint32_t blinding_factors, uint32_t k,
                           uint32_t ext_k, void* d_values);
+// ---- lookup.cu (returns true when an input value is missing from the table)
+bool permute_expression_pair_run(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
+                                 void* d_permuted_input, void* d_permuted_table);
+// ---- srs.cu
+void g_to_lagrange_run(h2b_ctx* ctx, const void* d_g, uint32_t k, void* d_g_lagrange);
+void srs_setup_run(h2b_ctx* ctx, const uint64_t tau[4], const uint64_t base_xy[8], uint32_t k, void* d_g, void* d_g_lagrange);
+size_t g1_count_off_curve_run(h2b_ctx* ctx, const void* d_points, size_t n);
 // ---- poly.cu
 void eval_polynomial_run(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t x[4], void* d_out);
 void kate_division_run(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t z[4], void* d_q);

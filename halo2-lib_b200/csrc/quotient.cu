@@ -59,7 +59,7 @@ __device__ __forceinline__ size_t rot_idx(size_t idx, int rot, u32 rshift, size_
     return (size_t)((long long)idx + (long long)rot * ((long long)1 << rshift)) & mask;  // get_rotation_idx
 }
 
-__device__ __noinline__ Fr graph_fetch(const GraphDev& g, u32 src, size_t idx, size_t mask, u32 rshift, const Fr& prev,
+__device__ __forceinline__ Fr graph_fetch(const GraphDev& g, u32 src, size_t idx, size_t mask, u32 rshift, const Fr& prev,
                                        const Fr* inter) {
     const u32 kind = src & 15u, index = (src >> 4) & 0xffffu, slot = src >> 20;
     switch (kind) {
@@ -141,10 +141,29 @@ struct PermDev {
     const uint64_t* const* columns;  // n_cols
     const uint64_t* const* sigma;    // n_cols
     const uint64_t* omega_pow2;      // [j] = extended_omega^(2^j), j < ext_k
-    u32 n_sets, n_cols, chunk_len;
+    const uint64_t* pow_lo;          // [i] = extended_omega^i, i < 2^lo_bits
+    const uint64_t* pow_hi;          // [j] = beta * zeta * extended_omega^(j << lo_bits)
+    u32 n_sets, n_cols, chunk_len, lo_bits;
     int last_rotation;
     Fr beta, gamma, y, zeta, delta;
 };
+
+// the two tables that turn beta * zeta * extended_omega^idx (= beta * X at row idx) into one product per row
+__global__ void __launch_bounds__(256) k_omega_tables(PermDev p, u32 ext_k, uint64_t* __restrict__ lo, uint64_t* __restrict__ hi) {
+    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x, n_lo = 1u << p.lo_bits, hi_bits = ext_k - p.lo_bits;
+    if (idx < n_lo) {
+        Fr r = Fr::one();
+        for (u32 j = 0; j < p.lo_bits; j++)
+            if ((idx >> j) & 1) r = r * Fr::load_nc(p.omega_pow2 + 4 * (size_t)j);
+        r.store(lo + 4 * (size_t)idx);
+    } else if (idx - n_lo < (1u << hi_bits)) {
+        const u32 h = idx - n_lo;
+        Fr r = p.beta * p.zeta;
+        for (u32 j = 0; j < hi_bits; j++)
+            if ((h >> j) & 1) r = r * Fr::load_nc(p.omega_pow2 + 4 * (size_t)(p.lo_bits + j));
+        r.store(hi + 4 * (size_t)h);
+    }
+}
 
 __global__ void __launch_bounds__(128) k_permutation_fold(PermDev p, const uint64_t* __restrict__ l0, const uint64_t* __restrict__ l_last,
                                                           const uint64_t* __restrict__ l_active, u32 ext_k, u32 rshift,
@@ -164,10 +183,7 @@ __global__ void __launch_bounds__(128) k_permutation_fold(PermDev p, const uint6
     for (u32 s = 1; s < p.n_sets; s++)
         v = v * p.y + (Fr::load_nc(p.z[s] + 4 * idx) - Fr::load_nc(p.z[s - 1] + 4 * r_last)) * v0;
     // current_delta = beta * zeta * extended_omega^idx  (= beta * X at this row), then *= DELTA per column
-    Fr cur = p.beta * p.zeta;
-#pragma unroll 1
-    for (u32 j = 0; j < ext_k; j++)
-        if ((idx >> j) & 1) cur = cur * Fr::load_nc(p.omega_pow2 + 4 * (size_t)j);
+    Fr cur = Fr::load_nc(p.pow_hi + 4 * (idx >> p.lo_bits)) * Fr::load_nc(p.pow_lo + 4 * (idx & (((size_t)1 << p.lo_bits) - 1)));
     u32 col = 0;
 #pragma unroll 1
     for (u32 s = 0; s < p.n_sets; s++) {
@@ -324,6 +340,12 @@ void permutation_fold_run(h2b_ctx* ctx, const void* const* d_z, size_t n_sets, c
     p.y = fr_from(y);
     p.zeta = fr_from(FR_ZETA_U64);
     p.delta = fr_from(FR_DELTA_U64);
+    p.lo_bits = ext_k < 11 ? ext_k : 11;
+    const size_t n_lo = (size_t)1 << p.lo_bits, n_hi = (size_t)1 << (ext_k - p.lo_bits);
+    uint64_t* tables = (uint64_t*)ctx->get(WS_MISC2, 32 * (n_lo + n_hi));
+    p.pow_lo = tables;
+    p.pow_hi = tables + 4 * n_lo;
+    H2B_LAUNCH(ctx, k_omega_tables, ceil_div(n_lo + n_hi, 256), 256, 0, p, ext_k, tables, tables + 4 * n_lo);
     H2B_LAUNCH(ctx, k_permutation_fold, ceil_div((size_t)1 << ext_k, 128), 128, 0, p, (const uint64_t*)d_l0, (const uint64_t*)d_l_last,
                (const uint64_t*)d_l_active, ext_k, ext_k - k, (uint64_t*)d_values);
 }

@@ -237,3 +237,13 @@ def poly_lincomb(ctx: Context, polys, scalars) -> np.ndarray:
     out = np.empty_like(ps[0])
     ctx.check(lib.h2b_poly_lincomb(ctx.h, _table(ps), _ptr(s), len(ps), len(ps[0]), _ptr(out) if len(out) else None))
     return out
+
+
+def permute_expression_pair(ctx: Context, input_expression, table_expression, k: int, blinding_factors: int):
+    """plonk/lookup/prover.rs `permute_expression_pair`: returns (permuted_input, permuted_table), 2^k rows each; the
+    last blinding_factors + 1 rows are left zero for the caller's blinding scalars.  Raises ConstraintSystemFailure."""
+    a, t = _u64(input_expression, 4), _u64(table_expression, 4)
+    assert len(a) == len(t) == 1 << k
+    pa, pt = np.zeros_like(a), np.zeros_like(t)
+    ctx.check(lib.h2b_permute_expression_pair(ctx.h, _ptr(a), _ptr(t), k, blinding_factors, _ptr(pa), _ptr(pt)))
+    return pa, pt

@@ -13,7 +13,7 @@ through libh2b200.so; nothing here does field arithmetic on the CPU."""
 from __future__ import annotations
 import ctypes as C
 import numpy as np
-from ._capi import lib, H2B_OK, H2B_ERR_LAYOUT, BASIS_MONOMIAL, BASIS_LAGRANGE
+from ._capi import lib, H2B_OK, H2B_ERR_LAYOUT, H2B_ERR_UNSATISFIED, BASIS_MONOMIAL, BASIS_LAGRANGE
 
 
 class H2BError(RuntimeError):
@@ -24,6 +24,10 @@ class H2BError(RuntimeError):
 
 class LayoutError(H2BError):
     """Where the Rust code panics (out of columns / rows)."""
+
+
+class ConstraintSystemFailure(H2BError):
+    """plonk::Error::ConstraintSystemFailure (a lookup input that the table does not hold)."""
 
 
 def _ptr(a):
@@ -54,7 +58,7 @@ class Context:
     def check(self, rc: int):
         if rc != H2B_OK:
             msg = lib.h2b_last_error(self.h).decode()
-            raise (LayoutError if rc == H2B_ERR_LAYOUT else H2BError)(rc, msg)
+            raise {H2B_ERR_LAYOUT: LayoutError, H2B_ERR_UNSATISFIED: ConstraintSystemFailure}.get(rc, H2BError)(rc, msg)
 
     def set_stream(self, cuda_stream: int | None):
         self.check(lib.h2b_ctx_set_stream(self.h, C.c_void_p(cuda_stream or 0)))

@@ -37,6 +37,7 @@ extern "C" {
 #define H2B_ERR_CUDA (-2)  /* CUDA runtime error (message carries cudaGetErrorString) */
 #define H2B_ERR_OOM (-3)   /* device or host allocation failed */
 #define H2B_ERR_LAYOUT (-4) /* witness layout error: where the Rust code panics (out of columns / rows) */
+#define H2B_ERR_UNSATISFIED (-5) /* plonk::Error::ConstraintSystemFailure: a lookup input is not in the table */
 
 typedef struct h2b_ctx h2b_ctx;
 typedef struct h2b_srs h2b_srs;
@@ -76,6 +77,26 @@ int h2b_srs_upload_dev(h2b_ctx* ctx, const void* d_g, const void* d_g_lagrange, 
 /* Window size c (bits) and number of table levels W = ceil(255 / c) chosen for this shard. */
 int h2b_srs_info(const h2b_srs* srs, int* window_bits, int* windows);
 void h2b_srs_destroy(h2b_ctx* ctx, h2b_srs* srs);
+
+/* Keygen-side SRS utilities (halo2-axiom 0.5.3 poly/kzg/commitment.rs, not vendored — restated).
+ * h2b_g_to_lagrange: `g_to_lagrange(g_projective, k)`: g_lagrange[i] = 2^-k * sum_j omega^(-i j) g[j] (a radix-2 FFT over
+ * G1), normalised to affine; g, g_lagrange: 2^k x 8 limbs.
+ * h2b_srs_setup: `ParamsKZG::setup` for a caller-supplied tau (the reference draws it from ChaCha20Rng seed 0,
+ * halo2-base/src/utils/mod.rs:439-443 — that draw stays on the Rust side): g[i] = tau^i * base, g_lagrange[i] =
+ * L_i(tau) * base; either output may be NULL.  tau must not be a 2^k-th root of unity.
+ * h2b_g1_check_on_curve: counts the points that are neither (0,0) nor on y^2 = x^3 + 3 (what `ParamsKZG::read` must
+ * reject, utils/mod.rs:401-424).
+ * h2b_params_raw_view: offsets into a `ParamsKZG::write` image in SerdeFormat::RawBytes — u32 LE k, 2^k x 64 B g,
+ * 2^k x 64 B g_lagrange, 128 B g2, 128 B s_g2, all Montgomery limbs, i.e. exactly the layouts of this header, so the
+ * file can be uploaded with h2b_srs_upload without a copy.  Host-only, no device work. */
+int h2b_g_to_lagrange(h2b_ctx* ctx, const uint64_t* g, uint32_t k, uint64_t* g_lagrange);
+int h2b_g_to_lagrange_dev(h2b_ctx* ctx, const void* d_g, uint32_t k, void* d_g_lagrange);
+int h2b_srs_setup(h2b_ctx* ctx, const uint64_t tau[4], const uint64_t base_xy[8], uint32_t k, uint64_t* g, uint64_t* g_lagrange);
+int h2b_srs_setup_dev(h2b_ctx* ctx, const uint64_t tau[4], const uint64_t base_xy[8], uint32_t k, void* d_g, void* d_g_lagrange);
+int h2b_g1_check_on_curve(h2b_ctx* ctx, const uint64_t* points_xy, size_t n, size_t* off_curve);
+int h2b_g1_check_on_curve_dev(h2b_ctx* ctx, const void* d_points_xy, size_t n, size_t* off_curve);
+int h2b_params_raw_view(const uint8_t* bytes, size_t len, uint32_t* k, size_t* g_offset, size_t* g_lagrange_offset,
+                        size_t* g2_offset, size_t* s_g2_offset);
 
 /* ---- MSM: replaces halo2curves-axiom 0.7.3 msm::best_multiexp(coeffs, bases) -> G1, as reached from
  *      ParamsKZG::commit / commit_lagrange inside create_proof ------------- */
@@ -180,6 +201,18 @@ int h2b_batch_invert_fr_dev(h2b_ctx* ctx, void* d_a, size_t n);
  * (`z.push(z[row - 1] * modified_values[row - 1])`; f[n-1] is not used).  f and z hold n elements. */
 int h2b_grand_product_fr(h2b_ctx* ctx, const uint64_t* f, const uint64_t start[4], size_t n, uint64_t* z);
 int h2b_grand_product_fr_dev(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z);
+
+/* The lookup argument's permuted columns: halo2-axiom 0.5.3 plonk/lookup/prover.rs `permute_expression_pair` (not
+ * vendored; restated).  input / table: the compressed expressions, 2^k rows (Lagrange form).  Over the usable rows
+ * u = 2^k - (blinding_factors + 1): permuted_input = input sorted by Fr's Ord (canonical integer order);
+ * permuted_table[row] = permuted_input[row] where a run starts, and the left-over table values — ascending — on the
+ * repeated rows from the last one backwards.  Rows >= u of both outputs are NOT written (the prover puts its blinding
+ * scalars there).  Outputs must not alias inputs.  H2B_ERR_UNSATISFIED when an input value is missing from the table.
+ * The `_dev` form synchronises the stream (it has to read the verdict). */
+int h2b_permute_expression_pair(h2b_ctx* ctx, const uint64_t* input, const uint64_t* table, uint32_t k, uint32_t blinding_factors,
+                                uint64_t* permuted_input, uint64_t* permuted_table);
+int h2b_permute_expression_pair_dev(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
+                                    void* d_permuted_input, void* d_permuted_table);
 
 /* ---- quotient evaluation, first slice: the custom-gate term of halo2-base's vertical gate
  * `q * (a + b*c - out)` (halo2-base/src/gates/flex_gate/mod.rs:80-91) on the extended coset domain, folded as the

@@ -733,6 +733,122 @@ void orc_permutation_fold(const u64 *const *z, size_t n_sets, const u64 *const *
         f_mul(&FR, beta_term, beta_term, ext_omega);
     }
 }
+/* ---- keygen-side SRS utilities: halo2-axiom 0.5.3 poly/kzg/commitment.rs `g_to_lagrange` (an FFT over G1 with
+ * omega^-1, every point scaled by 2^-k, normalised) and `ParamsKZG::setup` for a given tau (not vendored; restated).
+ * The FFT here is the textbook iterative one on Jacobian points with a general scalar multiplication per butterfly. */
+static void jac_scalar_mul(jac_t *r, const u64 s_mont[4], const jac_t *p) {
+    u64 s[4];
+    f_from_mont(&FR, s, s_mont);
+    jac_t acc; jac_set_identity(&acc);
+    for (int i = 255; i >= 0; i--) {
+        jac_double(&acc, &acc);
+        if ((s[i >> 6] >> (i & 63)) & 1) jac_add(&acc, &acc, p);
+    }
+    *r = acc;
+}
+void orc_g_to_lagrange(const u64 *g_xy, unsigned k, u64 *out_xy) {
+    size_t n = (size_t)1 << k;
+    jac_t *a = (jac_t *)malloc(n * sizeof(jac_t));
+    for (size_t i = 0; i < n; i++) { /* bit-reversed load */
+        const aff_t *p = (const aff_t *)(g_xy + 8 * i);
+        jac_t *d = a + (k ? bitrev((unsigned)i, k) : 0);
+        if (aff_is_identity(p)) { jac_set_identity(d); continue; }
+        memcpy(d->x, p->x, 32); memcpy(d->y, p->y, 32); memcpy(d->z, FQ.one, 32);
+    }
+    u64 w_n[4], w_inv[4];
+    orc_omega(k, w_n); f_inv(&FR, w_inv, w_n);
+    for (unsigned s = 1; s <= k; s++) {
+        size_t m = (size_t)1 << s, half = m >> 1;
+        u64 w_m[4]; memcpy(w_m, w_inv, 32);
+        for (unsigned i = s; i < k; i++) f_mul(&FR, w_m, w_m, w_m); /* omega^-(n/m) */
+#pragma omp parallel for schedule(dynamic, 1)
+        for (size_t blk = 0; blk < n; blk += m) {
+            u64 w[4]; memcpy(w, FR.one, 32);
+            for (size_t j = 0; j < half; j++) {
+                jac_t t, neg;
+                jac_scalar_mul(&t, w, a + blk + j + half);
+                neg = t; f_neg(&FQ, neg.y, t.y);
+                jac_add(a + blk + j + half, a + blk + j, &neg);
+                jac_add(a + blk + j, a + blk + j, &t);
+                f_mul(&FR, w, w, w_m);
+            }
+        }
+    }
+    u64 nn[4], n_inv[4];
+    fr_from_u64(nn, (u64)n); f_inv(&FR, n_inv, nn);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < n; i++) {
+        jac_t r; jac_scalar_mul(&r, n_inv, a + i);
+        if (jac_is_identity(&r)) { memset(out_xy + 8 * i, 0, 64); continue; }
+        jac_normalize(&r);
+        memcpy(out_xy + 8 * i, r.x, 32); memcpy(out_xy + 8 * i + 4, r.y, 32);
+    }
+    free(a);
+}
+/* g[i] = tau^i * base; g_lagrange[i] = L_i(tau) * base, L_i(tau) = (tau^n - 1)/n * omega^i / (tau - omega^i) */
+void orc_srs_setup(const u64 *tau, const u64 *base_xy, unsigned k, u64 *g_xy, u64 *g_lagrange_xy) {
+    size_t n = (size_t)1 << k;
+    u64 *sc = (u64 *)malloc(n * 32), acc[4], w[4], wi[4], c[4], nn[4], t[4];
+    memcpy(acc, FR.one, 32);
+    for (size_t i = 0; i < n; i++) { memcpy(sc + 4 * i, acc, 32); f_mul(&FR, acc, acc, tau); } /* acc ends as tau^n */
+    if (g_xy) orc_g1_fixed_base_mul(sc, n, base_xy, g_xy);
+    if (g_lagrange_xy) {
+        f_sub(&FR, c, acc, FR.one); fr_from_u64(nn, (u64)n); f_inv(&FR, nn, nn); f_mul(&FR, c, c, nn);
+        orc_omega(k, w); memcpy(wi, FR.one, 32);
+        for (size_t i = 0; i < n; i++) {
+            f_sub(&FR, t, tau, wi); f_inv(&FR, t, t); f_mul(&FR, t, t, wi); f_mul(&FR, sc + 4 * i, t, c);
+            f_mul(&FR, wi, wi, w);
+        }
+        orc_g1_fixed_base_mul(sc, n, base_xy, g_lagrange_xy);
+    }
+    free(sc);
+}
+/* ---- lookup argument: halo2-axiom 0.5.3 plonk/lookup/prover.rs `permute_expression_pair` (not vendored), walked the
+ * way the Rust code does: sort the inputs, count the table values in an ordered map, give every first occurrence its own
+ * value, then hand the left-over table values (ascending) to the repeated rows popped from the back.
+ * Returns 0, or -1 for Error::ConstraintSystemFailure (an input value that the table does not hold).  Only the usable
+ * rows [0, 2^k - (blinding_factors + 1)) of the outputs are written. */
+static int canon_cmp(const void *a, const void *b) { /* Fr::cmp: canonical value, most significant limb first */
+    const u64 *x = (const u64 *)a, *y = (const u64 *)b;
+    for (int i = 3; i >= 0; i--) { if (x[i] < y[i]) return -1; if (x[i] > y[i]) return 1; }
+    return 0;
+}
+int orc_permute_expression_pair(const u64 *input, const u64 *table, unsigned k, unsigned blinding_factors, u64 *permuted_input,
+                                u64 *permuted_table) {
+    size_t usable = ((size_t)1 << k) - (blinding_factors + 1);
+    u64 *a = (u64 *)malloc(usable * 32), *t = (u64 *)malloc(usable * 32);
+    size_t *count = (size_t *)calloc(usable, sizeof(size_t)), *repeated = (size_t *)malloc(usable * sizeof(size_t));
+    for (size_t i = 0; i < usable; i++) { f_from_mont(&FR, a + 4 * i, input + 4 * i); f_from_mont(&FR, t + 4 * i, table + 4 * i); }
+    qsort(a, usable, 32, canon_cmp); /* permuted_input_expression.sort() */
+    qsort(t, usable, 32, canon_cmp);
+    /* leftover_table_map: distinct table values (ascending) with their counts */
+    size_t n_keys = 0;
+    for (size_t i = 0; i < usable; i++) {
+        if (n_keys && canon_cmp(t + 4 * (n_keys - 1), t + 4 * i) == 0) { count[n_keys - 1]++; continue; }
+        memmove(t + 4 * n_keys, t + 4 * i, 32);
+        count[n_keys++] = 1;
+    }
+    int rc = 0;
+    size_t n_rep = 0;
+    for (size_t row = 0; row < usable && rc == 0; row++) {
+        f_to_mont(&FR, permuted_input + 4 * row, a + 4 * row);
+        if (row == 0 || canon_cmp(a + 4 * row, a + 4 * (row - 1)) != 0) {
+            memcpy(permuted_table + 4 * row, permuted_input + 4 * row, 32);
+            u64 *hit = (u64 *)bsearch(a + 4 * row, t, n_keys, 32, canon_cmp);
+            if (!hit || count[(hit - t) / 4] == 0) rc = -1; else count[(hit - t) / 4]--;
+        } else {
+            repeated[n_rep++] = row;
+        }
+    }
+    for (size_t j = 0; j < n_keys && rc == 0; j++)
+        for (size_t c = 0; c < count[j]; c++) {
+            if (n_rep == 0) { rc = -1; break; }
+            f_to_mont(&FR, permuted_table + 4 * repeated[--n_rep], t + 4 * j);
+        }
+    if (rc == 0 && n_rep != 0) rc = -1; /* assert!(repeated_input_rows.is_empty()) */
+    free(a); free(t); free(count); free(repeated);
+    return rc;
+}
 /* ---- opening arithmetic: halo2-axiom 0.5.3 arithmetic.rs `eval_polynomial` (Horner) and `kate_division` */
 void orc_eval_polynomial(const u64 *coeffs, size_t n, const u64 *x, u64 *out) {
     u64 acc[4] = {0, 0, 0, 0};

@@ -28,6 +28,7 @@ def lib():
         _lib.orc_assign_witnesses.restype = C.c_int
         _lib.orc_assign_lookups.restype = C.c_int
         _lib.orc_max_threads.restype = C.c_int
+        _lib.orc_permute_expression_pair.restype = C.c_int
     return _lib
 
 
@@ -278,3 +279,28 @@ def poly_lincomb(polys, scalars):
     out = np.empty_like(ps[0])
     lib().orc_poly_lincomb(_ptr_table(ps), _p(s), C.c_size_t(len(ps)), C.c_size_t(len(ps[0])), _p(out))
     return out
+
+
+def permute_expression_pair(input_col, table_col, k, blinding_factors):
+    """returns (rc, permuted_input, permuted_table); rows >= usable are zero-filled here (the prover writes randoms)"""
+    a = np.ascontiguousarray(input_col, dtype=np.uint64).reshape(-1, 4)
+    t = np.ascontiguousarray(table_col, dtype=np.uint64).reshape(-1, 4)
+    pa, pt = np.zeros_like(a), np.zeros_like(t)
+    rc = lib().orc_permute_expression_pair(_p(a), _p(t), C.c_uint(k), C.c_uint(blinding_factors), _p(pa), _p(pt))
+    return rc, pa, pt
+
+
+def g_to_lagrange(g_xy, k):
+    g = np.ascontiguousarray(g_xy, dtype=np.uint64).reshape(-1, 8)
+    assert len(g) == 1 << k
+    out = np.empty_like(g)
+    lib().orc_g_to_lagrange(_p(g), C.c_uint(k), _p(out))
+    return out
+
+
+def srs_setup(tau, base_xy, k):
+    t = np.ascontiguousarray(tau, dtype=np.uint64).reshape(4)
+    b = np.ascontiguousarray(base_xy, dtype=np.uint64).reshape(8)
+    g, gl = np.empty((1 << k, 8), dtype=np.uint64), np.empty((1 << k, 8), dtype=np.uint64)
+    lib().orc_srs_setup(_p(t), _p(b), C.c_uint(k), _p(g), _p(gl))
+    return g, gl

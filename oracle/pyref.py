@@ -311,3 +311,25 @@ def graph_row(program, n_calc, result, constants, rotations, fixed, advice, inst
         inter.append(r)
     assert pc == len(program)
     return fetch(result)
+
+
+def permute_expression_pair(inputs, table):
+    """usable rows only, plain integers; returns (A', S') or None for ConstraintSystemFailure"""
+    a = sorted(inputs)
+    left = {}
+    for v in table:
+        left[v] = left.get(v, 0) + 1
+    s_perm, repeated = [None] * len(a), []
+    for row, v in enumerate(a):
+        if row == 0 or v != a[row - 1]:
+            s_perm[row] = v
+            if left.get(v, 0) == 0:
+                return None
+            left[v] -= 1
+        else:
+            repeated.append(row)
+    for v in sorted(left):
+        for _ in range(left[v]):
+            s_perm[repeated.pop()] = v
+    assert not repeated
+    return a, s_perm

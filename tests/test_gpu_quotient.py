@@ -321,3 +321,74 @@ def test_quotient_device_pointers_full_size(ctx, h2b):
     blh = ev.BoundGraph(g2, lk, fixed=[host[0], host[5]], advice=[host[1]], **kw)
     want = orc.lookup_fold(blh.struct, host[2], host[4], host[6], host[9], host[10], host[11], k, ext_k, want)
     assert np.array_equal(acc_d.cpu().numpy().view(np.uint64), want)
+
+
+# ------------------------------------------------------------------ lookup argument: permute_expression_pair
+@pytest.mark.parametrize("kind,k", [("range", 7), ("dup_table", 9), ("wide", 10), ("all_same", 8), ("perm", 9), ("range", 16), ("wide", 15)])
+def test_permute_expression_pair(ctx, h2b, kind, k):
+    from test_oracle_quotient import lookup_columns
+    bf = 5
+    rng = np.random.default_rng(2200 + k)
+    u = (1 << k) - (bf + 1)
+    inputs, table = lookup_columns(rng, k, bf, kind)
+    pad = rand_ints(rng, bf + 1, R)
+    A, T = mont(inputs + pad, R), mont(table + pad, R)
+    pa, pt = h2b.permute_expression_pair(ctx, A, T, k, bf)
+    rc, wa, wt = orc.permute_expression_pair(A, T, k, bf)
+    assert rc == 0
+    assert np.array_equal(pa, wa) and np.array_equal(pt, wt)
+    assert not pa[u:].any() and not pt[u:].any()  # blinding rows are the caller's
+
+
+def test_permute_expression_pair_missing_value_and_bad_arguments(ctx, h2b):
+    k, bf = 8, 5
+    u = (1 << k) - (bf + 1)
+    table = list(range(u))
+    inputs = [3] * (u - 1) + [u + 9]
+    with pytest.raises(h2b.ConstraintSystemFailure):
+        h2b.permute_expression_pair(ctx, mont(inputs + [0] * (bf + 1), R), mont(table + [0] * (bf + 1), R), k, bf)
+    from halo2_lib_b200._capi import lib
+    a = mont(table + [0] * (bf + 1), R)
+    assert lib.h2b_permute_expression_pair(ctx.h, C.c_void_p(a.ctypes.data), C.c_void_p(a.ctypes.data), 2, 5, C.c_void_p(a.ctypes.data),
+                                           C.c_void_p(a.ctypes.data)) == -1  # 2^2 rows, 6 of them blinding: no usable rows
+    # the context stays usable after the failures
+    pa, pt = h2b.permute_expression_pair(ctx, a, a, k, bf)
+    assert unmont(pa[:u], R) == table and unmont(pt[:u], R) == table
+
+
+def test_lookup_argument_end_to_end(ctx, h2b):
+    """the GPU pipeline a prover runs for one lookup: permute_expression_pair -> denominators batch-inverted -> grand
+    product -> the five quotient terms; a satisfied lookup must vanish on the 2^k domain."""
+    from halo2_lib_b200 import evaluation as ev
+    k, ext_k, bf = 7, 10, 5
+    n = 1 << k
+    rng = np.random.default_rng(2300)
+    beta, gamma, theta, y = rand_ints(rng, 4, R)
+    m1 = lambda v: mont([v], R)[0]
+    l0, l_last, l_active, u = qc.lagrange_basis_columns(k, bf)
+    q = [int(rng.integers(0, 2)) for _ in range(u)] + [0] * (n - u)
+    a = [int(rng.integers(0, u)) for _ in range(u)] + rand_ints(rng, n - u, R)
+    table = list(range(u)) + rand_ints(rng, n - u, R)
+    inputs = [qq * aa % R for qq, aa in zip(q, a)]
+    pa, pt = h2b.permute_expression_pair(ctx, mont(inputs, R), mont(table, R), k, bf)
+    blind = rnd_fr(rng, 2 * (bf + 1))
+    pa[u:], pt[u:] = blind[:bf + 1], blind[bf + 1:]
+    # z[i+1] = z[i] * (A_i + beta)(S_i + gamma) / ((A'_i + beta)(S'_i + gamma)); all field work on the GPU
+    B, G = np.tile(m1(beta), (n, 1)), np.tile(m1(gamma), (n, 1))
+    add = lambda x, yv: ctx.field_op(1, 1, x, yv)
+    mul = lambda x, yv: ctx.field_op(1, 0, x, yv)
+    num = mul(add(mont(inputs, R), B), add(mont(table, R), G))
+    den = ctx.batch_invert(mul(add(pa, B), add(pt, G)))
+    z = ctx.grand_product(mul(num, den), m1(1))
+    assert unmont(z[u:u + 1], R)[0] == 1  # the product over the usable rows closes
+    z[u + 1:] = rnd_fr(rng, n - u - 1)
+    dom = h2b.EvaluationDomain(ctx, 2, k)
+    dom.extended_k = ext_k
+    ext = lambda col: dom.coeff_to_extended(dom.lagrange_to_coeff(col))
+    g = ev.GraphEvaluator()
+    res = g.add_lookup([("product", ("fixed", 0, 0), ("advice", 0, 0))], [("fixed", 1, 0)])
+    bound = ev.BoundGraph(g, res, fixed=[ext(mont(q, R)), ext(mont(table, R))], advice=[ext(mont(a, R))], beta=m1(beta), gamma=m1(gamma),
+                          theta=m1(theta), y=m1(y))
+    numer = h2b.lookup_fold(ctx, bound, ext(z), ext(pa), ext(pt), ext(mont(l0, R)), ext(mont(l_last, R)), ext(mont(l_active, R)), k, ext_k,
+                            np.zeros((1 << ext_k, 4), dtype=np.uint64))
+    assert all(v == 0 for v in on_domain_values(ctx, h2b, numer, k, ext_k, range(n)))

@@ -150,3 +150,50 @@ def test_lookup_terms_vs_python_and_vanish_when_satisfied():
             assert unmont(got, R) == want
         on_domain = vanishes_on_domain(got, k, ext_k)
         assert all(v == 0 for v in on_domain) != broken
+
+
+def lookup_columns(rng, k, bf, kind):
+    """(inputs, table) integers over the usable rows for a few shapes of lookup"""
+    u = (1 << k) - (bf + 1)
+    if kind == "range":      # range check: table 0..u-1, inputs small with many repeats
+        table = list(range(u))
+        inputs = [int(x) for x in rng.integers(0, min(u, 37), size=u)]
+    elif kind == "dup_table":  # the table itself holds duplicates (zero padding), inputs hit a few values
+        table = [int(x) for x in rng.integers(0, 16, size=u)]
+        inputs = [table[int(j)] for j in rng.integers(0, u, size=u)]
+    elif kind == "wide":     # full-width field elements: every limb takes part in the order
+        table = rand_ints(rng, u, R)
+        inputs = [table[int(j)] for j in rng.integers(0, u, size=u)]
+    elif kind == "all_same":
+        table = list(range(u))
+        inputs = [5] * u
+    else:                    # a permutation of the table: no repeated row at all
+        table = rand_ints(rng, u, R)
+        inputs = [table[int(j)] for j in rng.permutation(u)]
+    return inputs, table
+
+
+@pytest.mark.parametrize("kind", ["range", "dup_table", "wide", "all_same", "perm"])
+def test_permute_expression_pair_vs_python(kind):
+    k, bf = 7, 5
+    rng = np.random.default_rng(47)
+    u = (1 << k) - (bf + 1)
+    inputs, table = lookup_columns(rng, k, bf, kind)
+    pad = rand_ints(rng, bf + 1, R)
+    rc, pa, pt = orc.permute_expression_pair(mont(inputs + pad, R), mont(table + pad, R), k, bf)
+    assert rc == 0
+    want_a, want_s = pyref.permute_expression_pair(inputs, table)
+    assert unmont(pa[:u], R) == want_a and unmont(pt[:u], R) == want_s
+    assert not pa[u:].any() and not pt[u:].any()
+    # the properties the lookup argument needs: S' is a permutation of S, and A'[i] is S'[i] or A'[i-1]
+    assert sorted(want_s) == sorted(table)
+    assert all(want_a[i] == want_s[i] or (i and want_a[i] == want_a[i - 1]) for i in range(u))
+
+
+def test_permute_expression_pair_missing_value():
+    k, bf = 5, 5
+    u = (1 << k) - (bf + 1)
+    table = list(range(u))
+    inputs = [3] * (u - 1) + [u + 9]
+    rc, _, _ = orc.permute_expression_pair(mont(inputs + [0] * (bf + 1), R), mont(table + [0] * (bf + 1), R), k, bf)
+    assert rc == -1 and pyref.permute_expression_pair(inputs, table) is None
