@@ -17,10 +17,10 @@ namespace h2b {
 
 static constexpr int PD_TILE = 2048;  // 256 threads x 8 contiguous coefficients
 
-// pw[j] = x^(2^j), j < 32
+// pw[j] = x^(2^j), j < 12 (x^8 and x^2048 are the chunk and tile weights)
 __global__ void k_pow2_table(Fr x, uint64_t* __restrict__ pw) {
     if (threadIdx.x | blockIdx.x) return;
-    for (int j = 0; j < 32; j++) {
+    for (int j = 0; j < 12; j++) {
         x.store(pw + 4 * j);
         x = x.sqr();
     }

@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(256) k_mul_elementwise(const uint64_t* __restr
 
 void batch_invert_run(h2b_ctx* ctx, void* d_a, size_t n) {
     if (n == 0) return;
-    // enough CTAs to fill the machine a few times over (their inversions overlap), at most 16 elements per thread
-    int E = (int)(n / ((size_t)256 * 4 * ctx->sm_count));
+    // one wave of CTAs (4 of these fit an SM at 64 registers per thread), so that every CTA's inversion chain runs
+    // concurrently: a second wave would add a full ~165 us chain; at most 16 elements per thread
+    const size_t slots = (size_t)256 * 4 * ctx->sm_count;
+    int E = (int)((n + slots - 1) / slots);
     if (E < 2) E = 2;
     if (E > 16) E = 16;
     uint64_t* scratch = (uint64_t*)ctx->get(WS_MISC2, n * 32);
