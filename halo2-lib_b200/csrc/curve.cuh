@@ -67,7 +67,7 @@ __device__ __forceinline__ XYZZ xyzz_dbl_affine(const Affine& p) {
     Fq xx = p.x.sqr();
     Fq m = xx.dbl() + xx;
     r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * p.y;
+    r.y = Fq::mul_sub_mul(m, s - r.x, w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -84,7 +84,7 @@ __device__ __forceinline__ XYZZ xyzz_dbl(const XYZZ& p) {
     Fq xx = p.x.sqr();
     Fq m = xx.dbl() + xx;
     r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * p.y;
+    r.y = Fq::mul_sub_mul(m, s - r.x, w, p.y);
     r.zz = v * p.zz;
     r.zzz = w * p.zzz;
     return r;
@@ -110,7 +110,7 @@ __device__ __forceinline__ void xyzz_madd(XYZZ& acc, const Affine& q) {
     Fq ppp = p * pp;
     Fq qq = acc.x * pp;
     Fq x3 = r.sqr() - ppp - qq.dbl();
-    acc.y = r * (qq - x3) - acc.y * ppp;
+    acc.y = Fq::mul_sub_mul(r, qq - x3, acc.y, ppp);  // one interleaved reduction for both products
     acc.x = x3;
     acc.zz = acc.zz * pp;
     acc.zzz = acc.zzz * ppp;
@@ -138,7 +138,7 @@ __device__ __forceinline__ void xyzz_add(XYZZ& acc, const XYZZ& q) {
     Fq ppp = p * pp;
     Fq qq = u1 * pp;
     Fq x3 = r.sqr() - ppp - qq.dbl();
-    acc.y = r * (qq - x3) - s1 * ppp;
+    acc.y = Fq::mul_sub_mul(r, qq - x3, s1, ppp);
     acc.x = x3;
     acc.zz = acc.zz * q.zz * pp;
     acc.zzz = acc.zzz * q.zzz * ppp;

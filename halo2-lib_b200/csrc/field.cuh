@@ -237,6 +237,74 @@ struct __align__(16) Fp {
         return reduce_once(s);
     }
 
+    // a*b + c*d (Montgomery, fully reduced) with ONE interleaved reduction: 192 wide multiplies instead of 256 for two
+    // products.  Same accumulator scheme as mul_cios: row i adds a*b_i and c*d_i before the reduction step clears
+    // limb i.  Bounds: after row i the running value is (a*b[0..i] + c*d[0..i] + M_i*p) / 2^(32(i+1)) < 2p + p < 2^256,
+    // so the 9-limb windows cannot overflow, and the result (a*b + c*d + M*p)/R < 2p^2/R + p < 1.5p needs one
+    // conditional subtraction.  Used for the y coordinate of the group law (r*(Q - X3) - S1*PPP = r*(..) + (p - S1)*PPP).
+    __device__ __forceinline__ static Fp mul_add_mul(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        u32 E[17], O[17];
+#pragma unroll
+        for (int k = 0; k < 17; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            u32* X = (i & 1) ? O : E;
+            u32* Y = (i & 1) ? E : O;
+            const u32 bi = b.l[i], di = d.l[i];
+            if (i == 0) {
+                mul_wide(Y[1], Y[2], a.l[1], bi);
+                mul_wide(Y[3], Y[4], a.l[3], bi);
+                mul_wide(Y[5], Y[6], a.l[5], bi);
+                mul_wide(Y[7], Y[8], a.l[7], bi);
+                mul_wide(X[0], X[1], a.l[0], bi);
+                mul_wide(X[2], X[3], a.l[2], bi);
+                mul_wide(X[4], X[5], a.l[4], bi);
+                mul_wide(X[6], X[7], a.l[6], bi);
+            } else {
+                add_cc(X[i], X[i], Y[i]);
+                madc_lo_cc(Y[i + 1], a.l[1], bi); madc_hi_cc(Y[i + 2], a.l[1], bi);
+                madc_lo_cc(Y[i + 3], a.l[3], bi); madc_hi_cc(Y[i + 4], a.l[3], bi);
+                madc_lo_cc(Y[i + 5], a.l[5], bi); madc_hi_cc(Y[i + 6], a.l[5], bi);
+                madc_lo_cc(Y[i + 7], a.l[7], bi); madc_hi(Y[i + 8], a.l[7], bi);
+                mad_lo_cc(X[i], a.l[0], bi);      madc_hi_cc(X[i + 1], a.l[0], bi);
+                madc_lo_cc(X[i + 2], a.l[2], bi); madc_hi_cc(X[i + 3], a.l[2], bi);
+                madc_lo_cc(X[i + 4], a.l[4], bi); madc_hi_cc(X[i + 5], a.l[4], bi);
+                madc_lo_cc(X[i + 6], a.l[6], bi); madc_hi_cc(X[i + 7], a.l[6], bi);
+                addc(X[i + 8], X[i + 8], 0);
+            }
+            // second product of the row: odd-j into Y at (i+1 .. i+8), even-j into X at (i .. i+7) (+ carry limb)
+            mad_lo_cc(Y[i + 1], c.l[1], di);  madc_hi_cc(Y[i + 2], c.l[1], di);
+            madc_lo_cc(Y[i + 3], c.l[3], di); madc_hi_cc(Y[i + 4], c.l[3], di);
+            madc_lo_cc(Y[i + 5], c.l[5], di); madc_hi_cc(Y[i + 6], c.l[5], di);
+            madc_lo_cc(Y[i + 7], c.l[7], di); madc_hi(Y[i + 8], c.l[7], di);
+            mad_lo_cc(X[i], c.l[0], di);      madc_hi_cc(X[i + 1], c.l[0], di);
+            madc_lo_cc(X[i + 2], c.l[2], di); madc_hi_cc(X[i + 3], c.l[2], di);
+            madc_lo_cc(X[i + 4], c.l[4], di); madc_hi_cc(X[i + 5], c.l[4], di);
+            madc_lo_cc(X[i + 6], c.l[6], di); madc_hi_cc(X[i + 7], c.l[6], di);
+            addc(X[i + 8], X[i + 8], 0);
+            const u32 m = X[i] * P::INV;
+            mad_lo_cc(Y[i + 1], m, P::MOD(1));  madc_hi_cc(Y[i + 2], m, P::MOD(1));
+            madc_lo_cc(Y[i + 3], m, P::MOD(3)); madc_hi_cc(Y[i + 4], m, P::MOD(3));
+            madc_lo_cc(Y[i + 5], m, P::MOD(5)); madc_hi_cc(Y[i + 6], m, P::MOD(5));
+            madc_lo_cc(Y[i + 7], m, P::MOD(7)); madc_hi(Y[i + 8], m, P::MOD(7));
+            mad_lo_cc(X[i], m, P::MOD(0));      madc_hi_cc(X[i + 1], m, P::MOD(0));
+            madc_lo_cc(X[i + 2], m, P::MOD(2)); madc_hi_cc(X[i + 3], m, P::MOD(2));
+            madc_lo_cc(X[i + 4], m, P::MOD(4)); madc_hi_cc(X[i + 5], m, P::MOD(4));
+            madc_lo_cc(X[i + 6], m, P::MOD(6)); madc_hi_cc(X[i + 7], m, P::MOD(6));
+            addc(X[i + 8], X[i + 8], 0);
+        }
+        Fp s;
+        add_cc(s.l[0], E[8], O[8]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) addc_cc(s.l[k], E[8 + k], O[8 + k]);
+        addc(s.l[7], E[15], O[15]);
+        return reduce_once(s);
+    }
+    // a*b - c*d
+    __device__ __forceinline__ static Fp mul_sub_mul(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        return mul_add_mul(a, b, c.neg(), d);
+    }
+
     // ---- Karatsuba variant: 48 + 64 = 112 wide multiplies instead of 128 (NOT the default) ------------------------
     // Measured on B200 (tools/latbench.cu, 8 warps per sub-partition): 599 cycles per warp-product against 556 for
     // the CIOS form above, and k_accumulate 1.86 ms against 1.31 ms: ptxas needs 303 instructions (incl. IMAD.MOV /

@@ -40,6 +40,13 @@ def test_field_ops(ctx, which, m):
     assert np.array_equal(ctx.field_op(which, 4, A), orc.from_mont(which, A))
     assert np.array_equal(ctx.field_op(which, 6, A), orc.f_mul(which, A, A))  # dedicated squaring
     assert np.array_equal(ctx.field_op(which, 6, B), orc.f_mul(which, B, B))
+    # fused two-product routine of the group law: a*b + (a+b)(a-b) and a*b - b*b
+    sm, df = orc.f_add(which, A, B), orc.f_sub(which, A, B)
+    assert np.array_equal(ctx.field_op(which, 7, A, B), orc.f_add(which, orc.f_mul(which, A, B), orc.f_mul(which, sm, df)))
+    assert np.array_equal(ctx.field_op(which, 8, A, B), orc.f_sub(which, orc.f_mul(which, A, B), orc.f_mul(which, B, B)))
+    ea2 = mont([x for x in edge for _ in edge], m)
+    eb2 = mont([y for _ in edge for y in edge], m)
+    assert np.array_equal(ctx.field_op(which, 8, ea2, eb2), orc.f_sub(which, orc.f_mul(which, ea2, eb2), orc.f_mul(which, eb2, eb2)))
     assert np.array_equal(ctx.field_op(which, 5, ints_to_limbs(a)), A)
     assert np.array_equal(ctx.field_op(which, 3, A[:300]), orc.f_inv(which, A[:300]))
     # products of edge x edge (carry patterns)
