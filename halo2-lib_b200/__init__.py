@@ -22,6 +22,7 @@ from .evaluation import (  # noqa: F401,E402
     quotient_graph,
     permutation_fold,
     lookup_fold,
+    divide_by_vanishing_poly,
     eval_polynomial,
     kate_division,
     poly_lincomb,

@@ -108,6 +108,8 @@ SIGNATURES = {
     "h2b_permutation_fold_dev": (_int, [_vp, _vpp, _sz, _vpp, _vpp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
     "h2b_lookup_fold": (_int, [_vp, _gp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "h2b_lookup_fold_dev": (_int, [_vp, _gp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "h2b_divide_by_vanishing_poly": (_int, [_vp, _vp, _u32, _u32]),
+    "h2b_divide_by_vanishing_poly_dev": (_int, [_vp, _vp, _u32, _u32]),
     "h2b_eval_polynomial": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "h2b_eval_polynomial_dev": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "h2b_kate_division": (_int, [_vp, _vp, _sz, _vp, _vp]),

@@ -877,6 +877,25 @@ int h2b_permutation_fold(h2b_ctx* ctx, const uint64_t* const* z, size_t n_sets, 
     });
 }
 
+int h2b_divide_by_vanishing_poly_dev(h2b_ctx* ctx, void* d_values, uint32_t k, uint32_t ext_k) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_values, "divide_by_vanishing_poly: null pointer");
+        divide_by_vanishing_run(ctx, d_values, k, ext_k);
+    });
+}
+int h2b_divide_by_vanishing_poly(h2b_ctx* ctx, uint64_t* values, uint32_t k, uint32_t ext_k) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(values, "divide_by_vanishing_poly: null pointer");
+        H2B_REQUIRE(ext_k > k && ext_k <= 28, "quotient: extended_k out of range");
+        const size_t bytes = ((size_t)1 << ext_k) * 32;
+        void* d = ctx->get(WS_NTT_A, bytes);
+        H2B_CUDA(cudaMemcpyAsync(d, values, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        divide_by_vanishing_run(ctx, d, k, ext_k);
+        H2B_CUDA(cudaMemcpyAsync(values, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
 // ------------------------------------------------------------------------------------------------ opening arithmetic
 int h2b_eval_polynomial_dev(h2b_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t x[4], uint64_t out[4]) {
     return guarded(ctx, [&] {

@@ -180,6 +180,7 @@ void peer_destroy(h2b_ctx* ctx);
 // ---- quotient.cu
 void flex_gate_fold_run(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k, uint32_t ext_k,
                         void* d_acc);
+void divide_by_vanishing_run(h2b_ctx* ctx, void* d_values, uint32_t k, uint32_t ext_k);
 void quotient_graph_run(h2b_ctx* ctx, const h2b_graph* g, uint32_t k, uint32_t ext_k, void* d_values);
 void lookup_fold_run(h2b_ctx* ctx, const h2b_graph* g, const void* d_z, const void* d_pin, const void* d_ptab, const void* d_l0,
                      const void* d_l_last, const void* d_l_active, uint32_t k, uint32_t ext_k, void* d_values);

@@ -200,6 +200,27 @@ __global__ void __launch_bounds__(128) k_permutation_fold(PermDev p, const uint6
     v.store(values + 4 * idx);
 }
 
+// EvaluationDomain::divide_by_vanishing_poly: t(X) = X^n - 1 takes only 2^(ext_k - k) distinct values on the coset
+// zeta * <extended_omega> (period 2^(ext_k - k) in the row index): t_inv[j] = 1 / (zeta^n * (extended_omega^n)^j - 1).
+__global__ void k_vanishing_table(Fr zeta, Fr ext_omega, u32 k, u32 period, uint64_t* __restrict__ t_inv) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= period) return;
+    Fr zn = zeta, step = ext_omega;
+    for (u32 i = 0; i < k; i++) { zn = zn.sqr(); step = step.sqr(); }  // ^n, n = 2^k
+    Fr cur = zn;
+    for (u32 b = 0; (j >> b) != 0; b++) {
+        if ((j >> b) & 1) cur = cur * step;
+        step = step.sqr();
+    }
+    (cur - Fr::one()).inv().store(t_inv + 4 * (size_t)j);
+}
+__global__ void __launch_bounds__(256) k_divide_by_vanishing(const uint64_t* __restrict__ t_inv, u32 ext_k, u32 period_mask,
+                                                             uint64_t* __restrict__ values) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> ext_k) return;
+    (Fr::load(values + 4 * i) * Fr::load_nc(t_inv + 4 * (i & period_mask))).store(values + 4 * i);
+}
+
 static Fr fr_from(const uint64_t x[4]) {
     Fr r;
     memcpy(&r, x, sizeof(Fr));
@@ -291,6 +312,15 @@ static GraphDev graph_upload(h2b_ctx* ctx, const h2b_graph* g) {
 }
 
 static void check_domain(uint32_t k, uint32_t ext_k) { H2B_REQUIRE(ext_k >= k && ext_k <= 28, "quotient: extended_k out of range"); }
+
+void divide_by_vanishing_run(h2b_ctx* ctx, void* d_values, uint32_t k, uint32_t ext_k) {
+    check_domain(k, ext_k);
+    H2B_REQUIRE(ext_k > k, "divide_by_vanishing_poly: the extended domain must be larger than the domain (t vanishes on it otherwise)");
+    const u32 period = 1u << (ext_k - k);
+    uint64_t* t_inv = (uint64_t*)ctx->get(WS_MISC2, 32 * (size_t)period);
+    H2B_LAUNCH(ctx, k_vanishing_table, ceil_div(period, 64), 64, 0, fr_from(FR_ZETA_U64), fr_from(FR_OMEGA[ext_k]), k, period, t_inv);
+    H2B_LAUNCH(ctx, k_divide_by_vanishing, ceil_div((size_t)1 << ext_k, 256), 256, 0, t_inv, ext_k, period - 1, (uint64_t*)d_values);
+}
 
 void quotient_graph_run(h2b_ctx* ctx, const h2b_graph* g, uint32_t k, uint32_t ext_k, void* d_values) {
     check_domain(k, ext_k);

@@ -213,6 +213,13 @@ def permutation_fold(ctx: Context, z_sets, columns, sigma, chunk_len: int, l0, l
     return v
 
 
+def divide_by_vanishing_poly(ctx: Context, values, k: int, ext_k: int) -> np.ndarray:
+    """EvaluationDomain::divide_by_vanishing_poly on the extended coset"""
+    v = _u64(values, 4).copy()
+    ctx.check(lib.h2b_divide_by_vanishing_poly(ctx.h, _ptr(v), k, ext_k))
+    return v
+
+
 def eval_polynomial(ctx: Context, poly, point) -> np.ndarray:
     """arithmetic::eval_polynomial(poly, point)"""
     a, x = _u64(poly, 4), _u64(point, 4)

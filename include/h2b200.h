@@ -302,6 +302,11 @@ int h2b_lookup_fold_dev(h2b_ctx* ctx, const h2b_graph* graph, const void* d_z, c
                         const void* d_permuted_table, const void* d_l0, const void* d_l_last, const void* d_l_active,
                         uint32_t k, uint32_t ext_k, void* d_values);
 
+/* `EvaluationDomain::divide_by_vanishing_poly`: values[i] *= 1 / t(zeta * extended_omega^i), t(X) = X^(2^k) - 1 — the
+ * last pointwise step of the quotient before extended_to_coeff and the split into h pieces.  Requires ext_k > k. */
+int h2b_divide_by_vanishing_poly(h2b_ctx* ctx, uint64_t* values, uint32_t k, uint32_t ext_k);
+int h2b_divide_by_vanishing_poly_dev(h2b_ctx* ctx, void* d_values, uint32_t k, uint32_t ext_k);
+
 /* ---- opening arithmetic: halo2-axiom 0.5.3 `arithmetic::{eval_polynomial, kate_division}`
  * and the polynomial linear combinations of `poly/kzg/multiopen/shplonk/prover.rs` ------------------------------- */
 /* out = sum_i coeffs[i] * x^i */

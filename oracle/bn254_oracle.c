@@ -849,6 +849,23 @@ int orc_permute_expression_pair(const u64 *input, const u64 *table, unsigned k, 
     free(a); free(t); free(count); free(repeated);
     return rc;
 }
+/* EvaluationDomain::divide_by_vanishing_poly (halo2-axiom 0.5.3 poly/domain.rs, restated): the table of
+ * t(zeta * extended_omega^i) = zeta^n * (extended_omega^n)^i - 1 is built by walking until it repeats, inverted, and
+ * applied with period 2^(ext_k - k). */
+void orc_divide_by_vanishing_poly(u64 *values, unsigned k, unsigned ext_k) {
+    size_t period = (size_t)1 << (ext_k - k), n_ext = (size_t)1 << ext_k;
+    u64 orig[4], step[4], cur[4], *t = (u64 *)malloc(period * 32);
+    zeta_mont(orig); orc_omega(ext_k, step);
+    for (unsigned i = 0; i < k; i++) { f_mul(&FR, orig, orig, orig); f_mul(&FR, step, step, step); }
+    memcpy(cur, orig, 32);
+    for (size_t j = 0; j < period; j++) {
+        f_sub(&FR, t + 4 * j, cur, FR.one);
+        f_inv(&FR, t + 4 * j, t + 4 * j);
+        f_mul(&FR, cur, cur, step);
+    }
+    for (size_t i = 0; i < n_ext; i++) f_mul(&FR, values + 4 * i, values + 4 * i, t + 4 * (i % period));
+    free(t);
+}
 /* ---- opening arithmetic: halo2-axiom 0.5.3 arithmetic.rs `eval_polynomial` (Horner) and `kate_division` */
 void orc_eval_polynomial(const u64 *coeffs, size_t n, const u64 *x, u64 *out) {
     u64 acc[4] = {0, 0, 0, 0};

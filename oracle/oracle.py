@@ -304,3 +304,9 @@ def srs_setup(tau, base_xy, k):
     g, gl = np.empty((1 << k, 8), dtype=np.uint64), np.empty((1 << k, 8), dtype=np.uint64)
     lib().orc_srs_setup(_p(t), _p(b), C.c_uint(k), _p(g), _p(gl))
     return g, gl
+
+
+def divide_by_vanishing_poly(values, k, ext_k):
+    v = np.array(values, dtype=np.uint64).reshape(-1, 4).copy()
+    lib().orc_divide_by_vanishing_poly(_p(v), C.c_uint(k), C.c_uint(ext_k))
+    return v

@@ -392,3 +392,11 @@ def test_lookup_argument_end_to_end(ctx, h2b):
     numer = h2b.lookup_fold(ctx, bound, ext(z), ext(pa), ext(pt), ext(mont(l0, R)), ext(mont(l_last, R)), ext(mont(l_active, R)), k, ext_k,
                             np.zeros((1 << ext_k, 4), dtype=np.uint64))
     assert all(v == 0 for v in on_domain_values(ctx, h2b, numer, k, ext_k, range(n)))
+
+
+@pytest.mark.parametrize("k,ext_k", [(4, 5), (9, 11), (12, 15), (17, 19)])
+def test_divide_by_vanishing_poly(ctx, h2b, k, ext_k):
+    v = rnd_fr(np.random.default_rng(2700 + k), 1 << ext_k)
+    assert np.array_equal(h2b.divide_by_vanishing_poly(ctx, v, k, ext_k), orc.divide_by_vanishing_poly(v, k, ext_k))
+    with pytest.raises(h2b.H2BError):
+        h2b.divide_by_vanishing_poly(ctx, v[: 1 << k], k, k)

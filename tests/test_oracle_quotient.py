@@ -197,3 +197,23 @@ def test_permute_expression_pair_missing_value():
     inputs = [3] * (u - 1) + [u + 9]
     rc, _, _ = orc.permute_expression_pair(mont(inputs + [0] * (bf + 1), R), mont(table + [0] * (bf + 1), R), k, bf)
     assert rc == -1 and pyref.permute_expression_pair(inputs, table) is None
+
+
+def test_divide_by_vanishing_poly_vs_python():
+    k, ext_k = 3, 5
+    n, ne = 1 << k, 1 << ext_k
+    rng = np.random.default_rng(48)
+    vals = rand_ints(rng, ne, R)
+    got = unmont(orc.divide_by_vanishing_poly(mont(vals, R), k, ext_k), R)
+    w = pyref.omega_for(ext_k)
+    want = [v * pow((pow(pyref.ZETA * pow(w, i, R) % R, n, R) - 1) % R, -1, R) % R for i, v in enumerate(vals)]
+    assert got == want
+    # a multiple of t(X) = X^n - 1 of degree < 2^ext_k divides exactly: (X^n - 1) * g(X) evaluated on the coset, divided, gives g
+    gcoef = rand_ints(rng, n, R)
+    prod = [0] * (2 * n)
+    for i, c in enumerate(gcoef):
+        prod[i] = (prod[i] - c) % R
+        prod[i + n] = (prod[i + n] + c) % R
+    ext = orc.coeff_to_extended(mont(prod, R), ext_k)
+    back = unmont(orc.extended_to_coeff(orc.divide_by_vanishing_poly(ext, k, ext_k), ext_k), R)
+    assert back[:n] == gcoef and not any(back[n:])
