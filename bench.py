@@ -498,17 +498,17 @@ def run_b200(args):
     # field products of the average launch (estimate): entries = pairs * windows * P(non-zero digit); witness-like columns
     # keep ~23% of their digits (35% zeros, 25% ones, 30% 88-bit limbs, 10% full width)
     entries = n_loc * params_windows * (sum(1.0 if c == "uniform" else 0.23 for _, c in MSM_SCHEDULE) / len(MSM_SCHEDULE))
-    products = 10.0 * entries
+    products = 9.06 * entries  # a mixed addition = 1160 wide multiplies = 9.06 x the 128 of one full product
     roofline = {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch on a uniform column at k=19, single GPU, from the
-                # `ncu --set full` capture summarised in profiles/ (976.2 + 37.3 MB)
-                "traffic": 1013457920 if (k == 19 and world == 1) else None, "peak_source": peak_src,
+                # `ncu --set full` capture summarised in profiles/ (979.2 + 37.7 MB)
+                "traffic": 1016869632 if (k == 19 and world == 1) else None, "peak_source": peak_src,
                 "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt, "algorithmic_bytes_per_launch": 96 * n_loc,
                 "timed_region_note": "launches of the timed region overlap with the kernels of the other two MSM lanes, which stretches each launch",
                 "isolated": {"avg_launch_ms": iso_avg_ms, "launches": iso_cnt, "achieved": achieved_iso, "frac": achieved_iso / peak,
                              "integer_multiplier": {"products_per_s": products / (iso_avg_ms / 1e3), "peak_products_per_s": 66.9e9,
                                                     "frac": products / (iso_avg_ms / 1e3) / 66.9e9,
-                                                    "note": "estimate: 10 Montgomery products per XYZZ mixed add x non-zero digits; peak = tools/latbench.cu (profiles/r01_pipe_microbench.txt)"}},
+                                                    "note": "estimate: 9.06 Montgomery-product equivalents per XYZZ mixed add (6 products + 2 squarings at 100/128 + one fused two-product at 192/128) x non-zero digits; peak = tools/latbench.cu (profiles/r01_pipe_microbench.txt)"}},
                 "note": "bucket accumulation is bound by the integer multiplier (IMAD.WIDE), not by HBM: traffic is ~10% of HBM peak; see DESIGN.md 4.1/4.2"}
     h2d = (len(MSM_SCHEDULE) * n_loc * 32 + (N_INTT * n * 32 + N_COSET * n * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n_cells * 32)
     d2h = (len(MSM_SCHEDULE) * 96 + (N_INTT * n * 32 + N_COSET * (1 << ext_k) * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n * 32)

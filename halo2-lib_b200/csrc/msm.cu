@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ bu
         const u32 hi = idx - (1u << ml);
         for (u32 lo = qid; lo < (1u << ml); lo += 32) quad_add(acc, XYZZ::load(base + ((size_t)hi << ml) + lo));
     }
-    acc = quad_block_sum(acc, sh);
+    acc = quad_block_sum<true>(acc, sh);
     // quad 0 of warp 0 holds the sum: store it already multiplied by its weight (lo for a row, hi for a column) so
     // that the final kernel only has plain sums left; the plain column sums are kept too (T = sum of all buckets)
     if (threadIdx.x < 4) {
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ bu
         const u32 weight = is_row ? idx : idx - (1u << ml);
         XYZZ* out = rc + (size_t)set * ((1u << ml) + 2 * (1u << mh));
         if (!is_row && threadIdx.x == 0) acc.store(out + (1u << ml) + (1u << mh) + weight);
-        XYZZ w = quad_small_mul(acc, weight, is_row ? ml : mh);
+        XYZZ w = quad_small_mul<true>(acc, weight, is_row ? ml : mh);
         if (threadIdx.x == 0) w.store(out + idx);
     }
 }

@@ -118,21 +118,26 @@ __device__ __forceinline__ XYZZ quad_shfl_down(const XYZZ& v, int delta_quads) {
     return r;
 }
 // sum over the 8 quads of a warp; valid in quad 0 (lanes 0..3).  All lanes must call.
+// INL = true inlines the point operations: right for kernels with hundreds of CTAs running the same code
+// (k_rowcol_sums: 90 us inlined, 127 us through the out-of-line copies); the lone-warp kernels use INL = false.
+template <bool INL = false>
 __device__ __forceinline__ XYZZ quad_warp_sum(XYZZ v) {
 #pragma unroll 1
     for (int dq = 4; dq >= 1; dq >>= 1) {
         __syncwarp();
         XYZZ o = quad_shfl_down(v, dq);
-        quad_add_nl(v, o);
+        if (INL) quad_add(v, o);
+        else quad_add_nl(v, o);
     }
     __syncwarp();
     return v;
 }
 // sum over all quads of the CTA (blockDim.x multiple of 32, <= 1024); valid in quad 0 of warp 0.
 // sh must hold one XYZZ per warp.
+template <bool INL = false>
 __device__ __forceinline__ XYZZ quad_block_sum(XYZZ v, XYZZ* sh) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    v = quad_warp_sum(v);
+    v = quad_warp_sum<INL>(v);
     __syncthreads();  // sh may still be read from a previous call
     if (lane == 0) v.store(sh + wid);
     __syncthreads();
@@ -140,19 +145,28 @@ __device__ __forceinline__ XYZZ quad_block_sum(XYZZ v, XYZZ* sh) {
     if (wid == 0) {
         // quad k of warp 0 takes the results of warps k, k+8, k+16, k+24 (serial), then the 8 quads are summed
         const int qid = lane >> 2;
-        for (int w = qid; w < nw; w += 8) quad_add_nl(r, XYZZ::load(sh + w));
-        r = quad_warp_sum(r);
+        for (int w = qid; w < nw; w += 8) {
+            if (INL) quad_add(r, XYZZ::load(sh + w));
+            else quad_add_nl(r, XYZZ::load(sh + w));
+        }
+        r = quad_warp_sum<INL>(r);
     }
     return r;
 }
 
 // k * p by left-to-right double-and-add, k < 2^bits
+template <bool INL = false>
 __device__ __forceinline__ XYZZ quad_small_mul(const XYZZ& p, u32 k, int bits) {
     XYZZ acc = XYZZ::identity();
 #pragma unroll 1
     for (int b = bits - 1; b >= 0; b--) {
-        quad_dbl_nl(acc);
-        if ((k >> b) & 1) quad_add_nl(acc, p);
+        if (INL) {
+            quad_dbl(acc);
+            if ((k >> b) & 1) quad_add(acc, p);
+        } else {
+            quad_dbl_nl(acc);
+            if ((k >> b) & 1) quad_add_nl(acc, p);
+        }
     }
     return acc;
 }

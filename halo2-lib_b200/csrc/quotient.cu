@@ -43,6 +43,8 @@ void flex_gate_fold_run(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, 
 
 namespace h2b {
 
+static constexpr u32 CALC_NOP = 8;  // internal: see graph_upload
+
 struct GraphDev {
     const u32* program;
     u32 n_calc, result;
@@ -83,6 +85,7 @@ __device__ __forceinline__ Fr graph_eval(const GraphDev& g, size_t idx, size_t m
 #pragma unroll 1
     for (u32 t = 0; t < g.n_calc; t++) {
         const u32 op = __ldg(pc++);
+        if (op == CALC_NOP) continue;  // a Store the host resolved into its users
         Fr r;
         if (op == H2B_CALC_HORNER) {
             r = graph_fetch(g, __ldg(pc), idx, mask, rshift, prev, inter);
@@ -274,14 +277,51 @@ static void graph_validate(const h2b_graph* g) {
 }
 
 // packs program + tables into one device blob (slot WS_MISC) and returns the device view
+// `Store(x)` calculations (every column query of an expression becomes one) are resolved on the host: users of the
+// intermediate read x directly and the Store becomes a no-op, which halves the local-memory traffic of the interpreter
+// for halo2-base's gate (5 of its 10 calculations are Stores).
+static std::vector<u32> graph_resolve_stores(const h2b_graph* g, u32* result) {
+    std::vector<u32> out, alias(g->n_calculations, 0);
+    std::vector<char> has(g->n_calculations, 0);
+    auto res = [&](u32 src) {
+        const u32 kind = src & 15u, index = (src >> 4) & 0xffffu;
+        return (kind == H2B_SRC_INTERMEDIATE && has[index]) ? alias[index] : src;
+    };
+    size_t pc = 0;
+    for (u32 t = 0; t < g->n_calculations; t++) {
+        const u32 op = g->program[pc++];
+        if (op == H2B_CALC_STORE) {
+            alias[t] = res(g->program[pc++]);
+            has[t] = 1;
+            out.push_back(CALC_NOP);
+        } else if (op == H2B_CALC_HORNER) {
+            const u32 np = g->program[pc + 2];
+            out.push_back(op);
+            out.push_back(res(g->program[pc]));
+            out.push_back(res(g->program[pc + 1]));
+            out.push_back(np);
+            for (u32 j = 0; j < np; j++) out.push_back(res(g->program[pc + 3 + j]));
+            pc += 3 + np;
+        } else {
+            out.push_back(op);
+            out.push_back(res(g->program[pc++]));
+            if (op <= H2B_CALC_MUL) out.push_back(res(g->program[pc++]));
+        }
+    }
+    *result = res(g->result);
+    return out;
+}
+
 static GraphDev graph_upload(h2b_ctx* ctx, const h2b_graph* g) {
     graph_validate(g);
+    u32 result = 0;
+    const std::vector<u32> program = graph_resolve_stores(g, &result);
     auto al = [](size_t x) { return (x + 31) & ~(size_t)31; };
-    const size_t o_prog = 0, o_const = al(o_prog + 4 * (g->program_words + 1)), o_rot = al(o_const + 32 * g->n_constants),
+    const size_t o_prog = 0, o_const = al(o_prog + 4 * (program.size() + 1)), o_rot = al(o_const + 32 * g->n_constants),
                  o_fix = al(o_rot + 4 * g->n_rotations), o_adv = al(o_fix + 8 * g->n_fixed), o_ins = al(o_adv + 8 * g->n_advice),
                  o_ch = al(o_ins + 8 * g->n_instance), total = al(o_ch + 32 * g->n_challenges) + 32;
     std::vector<char> host(total, 0);
-    if (g->program_words) memcpy(host.data() + o_prog, g->program, 4 * g->program_words);
+    if (!program.empty()) memcpy(host.data() + o_prog, program.data(), 4 * program.size());
     if (g->n_constants) memcpy(host.data() + o_const, g->constants, 32 * g->n_constants);
     if (g->n_rotations) memcpy(host.data() + o_rot, g->rotations, 4 * g->n_rotations);
     if (g->n_fixed) memcpy(host.data() + o_fix, g->fixed, 8 * g->n_fixed);
@@ -297,7 +337,7 @@ static GraphDev graph_upload(h2b_ctx* ctx, const h2b_graph* g) {
     GraphDev r;
     r.program = (const u32*)(d + o_prog);
     r.n_calc = g->n_calculations;
-    r.result = g->result;
+    r.result = result;
     r.constants = (const uint64_t*)(d + o_const);
     r.rotations = (const int32_t*)(d + o_rot);
     r.fixed = (const uint64_t* const*)(d + o_fix);

@@ -11,6 +11,7 @@ from halo2_lib_b200._capi import lib
 from oracle import oracle as orc
 
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 19
+QUICK = "--quick" in sys.argv  # one repetition, no CPU leg: the target of an `ncu --set full` capture
 ext_k, n, bf = k + 2, 1 << k, 5
 ne = 1 << ext_k
 dev = torch.device("cuda", 0)
@@ -32,6 +33,8 @@ vp = C.c_void_p
 acc = torch.from_numpy(rnd(ne).view(np.int64)).to(dev)
 
 def timeit(label, fn, bytes_alg, cpu=None, reps=10):
+    if QUICK:
+        reps, cpu = 1, None
     fn(); torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tot = 0.0
