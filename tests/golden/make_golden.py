@@ -62,4 +62,31 @@ json.dump({"k": 4, "threads": [[hexs(v) for v in t] for t in threads], "break_po
            "columns": [[hexs(v) for v in c] for c in cols],
            "lookup_values": [hexs(v) for t in threads for v in t][:11], "lookup_columns": [[hexs(v) for v in c] for c in lk]},
           open(os.path.join(HERE, "assign.json"), "w"), indent=1)
-print("wrote msm_g1.json ntt_fr.json assign.json")
+
+# ---- next rows: opening arithmetic, the lookup permutation, quotient terms — k = 3, extended 2^5
+k, ext_k, bf = 3, 5, 2
+n, ne, u = 1 << k, 1 << ext_k, (1 << k) - 3
+poly = [rnd.randrange(p.R) for _ in range(11)]
+z = rnd.randrange(p.R)
+table = [4, 9, 9, 2, 7]
+inputs = [9, 2, 9, 9, 4]
+a_perm, s_perm = p.permute_expression_pair(inputs, table)
+col = lambda: [rnd.randrange(p.R) for _ in range(ne)]
+zs, cs, ss = [col(), col()], [col(), col(), col()], [col(), col(), col()]
+l0, l_last, l_active, start = col(), col(), col(), col()
+beta, gamma, y = (rnd.randrange(p.R) for _ in range(3))
+perm = p.permutation_terms(zs, cs, ss, 2, l0, l_last, l_active, beta, gamma, y, bf, k, ext_k, start)
+tv, zc, ap, sp = col(), col(), col(), col()
+lookup = p.lookup_terms(tv, zc, ap, sp, l0, l_last, l_active, beta, gamma, y, k, ext_k, start)
+H = lambda xs: [hexs(v) for v in xs]
+json.dump({
+    "note": "BN254 Fr, canonical integers; formulas of oracle/pyref.py (halo2 evaluate_h / arithmetic restated)",
+    "k": k, "extended_k": ext_k, "blinding_factors": bf,
+    "poly": H(poly), "point": hexs(z), "eval_polynomial": hexs(p.eval_polynomial(poly, z)), "kate_division": H(p.kate_division(poly, z)),
+    "lookup_inputs": H(inputs), "lookup_table": H(table), "permuted_input": H(a_perm), "permuted_table": H(s_perm),
+    "z_sets": [H(c) for c in zs], "columns": [H(c) for c in cs], "sigma": [H(c) for c in ss], "chunk_len": 2,
+    "l0": H(l0), "l_last": H(l_last), "l_active": H(l_active), "start": H(start), "beta": hexs(beta), "gamma": hexs(gamma), "y": hexs(y),
+    "permutation_fold": H(perm),
+    "table_values": H(tv), "lookup_z": H(zc), "lookup_a": H(ap), "lookup_s": H(sp), "lookup_fold": H(lookup),
+}, open(os.path.join(HERE, "next_rows.json"), "w"), indent=1)
+print("wrote msm_g1.json ntt_fr.json assign.json next_rows.json")

@@ -25,7 +25,7 @@ def _msm_cases():
 def test_golden_regenerates_identically():
     """the generator is deterministic: the committed files are what pyref produces today"""
     import subprocess, sys, hashlib
-    before = {f: hashlib.sha256(open(os.path.join(G, f), "rb").read()).hexdigest() for f in ("msm_g1.json", "ntt_fr.json", "assign.json")}
+    before = {f: hashlib.sha256(open(os.path.join(G, f), "rb").read()).hexdigest() for f in ("msm_g1.json", "ntt_fr.json", "assign.json", "next_rows.json")}
     subprocess.check_call([sys.executable, os.path.join(G, "make_golden.py")], stdout=subprocess.DEVNULL)
     after = {f: hashlib.sha256(open(os.path.join(G, f), "rb").read()).hexdigest() for f in before}
     assert before == after
@@ -50,6 +50,50 @@ def test_oracle_matches_golden():
     assert rc == 0 and [limbs_to_ints(c) for c in cols] == [ints(c) for c in d["columns"]]
     rc, lk = orc.assign_lookups(ints_to_limbs(ints(d["lookup_values"])), d["k"], 3)
     assert rc == 0 and [limbs_to_ints(c) for c in lk] == [ints(c) for c in d["lookup_columns"]]
+
+
+def _next_rows(lib_eval, lib_kate, lib_permute, lib_perm_fold, lib_lookup_fold):
+    """shared by the CPU (oracle) and GPU (CUDA) checks of tests/golden/next_rows.json"""
+    d = json.load(open(os.path.join(G, "next_rows.json")))
+    k, ek, bf = d["k"], d["extended_k"], d["blinding_factors"]
+    m = lambda xs: mont(ints(xs), R)
+    m1 = lambda x: mont([int(x, 16)], R)[0]
+    assert unmont(lib_eval(m(d["poly"]), m1(d["point"])).reshape(1, 4), R) == [int(d["eval_polynomial"], 16)]
+    assert unmont(lib_kate(m(d["poly"]), m1(d["point"])), R) == ints(d["kate_division"])
+    pad = [0] * (bf + 1)
+    pa, pt = lib_permute(mont(ints(d["lookup_inputs"]) + pad, R), mont(ints(d["lookup_table"]) + pad, R), k, bf)
+    u = (1 << k) - (bf + 1)
+    assert unmont(pa[:u], R) == ints(d["permuted_input"]) and unmont(pt[:u], R) == ints(d["permuted_table"])
+    got = lib_perm_fold([m(c) for c in d["z_sets"]], [m(c) for c in d["columns"]], [m(c) for c in d["sigma"]], d["chunk_len"], m(d["l0"]),
+                        m(d["l_last"]), m(d["l_active"]), m1(d["beta"]), m1(d["gamma"]), m1(d["y"]), bf, k, ek, m(d["start"]))
+    assert unmont(got, R) == ints(d["permutation_fold"])
+    # the lookup's table value comes from a one-calculation program: Store(fixed column 0)
+    from halo2_lib_b200 import evaluation as ev
+    g = ev.GraphEvaluator()
+    res = g.add_calculation((ev.STORE, ev.src(ev.FIXED, 0, g.add_rotation(0))))
+    bound = ev.BoundGraph(g, res, fixed=[m(d["table_values"])], beta=m1(d["beta"]), gamma=m1(d["gamma"]), y=m1(d["y"]))
+    got = lib_lookup_fold(bound, m(d["lookup_z"]), m(d["lookup_a"]), m(d["lookup_s"]), m(d["l0"]), m(d["l_last"]), m(d["l_active"]), k, ek,
+                          m(d["start"]))
+    assert unmont(got, R) == ints(d["lookup_fold"])
+
+
+def test_oracle_matches_golden_next_rows():
+    def permute(a, t, k, bf):
+        rc, pa, pt = orc.permute_expression_pair(a, t, k, bf)
+        assert rc == 0
+        return pa, pt
+    _next_rows(orc.eval_polynomial, orc.kate_division, permute, orc.permutation_fold,
+               lambda b, *a: orc.lookup_fold(b.struct, *a))
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden_next_rows():
+    import halo2_lib_b200 as h
+    ctx = h.Context(0)
+    _next_rows(lambda a, x: h.eval_polynomial(ctx, a, x), lambda a, x: h.kate_division(ctx, a, x),
+               lambda a, t, k, bf: h.permute_expression_pair(ctx, a, t, k, bf),
+               lambda *a: h.permutation_fold(ctx, *a), lambda *a: h.lookup_fold(ctx, *a))
+    ctx.close()
 
 
 @pytest.mark.gpu
