@@ -964,7 +964,7 @@ int h2b_poly_lincomb(h2b_ctx* ctx, const uint64_t* const* polys, const uint64_t*
 // ------------------------------------------------------------------------------------------------ test hook
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
     return guarded(ctx, [&] {
-        H2B_REQUIRE(a && out && (b || (op > 2 && op < 7)) && (field == 0 || field == 1) && op >= 0 && op <= 8, "field_op: bad argument");
+        H2B_REQUIRE(a && out && (b || (op > 2 && op < 7) || op == 9) && (field == 0 || field == 1) && op >= 0 && op <= 9, "field_op: bad argument");
         if (n == 0) return;
         char* d = (char*)ctx->get(WS_ASSIGN_IN, 3 * n * 32);
         H2B_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));

@@ -516,6 +516,59 @@ struct __align__(16) Fp {
         }
         return acc;
     }
+
+    // a^-1 by the binary extended Euclidean algorithm: shifts, compares and modular add / sub only, no products.
+    // For code where ONE lane inverts while the rest of the CTA waits (k_batch_invert, the small set-up kernels): the
+    // Fermat chain above is ~260 dependent squarings = 165 us on a lone warp, this is ~500 halvings + ~250
+    // subtractions of 8-limb integers.  Data-dependent branches: do not use it where all lanes invert different values.
+    // Invariant: x1 * A = u, x2 * A = v (mod p) with A the value held in the limbs (the Montgomery form aR), so the
+    // loop ends with (aR)^-1 as a plain residue; one Montgomery product with R^3 turns that into a^-1 R.  inv(0) = 0.
+    __device__ __noinline__ Fp inv_bgcd() const {
+        if (is_zero()) return *this;
+        Fp u = *this, v, x1 = zero(), x2 = zero();
+#pragma unroll
+        for (int i = 0; i < 8; i++) v.l[i] = P::MOD(i);
+        x1.l[0] = 1;
+        auto shr1 = [](Fp& a) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) a.l[i] = __funnelshift_r(a.l[i], a.l[i + 1], 1);
+            a.l[7] >>= 1;
+        };
+        auto halve = [&](Fp& x) {  // x / 2 mod p: x < p < 2^254, so x + p does not overflow 256 bits
+            if (x.l[0] & 1) {
+                add_cc(x.l[0], x.l[0], P::MOD(0));
+#pragma unroll
+                for (int i = 1; i < 7; i++) addc_cc(x.l[i], x.l[i], P::MOD(i));
+                addc(x.l[7], x.l[7], P::MOD(7));
+            }
+            shr1(x);
+        };
+        auto is_one = [](const Fp& a) { return a.l[0] == 1 && (a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0; };
+        auto sub_if_geq = [](Fp& a, const Fp& b) -> bool {  // a >= b ? (a -= b, true) : false
+            Fp d;
+            u32 borrow;
+            sub_cc(d.l[0], a.l[0], b.l[0]);
+#pragma unroll
+            for (int i = 1; i < 8; i++) subc_cc(d.l[i], a.l[i], b.l[i]);
+            subc(borrow, 0, 0);
+            if (borrow) return false;
+            a = d;
+            return true;
+        };
+        Fp r;
+#pragma unroll 1
+        for (;;) {
+#pragma unroll 1
+            while (!(u.l[0] & 1)) { shr1(u); halve(x1); }
+            if (is_one(u)) { r = x1; break; }
+#pragma unroll 1
+            while (!(v.l[0] & 1)) { shr1(v); halve(x2); }
+            if (is_one(v)) { r = x2; break; }
+            if (sub_if_geq(u, v)) x1 = x1 - x2;
+            else { sub_if_geq(v, u); x2 = x2 - x1; }
+        }
+        return r * (r2() * r2());  // R^2 * R^2 * R^-1 = R^3;  r * R^3 * R^-1 = r R^2 = a^-1 R
+    }
 };
 
 typedef Fp<FqParams> Fq;

@@ -69,7 +69,7 @@ __global__ void k_pow_table(Fr omega, uint64_t mult, u32 count, Fr* __restrict__
 __global__ void k_n_inv(u32 log_n, Fr* out) {
     Fr two = Fr::one() + Fr::one(), acc = Fr::one();
     for (u32 i = 0; i < log_n; i++) acc = acc * two;
-    acc.inv().store(out);
+    acc.inv_bgcd().store(out);
 }
 
 // tw_full[g] = omega_t^(row * j') (times n_inv when given) for every in-place address g of a non-last pass

@@ -215,7 +215,7 @@ __global__ void k_vanishing_table(Fr zeta, Fr ext_omega, u32 k, u32 period, uint
         if ((j >> b) & 1) cur = cur * step;
         step = step.sqr();
     }
-    (cur - Fr::one()).inv().store(t_inv + 4 * (size_t)j);
+    (cur - Fr::one()).inv_bgcd().store(t_inv + 4 * (size_t)j);
 }
 __global__ void __launch_bounds__(256) k_divide_by_vanishing(const uint64_t* __restrict__ t_inv, u32 ext_k, u32 period_mask,
                                                              uint64_t* __restrict__ values) {

@@ -13,8 +13,8 @@ namespace h2b {
 // ---------------------------------------------------------------- batch inversion
 // One Fermat inversion per CTA of 256 threads x E elements (thread t owns elements base + e*256 + t, coalesced):
 //   1. every thread multiplies its non-zero elements;  2. block-wide exclusive prefix / suffix products of the thread
-//   totals;  3. thread 0 inverts the CTA total (the only long dependency chain: ~380 products, ~165 us of latency
-//   that the other resident CTAs cover);  4. thread t starts from u = total^-1 * (product of the threads after t)
+//   totals;  3. thread 0 inverts the CTA total (binary extended Euclid, Fp::inv_bgcd: the only long dependency chain,
+//   which the other resident CTAs cover);  4. thread t starts from u = total^-1 * (product of the threads after t)
 //   and walks its elements backwards: a_i^-1 = u * (everything before i), u *= a_i.
 // 4 products per element plus the scans; the per-thread inversion this replaces cost ~47 products per element.
 __device__ __forceinline__ Fr block_exclusive_prefix_product(Fr v, Fr* sh /* 256 */, Fr* total);
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_batch_invert(uint64_t* __restrict__ a, 
     Fr total;
     const Fr before = block_exclusive_prefix_product(mine, sh, &total);
     const Fr after = block_exclusive_suffix_product(mine, sh);
-    if (threadIdx.x == 0) sh_inv = total.inv();
+    if (threadIdx.x == 0) sh_inv = total.inv_bgcd();  // one lane: the product-free inversion has the shorter chain
     // forward again: running product of everything before element i (threads before me, then my earlier elements)
     Fr run = before;
     for (int e = 0; e < E; e++) {

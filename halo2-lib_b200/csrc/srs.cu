@@ -61,7 +61,7 @@ __global__ void k_srs_consts(Fr x, u32 k, uint64_t* __restrict__ pw, uint64_t* _
     }
     Fr n = Fr::zero();
     n.l[k >> 5] = 1u << (k & 31);
-    const Fr n_inv = n.to_mont().inv();
+    const Fr n_inv = n.to_mont().inv_bgcd();
     n_inv.from_mont().store(extra);
     ((xn - Fr::one()) * n_inv).store(extra + 4);
 }

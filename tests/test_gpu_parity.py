@@ -49,6 +49,7 @@ def test_field_ops(ctx, which, m):
     assert np.array_equal(ctx.field_op(which, 8, ea2, eb2), orc.f_sub(which, orc.f_mul(which, ea2, eb2), orc.f_mul(which, eb2, eb2)))
     assert np.array_equal(ctx.field_op(which, 5, ints_to_limbs(a)), A)
     assert np.array_equal(ctx.field_op(which, 3, A[:300]), orc.f_inv(which, A[:300]))
+    assert np.array_equal(ctx.field_op(which, 9, A[:600]), orc.f_inv(which, A[:600]))  # binary-Euclid inversion (single-lane paths)
     # products of edge x edge (carry patterns)
     ea = [x for x in edge for _ in edge]
     eb = [y for _ in edge for y in edge]
