@@ -374,23 +374,37 @@ def run_b200(args):
     side_pool = ThreadPoolExecutor(max_workers=1)  # the host thread that drives the transform context (ctypes drops the GIL)
 
     def ntt_side_host(polys):
-        """h2b_*_batch on the second context: pinned host buffers in and out, PCIe legs pipelined inside the call"""
-        a = [i for i in polys if my_ntt(i)]
+        """h2b_lagrange_to_coeff_and_extended_batch on the second context: pinned host buffers in and out, the coefficients
+        stay on the device between the two transforms, PCIe legs pipelined against the kernels inside the call"""
+        both = [i for i in polys if my_ntt(i) and my_ntt(N_INTT + i)]
+        if both:
+            pa = (C.c_void_p * len(both))(*[polys_host[i].data_ptr() for i in both])
+            pe = (C.c_void_p * len(both))(*[ext_host[i].data_ptr() for i in both])
+            ctx_ntt.check(lib.h2b_lagrange_to_coeff_and_extended_batch(ctx_ntt.h, pa, len(both), k, ext_k, pe))
+        a = [i for i in polys if my_ntt(i) and i not in both]
         if a:
             ptrs = (C.c_void_p * len(a))(*[polys_host[i].data_ptr() for i in a])
             ctx_ntt.check(lib.h2b_lagrange_to_coeff_batch(ctx_ntt.h, ptrs, len(a), k))
-        b = [i for i in polys if my_ntt(N_INTT + i)]
+        b = [i for i in polys if my_ntt(N_INTT + i) and i not in both]
         if b:
             pin = (C.c_void_p * len(b))(*[polys_host[i].data_ptr() for i in b])
             pout = (C.c_void_p * len(b))(*[ext_host[i].data_ptr() for i in b])
             ctx_ntt.check(lib.h2b_coeff_to_extended_batch(ctx_ntt.h, pin, len(b), n, ext_k, pout))
 
+    trace = [] if os.environ.get("H2B_E2E_TRACE") else None  # host wall-clock marks of one e2e step (diagnostic, stderr)
+
+    def mark(label):
+        if trace is not None:
+            trace.append((label, time.perf_counter()))
+
     def step_e2e(overlap=True):
         """the same step through the host-pointer C ABI: pinned host buffers in, host buffers out.  With `overlap` a second
         host thread drives the transforms of the polynomials that already exist (same dependency model as step_resident)
         through a second context, so their PCIe traffic runs beside the commitment phases."""
+        mark("start")
         if rank == 0:
             ctx.check(lib.h2b_assign_columns(ctx.h, vp(vcol_host.data_ptr()), n_cells, None, 0, k, 1, vp(acol_host.data_ptr())))
+        mark("assign")
         pending = []
         for pi, phase in enumerate(MSM_PHASES):
             if pi in NTT_READY:
@@ -402,8 +416,10 @@ def run_b200(args):
                         f.result()
                 else:
                     ntt_side_host([0, 1, 2, 3, 4])
+                mark("join_side")
                 if my_ntt(N_INTT + N_COSET):
                     ctx.check(lib.h2b_extended_to_coeff(ctx.h, vp(ext_host[0].data_ptr()), ext_k))
+                mark("ext_to_coeff")
             m = len(phase)
             ptrs = (C.c_void_p * m)(*[cols_host[j].data_ptr() for j in phase])
             bs = (C.c_int * m)(*[basis_id[j] for j in phase])
@@ -416,6 +432,7 @@ def run_b200(args):
                     ctx.check(lib.h2b_g1_sum_dev(ctx.h, vp(g[jj].data_ptr()), world, vp(t[jj].data_ptr())))
                 out = t.cpu().numpy().view(np.uint64)
             outs_host[phase] = out
+            mark("phase%d" % pi)
 
     def barrier():
         if world > 1:
@@ -454,6 +471,12 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 5)), 1)
     ms_e2e_seq, _ = timed(lambda: step_e2e(False), max(1, min(args.steps, 3)), 1)
+    if trace is not None and rank == 0:
+        trace.clear()
+        step_e2e(True)
+        torch.cuda.synchronize()
+        t0 = trace[0][1]
+        print("e2e trace (ms since start): " + ", ".join("%s=%.2f" % (l, 1e3 * (t - t0)) for l, t in trace[1:]), file=sys.stderr)
 
     # per-op device timings (context for the headline; same CUDA-event method, 3 reps each)
     def time_op(fn, reps=3):
@@ -510,7 +533,9 @@ def run_b200(args):
                                                     "frac": products / (iso_avg_ms / 1e3) / 66.9e9,
                                                     "note": "estimate: 9.06 Montgomery-product equivalents per XYZZ mixed add (6 products + 2 squarings at 100/128 + one fused two-product at 192/128) x non-zero digits; peak = tools/latbench.cu (profiles/r01_pipe_microbench.txt)"}},
                 "note": "bucket accumulation is bound by the integer multiplier (IMAD.WIDE), not by HBM: traffic is ~10% of HBM peak; see DESIGN.md 4.1/4.2"}
-    h2d = (len(MSM_SCHEDULE) * n_loc * 32 + (N_INTT * n * 32 + N_COSET * n * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n_cells * 32)
+    # the coefficients of a polynomial go up once for both of its transforms (fused batch call) when one rank owns both
+    coset_up = 0 if world == 1 else N_COSET * n * 32
+    h2d = (len(MSM_SCHEDULE) * n_loc * 32 + (N_INTT * n * 32 + coset_up + N_COSET_INV * (1 << ext_k) * 32) // world + n_cells * 32)
     d2h = (len(MSM_SCHEDULE) * 96 + (N_INTT * n * 32 + N_COSET * (1 << ext_k) * 32 + N_COSET_INV * (1 << ext_k) * 32) // world + n * 32)
     cpu = cpu_sample(k) if world == 1 and not args.no_cpu else None
     line = {
@@ -525,7 +550,7 @@ def run_b200(args):
         "op_ms": op_ms,
         "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "G1 pairs/s", "ms_per_step": ms_e2e, "ms_per_step_sequential_calls": ms_e2e_seq,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "path": "h2b_assign_columns / h2b_msm_g1_batch / h2b_lagrange_to_coeff_batch / h2b_coeff_to_extended_batch / h2b_extended_to_coeff with pinned host buffers; transforms driven by a second host thread + context beside the commitment phases (dependency model of step_resident)"},
+                "path": "h2b_assign_columns / h2b_msm_g1_batch / h2b_lagrange_to_coeff_and_extended_batch / h2b_extended_to_coeff with pinned host buffers; transforms driven by a second host thread + context beside the commitment phases (dependency model of step_resident)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

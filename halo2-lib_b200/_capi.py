@@ -76,6 +76,7 @@ SIGNATURES = {
     "h2b_coeff_to_lagrange_dev": (_int, [_vp, _vp, _u32]),
     "h2b_lagrange_to_coeff_batch": (_int, [_vp, C.POINTER(_vp), _sz, _u32]),
     "h2b_coeff_to_lagrange_batch": (_int, [_vp, C.POINTER(_vp), _sz, _u32]),
+    "h2b_lagrange_to_coeff_and_extended_batch": (_int, [_vp, C.POINTER(_vp), _sz, _u32, _u32, C.POINTER(_vp)]),
     "h2b_coeff_to_extended_batch": (_int, [_vp, C.POINTER(_vp), _sz, _sz, _u32, C.POINTER(_vp)]),
     "h2b_coeff_to_extended": (_int, [_vp, _vp, _sz, _u32, _vp]),
     "h2b_coeff_to_extended_dev": (_int, [_vp, _vp, _sz, _u32, _vp]),

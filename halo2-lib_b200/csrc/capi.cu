@@ -540,6 +540,50 @@ static void ntt_batch_host(h2b_ctx* ctx, int mode, const uint64_t* const* in, ui
     H2B_CUDA(cudaStreamSynchronize(down));
     H2B_CUDA(cudaStreamSynchronize(ks));
 }
+// lagrange_to_coeff followed by coeff_to_extended for m columns, fused: the coefficients go up once, stay on the device
+// for the coset transform, and both results come down on the second copy stream while the next column computes.
+static void ntt_fused_batch_host(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k, uint32_t ext_k, uint64_t* const* ext_out) {
+    H2B_REQUIRE(a && ext_out, "ntt batch: null pointer");
+    H2B_REQUIRE(k <= ext_k && ext_k <= 28, "ntt batch: sizes out of range");
+    if (m == 0) return;
+    const size_t n = (size_t)1 << k, ne = (size_t)1 << ext_k;
+    const int small_slots[3] = {WS_NTT_E, WS_NTT_F, WS_NTT_G}, big_slots[3] = {WS_NTT_A, WS_NTT_C, WS_NTT_D};
+    void *sm[3], *big[3];
+    for (int b = 0; b < 3; b++) {
+        sm[b] = ctx->get(small_slots[b], n * 32);
+        big[b] = ctx->get(big_slots[b], ne * 32);
+    }
+    (void)ctx->get(WS_NTT_B, ne * 32);  // scratch of ntt_run: allocate before anything is in flight
+    uint64_t w_inv[4], w_ext[4];
+    domain_omega(k, w_inv, true);
+    domain_omega(ext_k, w_ext, false);
+    cudaStream_t up = ctx->copy_stream, ks = ctx->stream, down = ctx->copy_stream2;
+    H2B_CUDA(cudaEventRecord(ctx->fork_ev, ks));
+    H2B_CUDA(cudaStreamWaitEvent(up, ctx->fork_ev, 0));
+    for (size_t i = 0; i < m; i++) {
+        const int b = (int)(i % 3);
+        H2B_REQUIRE(a[i] && ext_out[i], "ntt batch: null column");
+        if (i >= 3) H2B_CUDA(cudaStreamWaitEvent(up, ctx->pipe_ev[b][2], 0));  // buffers b downloaded
+        H2B_CUDA(cudaMemcpyAsync(sm[b], a[i], n * 32, cudaMemcpyHostToDevice, up));
+        H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][0], up));
+        H2B_CUDA(cudaStreamWaitEvent(ks, ctx->pipe_ev[b][0], 0));
+        ntt_run(ctx, sm[b], n, sm[b], k, w_inv, 1, 0);
+        H2B_CUDA(cudaEventRecord(ctx->ev[b], ks));  // coefficients ready
+        ntt_run(ctx, sm[b], n, big[b], ext_k, w_ext, 0, 1);
+        H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][1], ks));
+        H2B_CUDA(cudaStreamWaitEvent(down, ctx->ev[b], 0));
+        H2B_CUDA(cudaMemcpyAsync(a[i], sm[b], n * 32, cudaMemcpyDeviceToHost, down));
+        H2B_CUDA(cudaStreamWaitEvent(down, ctx->pipe_ev[b][1], 0));
+        H2B_CUDA(cudaMemcpyAsync(ext_out[i], big[b], ne * 32, cudaMemcpyDeviceToHost, down));
+        H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][2], down));
+    }
+    H2B_CUDA(cudaStreamSynchronize(down));
+    H2B_CUDA(cudaStreamSynchronize(ks));
+}
+int h2b_lagrange_to_coeff_and_extended_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k, uint32_t ext_k,
+                                             uint64_t* const* ext_out) {
+    return guarded(ctx, [&] { ntt_fused_batch_host(ctx, a, m, k, ext_k, ext_out); });
+}
 int h2b_lagrange_to_coeff_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k) {
     return guarded(ctx, [&] { ntt_batch_host(ctx, 1, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k); });
 }

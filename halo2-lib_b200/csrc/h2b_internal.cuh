@@ -53,6 +53,9 @@ enum WsSlot {
     WS_NTT_B,
     WS_NTT_C,
     WS_NTT_D,
+    WS_NTT_E,         // small (2^k) buffers of the fused lagrange -> coeff -> extended batch
+    WS_NTT_F,
+    WS_NTT_G,
     WS_ASSIGN_IN,
     WS_ASSIGN_OUT,
     WS_MISC,

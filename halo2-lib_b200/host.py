@@ -270,6 +270,15 @@ class EvaluationDomain:
         self.ctx.check(lib.h2b_lagrange_to_coeff_batch(self.ctx.h, ptrs, len(arrs), self.k))
         return arrs
 
+    def lagrange_to_coeff_and_extended_many(self, cols) -> tuple:
+        """(coefficients, coset evaluations) of every column: one fused, PCIe-pipelined call"""
+        arrs = [_u64(a, 4).copy() for a in cols]
+        outs = [np.empty((1 << self.extended_k, 4), dtype=np.uint64) for _ in arrs]
+        pin = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        pout = (C.c_void_p * len(arrs))(*[o.ctypes.data for o in outs])
+        self.ctx.check(lib.h2b_lagrange_to_coeff_and_extended_batch(self.ctx.h, pin, len(arrs), self.k, self.extended_k, pout))
+        return arrs, outs
+
     def coeff_to_extended_many(self, cols) -> list:
         arrs = [_u64(a, 4) for a in cols]
         outs = [np.empty((1 << self.extended_k, 4), dtype=np.uint64) for _ in arrs]

@@ -171,6 +171,11 @@ int h2b_extended_to_coeff_dev(h2b_ctx* ctx, void* d_a, uint32_t ext_k);
  * a[i] / coeffs[i] / out[i] are host pointers (pinned memory makes the copies truly asynchronous). */
 int h2b_lagrange_to_coeff_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k);
 int h2b_coeff_to_lagrange_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k);
+/* `domain.lagrange_to_coeff(p)` followed by `domain.coeff_to_extended(p)` for the same m columns (what create_proof does
+ * with every advice / permuted / product column): a[j] holds the 2^k Lagrange values on entry and the coefficients on
+ * return, ext_out[j] receives the 2^ext_k coset evaluations.  The coefficients cross PCIe once in each direction. */
+int h2b_lagrange_to_coeff_and_extended_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k, uint32_t ext_k,
+                                             uint64_t* const* ext_out);
 int h2b_coeff_to_extended_batch(h2b_ctx* ctx, const uint64_t* const* coeffs, size_t m, size_t n_coeffs, uint32_t ext_k,
                                 uint64_t* const* out);
 

@@ -243,6 +243,11 @@ def test_ntt_batch_pipelined(ctx, h2b):
     for c, co, ex in zip(cols, coeffs, exts):
         assert np.array_equal(co, orc.lagrange_to_coeff(c, k))
         assert np.array_equal(ex, orc.coeff_to_extended(co, dom.extended_k))
+    # the fused call (coefficients stay on the device between the two transforms) gives the same pair of results
+    for m in (1, 2, 7):
+        co2, ex2 = dom.lagrange_to_coeff_and_extended_many(cols[:m])
+        for j in range(m):
+            assert np.array_equal(co2[j], coeffs[j]) and np.array_equal(ex2[j], exts[j])
 
 
 # ------------------------------------------------------------------ L3: KZG identity ties MSM, NTT and SRS layout together
