@@ -15,9 +15,18 @@
 //   halo2_base::virtual_region::lookups::LookupAnyManager::assign_raw               h2b::assign_lookups
 //       (halo2-base/src/virtual_region/lookups.rs:130-155)
 //
+//   ff::BatchInvert::batch_invert, the grand-product column of the permutation / lookup provers   h2b::batch_invert, grand_product
+//   halo2_proofs::plonk::lookup::prover::permute_expression_pair                      h2b::permute_expression_pair
+//   halo2_proofs::plonk::evaluation::{GraphEvaluator, Evaluator::evaluate_h}          h2b::GraphEvaluator, quotient_graph,
+//                                                                                     permutation_fold, lookup_fold
+//   halo2_proofs::poly::EvaluationDomain::divide_by_vanishing_poly                    h2b::divide_by_vanishing_poly
+//   halo2_proofs::arithmetic::{eval_polynomial, kate_division}                        h2b::eval_polynomial, kate_division
+//   halo2_proofs::poly::kzg::commitment::g_to_lagrange                                h2b::g_to_lagrange
+//
 // Where the Rust code panics (`expect("prover should not fail")`, halo2-base/src/utils/testing.rs:48; index out of
 // bounds in assign_witnesses) these wrappers throw h2b::Error; nothing is computed on the CPU.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <stdexcept>
@@ -211,6 +220,184 @@ inline std::vector<Fr> kate_division(const Context& ctx, const std::vector<Fr>& 
     ctx.check(h2b_kate_division(ctx.raw(), reinterpret_cast<const uint64_t*>(a.data()), a.size(), reinterpret_cast<const uint64_t*>(&b),
                                 reinterpret_cast<uint64_t*>(q.data())));
     return q;
+}
+
+// ff::BatchInvert::batch_invert on a slice (zeros stay zero)
+inline void batch_invert(const Context& ctx, std::vector<Fr>& a) {
+    ctx.check(h2b_batch_invert_fr(ctx.raw(), reinterpret_cast<uint64_t*>(a.data()), a.size()));
+}
+// z[0] = start, z[i] = z[i-1] * f[i-1]
+inline std::vector<Fr> grand_product(const Context& ctx, const std::vector<Fr>& f, const Fr& start) {
+    std::vector<Fr> z(f.size());
+    ctx.check(h2b_grand_product_fr(ctx.raw(), reinterpret_cast<const uint64_t*>(f.data()), start.data(), f.size(),
+                                   reinterpret_cast<uint64_t*>(z.data())));
+    return z;
+}
+// permute_expression_pair: (A', S') over the usable rows, the last blinding_factors + 1 rows left zero for the caller's
+// blinding scalars.  Throws Error(H2B_ERR_UNSATISFIED) for `Error::ConstraintSystemFailure`.
+inline std::pair<std::vector<Fr>, std::vector<Fr>> permute_expression_pair(const Context& ctx, const std::vector<Fr>& input,
+                                                                           const std::vector<Fr>& table, uint32_t k,
+                                                                           uint32_t blinding_factors) {
+    if (input.size() != (size_t(1) << k) || table.size() != input.size()) throw Error(H2B_ERR_ARG, "permute_expression_pair: need 2^k rows");
+    std::vector<Fr> a(input.size(), Fr{0, 0, 0, 0}), s(input.size(), Fr{0, 0, 0, 0});
+    ctx.check(h2b_permute_expression_pair(ctx.raw(), reinterpret_cast<const uint64_t*>(input.data()),
+                                          reinterpret_cast<const uint64_t*>(table.data()), k, blinding_factors,
+                                          reinterpret_cast<uint64_t*>(a.data()), reinterpret_cast<uint64_t*>(s.data())));
+    return {a, s};
+}
+
+// ---- plonk::evaluation::GraphEvaluator: value sources, calculations, and the program h2b_graph carries
+struct ValueSource {
+    uint32_t kind, index, rotation_slot;
+    static ValueSource Constant(uint32_t i) { return {H2B_SRC_CONSTANT, i, 0}; }
+    static ValueSource Intermediate(uint32_t i) { return {H2B_SRC_INTERMEDIATE, i, 0}; }
+    static ValueSource Fixed(uint32_t col, uint32_t rot) { return {H2B_SRC_FIXED, col, rot}; }
+    static ValueSource Advice(uint32_t col, uint32_t rot) { return {H2B_SRC_ADVICE, col, rot}; }
+    static ValueSource Instance(uint32_t col, uint32_t rot) { return {H2B_SRC_INSTANCE, col, rot}; }
+    static ValueSource Challenge(uint32_t i) { return {H2B_SRC_CHALLENGE, i, 0}; }
+    static ValueSource Beta() { return {H2B_SRC_BETA, 0, 0}; }
+    static ValueSource Gamma() { return {H2B_SRC_GAMMA, 0, 0}; }
+    static ValueSource Theta() { return {H2B_SRC_THETA, 0, 0}; }
+    static ValueSource Y() { return {H2B_SRC_Y, 0, 0}; }
+    static ValueSource PreviousValue() { return {H2B_SRC_PREVIOUS, 0, 0}; }
+    uint32_t word() const { return H2B_SRC(kind, index, rotation_slot); }
+    bool operator==(const ValueSource& o) const { return kind == o.kind && index == o.index && rotation_slot == o.rotation_slot; }
+};
+struct Calculation {
+    uint32_t op;                     // H2B_CALC_*
+    std::vector<ValueSource> args;   // Horner: start, factor, parts...
+    static Calculation Add(ValueSource a, ValueSource b) { return {H2B_CALC_ADD, {a, b}}; }
+    static Calculation Sub(ValueSource a, ValueSource b) { return {H2B_CALC_SUB, {a, b}}; }
+    static Calculation Mul(ValueSource a, ValueSource b) { return {H2B_CALC_MUL, {a, b}}; }
+    static Calculation Square(ValueSource a) { return {H2B_CALC_SQUARE, {a}}; }
+    static Calculation Double(ValueSource a) { return {H2B_CALC_DOUBLE, {a}}; }
+    static Calculation Negate(ValueSource a) { return {H2B_CALC_NEGATE, {a}}; }
+    static Calculation Store(ValueSource a) { return {H2B_CALC_STORE, {a}}; }
+    static Calculation Horner(ValueSource start, std::vector<ValueSource> parts, ValueSource factor) {
+        std::vector<ValueSource> v{start, factor};
+        v.insert(v.end(), parts.begin(), parts.end());
+        return {H2B_CALC_HORNER, v};
+    }
+    bool operator==(const Calculation& o) const { return op == o.op && args == o.args; }
+};
+class GraphEvaluator {
+public:
+    uint32_t add_rotation(int32_t rotation) {
+        auto it = std::find(rotations.begin(), rotations.end(), rotation);
+        if (it != rotations.end()) return uint32_t(it - rotations.begin());
+        rotations.push_back(rotation);
+        return uint32_t(rotations.size() - 1);
+    }
+    ValueSource add_constant(const Fr& c) {
+        auto it = std::find(constants.begin(), constants.end(), c);
+        if (it != constants.end()) return ValueSource::Constant(uint32_t(it - constants.begin()));
+        constants.push_back(c);
+        return ValueSource::Constant(uint32_t(constants.size() - 1));
+    }
+    ValueSource add_calculation(const Calculation& c) {  // identical calculations are shared, as upstream does
+        auto it = std::find(calculations.begin(), calculations.end(), c);
+        if (it != calculations.end()) return ValueSource::Intermediate(uint32_t(it - calculations.begin()));
+        calculations.push_back(c);
+        return ValueSource::Intermediate(uint32_t(calculations.size() - 1));
+    }
+    std::vector<uint32_t> program() const {
+        std::vector<uint32_t> w;
+        for (auto& c : calculations) {
+            w.push_back(c.op);
+            if (c.op == H2B_CALC_HORNER) {
+                w.push_back(c.args[0].word());
+                w.push_back(c.args[1].word());
+                w.push_back(uint32_t(c.args.size() - 2));
+                for (size_t j = 2; j < c.args.size(); j++) w.push_back(c.args[j].word());
+            } else {
+                for (auto& a : c.args) w.push_back(a.word());
+            }
+        }
+        return w;
+    }
+    std::vector<Fr> constants;
+    std::vector<int32_t> rotations;
+    std::vector<Calculation> calculations;
+};
+struct Challenges {
+    Fr beta{}, gamma{}, theta{}, y{};
+    std::vector<Fr> user;  // ValueSource::Challenge(i)
+};
+namespace detail {
+// owns the arrays an h2b_graph points to for the duration of one call (host columns)
+struct GraphHolder {
+    std::vector<uint32_t> prog;
+    std::vector<const void*> fixed, advice, instance;
+    h2b_graph g{};
+    GraphHolder(const GraphEvaluator& ev, ValueSource result, const std::vector<const std::vector<Fr>*>& f,
+                const std::vector<const std::vector<Fr>*>& a, const std::vector<const std::vector<Fr>*>& i, const Challenges& ch)
+        : prog(ev.program()) {
+        for (auto c : f) fixed.push_back(c->data());
+        for (auto c : a) advice.push_back(c->data());
+        for (auto c : i) instance.push_back(c->data());
+        g.program = prog.data();
+        g.program_words = prog.size();
+        g.n_calculations = uint32_t(ev.calculations.size());
+        g.result = result.word();
+        g.constants = reinterpret_cast<const uint64_t*>(ev.constants.data());
+        g.n_constants = ev.constants.size();
+        g.rotations = ev.rotations.data();
+        g.n_rotations = ev.rotations.size();
+        g.fixed = fixed.data();
+        g.n_fixed = fixed.size();
+        g.advice = advice.data();
+        g.n_advice = advice.size();
+        g.instance = instance.data();
+        g.n_instance = instance.size();
+        g.challenges = reinterpret_cast<const uint64_t*>(ch.user.data());
+        g.n_challenges = ch.user.size();
+        std::copy(ch.beta.begin(), ch.beta.end(), g.beta);
+        std::copy(ch.gamma.begin(), ch.gamma.end(), g.gamma);
+        std::copy(ch.theta.begin(), ch.theta.end(), g.theta);
+        std::copy(ch.y.begin(), ch.y.end(), g.y);
+    }
+};
+inline std::vector<const uint64_t*> ptrs(const std::vector<const std::vector<Fr>*>& cols) {
+    std::vector<const uint64_t*> p;
+    for (auto c : cols) p.push_back(reinterpret_cast<const uint64_t*>(c->data()));
+    return p;
+}
+}  // namespace detail
+using Columns = std::vector<const std::vector<Fr>*>;  // extended-domain columns (2^ext_k values each)
+
+// custom gates of evaluate_h: values[i] = graph(previous = values[i]) on every extended-domain row
+inline void quotient_graph(const Context& ctx, const GraphEvaluator& ev, ValueSource result, const Columns& fixed, const Columns& advice,
+                           const Columns& instance, const Challenges& ch, uint32_t k, uint32_t ext_k, std::vector<Fr>& values) {
+    detail::GraphHolder h(ev, result, fixed, advice, instance, ch);
+    ctx.check(h2b_quotient_graph(ctx.raw(), &h.g, k, ext_k, reinterpret_cast<uint64_t*>(values.data())));
+}
+inline void permutation_fold(const Context& ctx, const Columns& z_sets, const Columns& columns, const Columns& sigma, size_t chunk_len,
+                             const std::vector<Fr>& l0, const std::vector<Fr>& l_last, const std::vector<Fr>& l_active,
+                             const Challenges& ch, uint32_t blinding_factors, uint32_t k, uint32_t ext_k, std::vector<Fr>& values) {
+    auto z = detail::ptrs(z_sets), c = detail::ptrs(columns), s = detail::ptrs(sigma);
+    ctx.check(h2b_permutation_fold(ctx.raw(), z.data(), z.size(), c.data(), s.data(), c.size(), chunk_len,
+                                   reinterpret_cast<const uint64_t*>(l0.data()), reinterpret_cast<const uint64_t*>(l_last.data()),
+                                   reinterpret_cast<const uint64_t*>(l_active.data()), ch.beta.data(), ch.gamma.data(), ch.y.data(),
+                                   blinding_factors, k, ext_k, reinterpret_cast<uint64_t*>(values.data())));
+}
+inline void lookup_fold(const Context& ctx, const GraphEvaluator& ev, ValueSource result, const Columns& fixed, const Columns& advice,
+                        const Columns& instance, const Challenges& ch, const std::vector<Fr>& z, const std::vector<Fr>& permuted_input,
+                        const std::vector<Fr>& permuted_table, const std::vector<Fr>& l0, const std::vector<Fr>& l_last,
+                        const std::vector<Fr>& l_active, uint32_t k, uint32_t ext_k, std::vector<Fr>& values) {
+    detail::GraphHolder h(ev, result, fixed, advice, instance, ch);
+    auto p = [](const std::vector<Fr>& v) { return reinterpret_cast<const uint64_t*>(v.data()); };
+    ctx.check(h2b_lookup_fold(ctx.raw(), &h.g, p(z), p(permuted_input), p(permuted_table), p(l0), p(l_last), p(l_active), k, ext_k,
+                              reinterpret_cast<uint64_t*>(values.data())));
+}
+inline void divide_by_vanishing_poly(const Context& ctx, std::vector<Fr>& values, uint32_t k, uint32_t ext_k) {
+    ctx.check(h2b_divide_by_vanishing_poly(ctx.raw(), reinterpret_cast<uint64_t*>(values.data()), k, ext_k));
+}
+// poly::kzg::commitment::g_to_lagrange
+inline std::vector<G1Affine> g_to_lagrange(const Context& ctx, const std::vector<G1Affine>& g, uint32_t k) {
+    if (g.size() != (size_t(1) << k)) throw Error(H2B_ERR_ARG, "g_to_lagrange: need 2^k points");
+    std::vector<G1Affine> out(g.size());
+    ctx.check(h2b_g_to_lagrange(ctx.raw(), reinterpret_cast<const uint64_t*>(g.data()), k, reinterpret_cast<uint64_t*>(out.data())));
+    return out;
 }
 
 }  // namespace h2b

@@ -86,6 +86,63 @@ int main() {
     CHECK(eval_polynomial(ctx, a, zero) == a[0]);
     CHECK(eval_polynomial(ctx, qd, zero) == a[1]);
 
+    // ---- the next rows through the mirror: batch inversion, the lookup permutation, a GraphEvaluator program
+    std::vector<Fr> inv = a;
+    inv[5] = zero;
+    batch_invert(ctx, inv);
+    std::vector<Fr> prod(n);
+    ctx.check(h2b_test_field_op(ctx.raw(), 1, 0, reinterpret_cast<const uint64_t*>(a.data()), reinterpret_cast<const uint64_t*>(inv.data()), n,
+                                reinterpret_cast<uint64_t*>(prod.data())));
+    const Fr one = small_mont(ctx, 1);
+    CHECK(prod[0] == one && prod[n - 1] == one && inv[5] == zero);
+    auto zcol = grand_product(ctx, a, one);
+    CHECK(zcol[0] == one && zcol[1] == a[0]);
+    {   // table [4,9,9,2,7], inputs [9,2,9,9,4] over 5 usable rows of 2^3 (blinding_factors = 2): tests/golden/next_rows.json
+        auto col = [&](std::initializer_list<uint64_t> v) {
+            std::vector<Fr> c;
+            for (auto x : v) c.push_back(small_mont(ctx, x));
+            c.resize(8, zero);
+            return c;
+        };
+        auto pr = permute_expression_pair(ctx, col({9, 2, 9, 9, 4}), col({4, 9, 9, 2, 7}), 3, 2);
+        CHECK(pr.first == col({2, 4, 9, 9, 9}) && pr.second == col({2, 4, 9, 9, 7}));
+        threw = false;
+        try { permute_expression_pair(ctx, col({9, 2, 9, 9, 5}), col({4, 9, 9, 2, 7}), 3, 2); } catch (const Error& e) { threw = e.code == H2B_ERR_UNSATISFIED; }
+        CHECK(threw);
+    }
+    {   // halo2-base's gate q * (a + b*c - out) as a GraphEvaluator program == the dedicated kernel
+        const uint32_t gk = 6, gek = 8;
+        const size_t ge = size_t(1) << gek;
+        std::vector<Fr> q(s.begin(), s.begin() + ge), adv(a.begin(), a.begin() + ge), acc1(b.begin(), b.begin() + ge), acc2 = acc1;
+        GraphEvaluator ev;
+        ValueSource qs = ev.add_calculation(Calculation::Store(ValueSource::Fixed(0, ev.add_rotation(0))));
+        ValueSource a0 = ev.add_calculation(Calculation::Store(ValueSource::Advice(0, ev.add_rotation(0))));
+        ValueSource a1 = ev.add_calculation(Calculation::Store(ValueSource::Advice(0, ev.add_rotation(1))));
+        ValueSource a2 = ev.add_calculation(Calculation::Store(ValueSource::Advice(0, ev.add_rotation(2))));
+        ValueSource a3 = ev.add_calculation(Calculation::Store(ValueSource::Advice(0, ev.add_rotation(3))));
+        ValueSource bc = ev.add_calculation(Calculation::Mul(a1, a2));
+        ValueSource sum = ev.add_calculation(Calculation::Add(a0, bc));
+        ValueSource dif = ev.add_calculation(Calculation::Sub(sum, a3));
+        ValueSource gate = ev.add_calculation(Calculation::Mul(qs, dif));
+        ValueSource res = ev.add_calculation(Calculation::Horner(ValueSource::PreviousValue(), {gate}, ValueSource::Y()));
+        Challenges ch;
+        ch.y = s[7];
+        quotient_graph(ctx, ev, res, {&q}, {&adv}, {}, ch, gk, gek, acc1);
+        ctx.check(h2b_flex_gate_fold(ctx.raw(), reinterpret_cast<const uint64_t*>(q.data()), reinterpret_cast<const uint64_t*>(adv.data()),
+                                     ch.y.data(), gk, gek, reinterpret_cast<uint64_t*>(acc2.data())));
+        CHECK(acc1 == acc2);
+        CHECK(ev.add_calculation(Calculation::Mul(a1, a2)) == bc);  // identical calculations are shared
+        divide_by_vanishing_poly(ctx, acc1, gk, gek);
+        CHECK(!(acc1 == acc2));
+    }
+    {   // g_to_lagrange of [G, G, G, G] at k = 2: only the constant Lagrange combination survives: out[0] = G, rest = identity
+        G1Affine G;
+        memcpy(&G, gxy, sizeof(G));
+        auto gl4 = g_to_lagrange(ctx, std::vector<G1Affine>(4, G), 2);
+        G1Affine idp{};
+        CHECK(memcmp(&gl4[0], &G, sizeof(G)) == 0 && memcmp(&gl4[1], &idp, sizeof(G)) == 0 && memcmp(&gl4[3], &idp, sizeof(G)) == 0);
+    }
+
     printf(fails ? "host mirror: %d FAILED\n" : "host mirror: all checks passed\n", fails);
     return fails ? 1 : 0;
 }
