@@ -93,3 +93,27 @@ timeit(f"grand_product 2^{k}", lambda: ctx.check(lib.h2b_grand_product_fr_dev(ct
        32 * n * 2, cpu=lambda: orc.grand_product(host[0][:n], ch[0]))
 inv = d[1][:n].clone()
 timeit(f"batch_invert 2^{k}", lambda: ctx.check(lib.h2b_batch_invert_fr_dev(ctx.h, vp(inv.data_ptr()), n)), 32 * n * 2, cpu=lambda: orc.batch_invert(host[1][:n]))
+
+# lookup permutation: a range-check column (values < 2^16 drawn from a 2^16-entry table padded with zeros), 2^k rows
+bfq = 5
+u = n - (bfq + 1)
+tab = np.zeros(n, dtype=np.uint64); tab[:1 << 16] = np.arange(1 << 16, dtype=np.uint64)
+inp = rng.integers(0, 1 << 16, size=n).astype(np.uint64)
+def to_m(v):
+    x = np.zeros((n, 4), dtype=np.uint64); x[:, 0] = v
+    return ctx.field_op(1, 5, x)
+Tm, Am = to_m(tab), to_m(inp)
+dT, dA = torch.from_numpy(Tm.view(np.int64)).to(dev), torch.from_numpy(Am.view(np.int64)).to(dev)
+dPA, dPT = torch.zeros_like(dA), torch.zeros_like(dT)
+timeit(f"permute_expression_pair 2^{k} rows (16-bit range table)",
+       lambda: ctx.check(lib.h2b_permute_expression_pair_dev(ctx.h, vp(dA.data_ptr()), vp(dT.data_ptr()), k, bfq, vp(dPA.data_ptr()), vp(dPT.data_ptr()))),
+       32 * u * 4, cpu=lambda: orc.permute_expression_pair(Am, Tm, k, bfq), reps=3)
+# keygen side: G1 FFT of 2^16 points (once per SRS; 2^19 is 8 x the points and 19/16 x the stages)
+if not QUICK:
+    kk = 16
+    gb = np.array([0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f,
+                   0xa6ba871b8b1e1b3a, 0x14f1d651eb8e167b, 0xccdd46def0f28c58, 0x1c14ef83340fbe5e], dtype=np.uint64)
+    dg = torch.empty((1 << kk, 8), dtype=torch.int64, device=dev); dgl = torch.empty_like(dg)
+    ctx.check(lib.h2b_srs_setup_dev(ctx.h, vp(ch[0].ctypes.data), vp(gb.ctypes.data), kk, vp(dg.data_ptr()), None))
+    timeit(f"g_to_lagrange 2^{kk} points (G1 FFT)", lambda: ctx.check(lib.h2b_g_to_lagrange_dev(ctx.h, vp(dg.data_ptr()), kk, vp(dgl.data_ptr()))),
+           64 * (1 << kk) * 2, reps=2)
