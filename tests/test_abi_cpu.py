@@ -67,3 +67,21 @@ def test_bench_schedule_shape():
     a = bench.witness_like(np.random.default_rng(0), 4096)
     frac0 = float((a == 0).all(axis=1).mean())
     assert 0.30 < frac0 < 0.40
+
+
+def test_graph_struct_layout_matches_the_header(tmp_path):
+    """the ctypes twin of h2b_graph (and with it the oracle's orc_graph, which tests fill through the same structure) has
+    the size and field offsets the C compiler gives the header's struct"""
+    import ctypes as C
+    import subprocess
+    from halo2_lib_b200._capi import Graph, HEADER_PATH
+    fields = [f[0] for f in Graph._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(void) {\n  printf("%%zu", sizeof(h2b_graph));\n%s  return 0;\n}\n'
+                   % (HEADER_PATH, "".join('  printf(" %%zu", offsetof(h2b_graph, %s));\n' % f for f in fields)))
+    exe = tmp_path / "layout"
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c11", str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got[0] == C.sizeof(Graph)
+    assert got[1:] == [getattr(Graph, f).offset for f in fields]
