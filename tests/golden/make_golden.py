@@ -79,6 +79,17 @@ perm = p.permutation_terms(zs, cs, ss, 2, l0, l_last, l_active, beta, gamma, y, 
 tv, zc, ap, sp = col(), col(), col(), col()
 lookup = p.lookup_terms(tv, zc, ap, sp, l0, l_last, l_active, beta, gamma, y, k, ext_k, start)
 H = lambda xs: [hexs(v) for v in xs]
+# keygen side at k = 2: g[i] = tau^i G, g_lagrange[i] = L_i(tau) G (closed form), and the vanishing-polynomial division
+tau = rnd.randrange(p.R)
+k2, n2 = 2, 4
+w2 = p.omega_for(k2)
+c2 = (pow(tau, n2, p.R) - 1) * pow(n2, -1, p.R) % p.R
+lag = [c2 * pow(w2, i, p.R) * pow((tau - pow(w2, i, p.R)) % p.R, -1, p.R) % p.R for i in range(n2)]
+srs = {"k": k2, "tau": hexs(tau), "g": [pt(p.g1_mul(pow(tau, i, p.R), p.G1)) for i in range(n2)],
+       "g_lagrange": [pt(p.g1_mul(l, p.G1)) for l in lag]}
+we = p.omega_for(ext_k)
+vanish_in = col()
+vanish_out = [v * pow((pow(p.ZETA * pow(we, i, p.R) % p.R, n, p.R) - 1) % p.R, -1, p.R) % p.R for i, v in enumerate(vanish_in)]
 json.dump({
     "note": "BN254 Fr, canonical integers; formulas of oracle/pyref.py (halo2 evaluate_h / arithmetic restated)",
     "k": k, "extended_k": ext_k, "blinding_factors": bf,
@@ -87,6 +98,7 @@ json.dump({
     "z_sets": [H(c) for c in zs], "columns": [H(c) for c in cs], "sigma": [H(c) for c in ss], "chunk_len": 2,
     "l0": H(l0), "l_last": H(l_last), "l_active": H(l_active), "start": H(start), "beta": hexs(beta), "gamma": hexs(gamma), "y": hexs(y),
     "permutation_fold": H(perm),
+    "srs": srs, "vanishing_in": H(vanish_in), "vanishing_out": H(vanish_out),
     "table_values": H(tv), "lookup_z": H(zc), "lookup_a": H(ap), "lookup_s": H(sp), "lookup_fold": H(lookup),
 }, open(os.path.join(HERE, "next_rows.json"), "w"), indent=1)
 print("wrote msm_g1.json ntt_fr.json assign.json next_rows.json")

@@ -52,7 +52,7 @@ def test_oracle_matches_golden():
     assert rc == 0 and [limbs_to_ints(c) for c in lk] == [ints(c) for c in d["lookup_columns"]]
 
 
-def _next_rows(lib_eval, lib_kate, lib_permute, lib_perm_fold, lib_lookup_fold):
+def _next_rows(lib_eval, lib_kate, lib_permute, lib_perm_fold, lib_lookup_fold, lib_vanish=None, lib_setup=None, lib_to_lagrange=None):
     """shared by the CPU (oracle) and GPU (CUDA) checks of tests/golden/next_rows.json"""
     d = json.load(open(os.path.join(G, "next_rows.json")))
     k, ek, bf = d["k"], d["extended_k"], d["blinding_factors"]
@@ -75,6 +75,14 @@ def _next_rows(lib_eval, lib_kate, lib_permute, lib_perm_fold, lib_lookup_fold):
     got = lib_lookup_fold(bound, m(d["lookup_z"]), m(d["lookup_a"]), m(d["lookup_s"]), m(d["l0"]), m(d["l_last"]), m(d["l_active"]), k, ek,
                           m(d["start"]))
     assert unmont(got, R) == ints(d["lookup_fold"])
+    if lib_vanish:
+        assert unmont(lib_vanish(m(d["vanishing_in"]), k, ek), R) == ints(d["vanishing_out"])
+    if lib_setup:
+        srs = d["srs"]
+        want_g, want_gl = affine_to_limbs([point(a) for a in srs["g"]]), affine_to_limbs([point(a) for a in srs["g_lagrange"]])
+        g, gl = lib_setup(m1(srs["tau"]), affine_to_limbs([pyref.G1])[0], srs["k"])
+        assert np.array_equal(g, want_g) and np.array_equal(gl, want_gl)
+        assert np.array_equal(lib_to_lagrange(want_g, srs["k"]), want_gl)
 
 
 def test_oracle_matches_golden_next_rows():
@@ -83,16 +91,30 @@ def test_oracle_matches_golden_next_rows():
         assert rc == 0
         return pa, pt
     _next_rows(orc.eval_polynomial, orc.kate_division, permute, orc.permutation_fold,
-               lambda b, *a: orc.lookup_fold(b.struct, *a))
+               lambda b, *a: orc.lookup_fold(b.struct, *a), orc.divide_by_vanishing_poly, orc.srs_setup, orc.g_to_lagrange)
 
 
 @pytest.mark.gpu
 def test_cuda_matches_golden_next_rows():
     import halo2_lib_b200 as h
     ctx = h.Context(0)
+    import ctypes as C
+    from halo2_lib_b200._capi import lib
+
+    def setup(tau, base, k):
+        g, gl = np.empty((1 << k, 8), dtype=np.uint64), np.empty((1 << k, 8), dtype=np.uint64)
+        ctx.check(lib.h2b_srs_setup(ctx.h, C.c_void_p(tau.ctypes.data), C.c_void_p(base.ctypes.data), k, C.c_void_p(g.ctypes.data), C.c_void_p(gl.ctypes.data)))
+        return g, gl
+
+    def to_lagrange(g, k):
+        g = np.ascontiguousarray(g)
+        out = np.empty_like(g)
+        ctx.check(lib.h2b_g_to_lagrange(ctx.h, C.c_void_p(g.ctypes.data), k, C.c_void_p(out.ctypes.data)))
+        return out
     _next_rows(lambda a, x: h.eval_polynomial(ctx, a, x), lambda a, x: h.kate_division(ctx, a, x),
                lambda a, t, k, bf: h.permute_expression_pair(ctx, a, t, k, bf),
-               lambda *a: h.permutation_fold(ctx, *a), lambda *a: h.lookup_fold(ctx, *a))
+               lambda *a: h.permutation_fold(ctx, *a), lambda *a: h.lookup_fold(ctx, *a),
+               lambda v, k, ek: h.divide_by_vanishing_poly(ctx, v, k, ek), setup, to_lagrange)
     ctx.close()
 
 
