@@ -217,3 +217,38 @@ def test_divide_by_vanishing_poly_vs_python():
     ext = orc.coeff_to_extended(mont(prod, R), ext_k)
     back = unmont(orc.extended_to_coeff(orc.divide_by_vanishing_poly(ext, k, ext_k), ext_k), R)
     assert back[:n] == gcoef and not any(back[n:])
+
+
+def test_graph_evaluator_builder_rules():
+    """the add_expression simplifications the upstream GraphEvaluator applies: shared calculations and constants,
+    x + 0, x * 1, x * 2 -> Double, x * x -> Square, a + (-b) -> Sub, scaling by 0 / 1"""
+    g = ev.GraphEvaluator()
+    zero, one, two = ("constant", ev.FR_ZERO), ("constant", ev.FR_ONE), ("constant", ev.FR_TWO)
+    a, b = ("advice", 0, 0), ("advice", 1, -1)
+    sa, sb = g.add_expression(a), g.add_expression(b)
+    assert sa == ev.src(ev.INTERMEDIATE, 0) and sb == ev.src(ev.INTERMEDIATE, 1) and g.rotations == [0, -1]
+    assert g.add_expression(a) == sa and len(g.calculations) == 2                      # shared
+    assert g.add_expression(("sum", a, zero)) == sa and g.add_expression(("sum", zero, b)) == sb
+    assert g.add_expression(("product", a, one)) == sa and g.add_expression(("product", zero, b)) == ev.src(ev.CONSTANT, 0)
+    assert g.calculations[g.add_expression(("product", two, a))[1]] == (ev.DOUBLE, sa)
+    assert g.calculations[g.add_expression(("product", a, a))[1]] == (ev.SQUARE, sa)
+    assert g.calculations[g.add_expression(("sum", a, ("negated", b)))[1]] == (ev.SUB, sa, sb)
+    assert g.calculations[g.add_expression(("sum", zero, ("negated", b)))[1]] == (ev.NEGATE, sb)
+    assert g.add_expression(("product", b, a)) == g.add_expression(("product", a, b))  # commutative operands are ordered
+    assert g.add_expression(("scaled", a, ev.FR_ZERO)) == ev.src(ev.CONSTANT, 0) and g.add_expression(("scaled", a, ev.FR_ONE)) == sa
+    seven = mont([7], R)[0]
+    s7 = g.add_expression(("scaled", a, seven))
+    assert g.calculations[s7[1]] == (ev.MUL, sa, ev.src(ev.CONSTANT, 3)) and g.constants[3] == tuple(int(x) for x in seven)
+    assert g.add_constant(seven) == ev.src(ev.CONSTANT, 3) and len(g.constants) == 4
+    n_before = len(g.calculations)
+    res = g.add_gates([("product", ("fixed", 0, 0), a)])
+    assert g.calculations[res[1]][0] == ev.HORNER and g.calculations[res[1]][1] == ev.src(ev.PREVIOUS) and len(g.calculations) == n_before + 3
+    # the encoded program round-trips through the oracle on a tiny domain
+    k, ext_k = 2, 3
+    rng = np.random.default_rng(49)
+    cols = [rand_ints(rng, 1 << ext_k, R) for _ in range(3)]
+    y = rand_ints(rng, 1, R)[0]
+    prev = rand_ints(rng, 1 << ext_k, R)
+    bound = ev.BoundGraph(g, res, fixed=[mont(cols[0], R)], advice=[mont(cols[1], R), mont(cols[2], R)], y=mont([y], R)[0])
+    got = unmont(orc.quotient_graph(bound.struct, k, ext_k, mont(prev, R)), R)
+    assert got == [(prev[i] * y + cols[0][i] * cols[1][i]) % R for i in range(1 << ext_k)]
