@@ -55,6 +55,7 @@ SIGNATURES = {
     "h2b_srs_destroy": (None, [_vp, _vp]),
     "h2b_msm_g1": (_int, [_vp, _vp, _int, _vp, _sz, _vp]),
     "h2b_msm_g1_batch": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_vp), _sz, _sz, _vp]),
+    "h2b_msm_g1_batch_reduced": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_vp), _sz, _sz, _vp]),
     "h2b_msm_g1_batch_dev": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_vp), _sz, _sz, _vp]),
     "h2b_msm_g1_bases": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "h2b_msm_g1_dev": (_int, [_vp, _vp, _int, _vp, _sz, _vp]),

@@ -164,7 +164,18 @@ int h2b_ctx_set_stream(h2b_ctx* ctx, void* cuda_stream) {
 int h2b_ctx_synchronize(h2b_ctx* ctx) {
     return guarded(ctx, [&] { H2B_CUDA(cudaStreamSynchronize(ctx->stream)); });
 }
-const char* h2b_last_error(const h2b_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* h2b_last_error(const h2b_ctx* ctx) {
+    // the message is copied under the lock into a per-thread buffer: rayon workers may fail concurrently
+    static thread_local std::string tl;
+    if (ctx) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        tl = ctx->err;
+    } else {
+        std::lock_guard<std::mutex> lock(g_create_mu);
+        tl = g_create_error;
+    }
+    return tl.c_str();
+}
 uint64_t h2b_kernel_launches(const h2b_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------ profiling
@@ -296,57 +307,70 @@ int h2b_msm_g1_batch_dev(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, con
         msm_run_batch(ctx, tables.data(), n, srs->c, srs->W, d_scalars, m, d_out);
     });
 }
-int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
-                     uint64_t* out_xyz) {
-    return guarded(ctx, [&] {
-        H2B_REQUIRE(basis && scalars && out_xyz, "msm: null pointer");
-        if (m == 0) return;
-        std::vector<const void*> tables(m);
-        for (size_t j = 0; j < m; j++) tables[j] = srs_table(srs, basis[j], n);
-        constexpr int NL = h2b_ctx::NLANES;
-        const int nl = (int)(m < (size_t)NL ? m : (size_t)NL);
-        void* stage[NL];
-        for (int l = 0; l < nl; l++) {
-            ctx->cur_lane = l;
-            stage[l] = ctx->get(WS_SCALARS, n * 32);
+// host columns -> m commitments on the host.  Uploads run on the copy stream into per-lane staging buffers; lane l's MSM
+// waits for its upload and releases the buffer as soon as the scatter pass has consumed it.  `reduce`: combine the
+// partial sums of all connected GPUs with the fused NVLink all-reduce kernel before the one device-to-host copy.
+static void msm_batch_host(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
+                           uint64_t* out_xyz, bool reduce) {
+    H2B_REQUIRE(basis && scalars && out_xyz, "msm: null pointer");
+    if (m == 0) return;
+    // validate everything before any stream is forked (a throw after the fork would leave the lanes unjoined)
+    std::vector<const void*> tables(m);
+    for (size_t j = 0; j < m; j++) {
+        H2B_REQUIRE(scalars[j], "msm: null scalar column");
+        tables[j] = srs_table(srs, basis[j], n);
+    }
+    constexpr int NL = h2b_ctx::NLANES;
+    const int nl = (int)(m < (size_t)NL ? m : (size_t)NL);
+    void* stage[NL];
+    for (int l = 0; l < nl; l++) {
+        ctx->cur_lane = l;
+        stage[l] = ctx->get(WS_SCALARS, n * 32);
+    }
+    ctx->cur_lane = 0;
+    void* d_out = ctx->get(WS_OUT, m * 96);
+    uint64_t* h_out = (uint64_t*)ctx->get_pinned(0, m * 96);
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    H2B_CUDA(cudaEventRecord(ctx->fork_ev, ks));
+    H2B_CUDA(cudaStreamWaitEvent(cs, ctx->fork_ev, 0));
+    for (int l = 0; l < nl; l++) H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork_ev, 0));
+    struct Join {  // joins the lanes back onto the caller's stream on every exit path
+        h2b_ctx* c; cudaStream_t ks; int nl;
+        ~Join() {
+            c->stream = ks;
+            c->cur_lane = 0;
+            for (int l = 0; l < nl; l++) {
+                cudaEventRecord(c->lane_done[l], c->lane_stream[l]);
+                cudaStreamWaitEvent(ks, c->lane_done[l], 0);
+            }
         }
-        ctx->cur_lane = 0;
-        void* d_out = ctx->get(WS_OUT, m * 96);
-        uint64_t* h_out = (uint64_t*)ctx->get_pinned(0, m * 96);
-        cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
-        // uploads run on the copy stream into per-lane staging buffers; lane l's MSM waits for its upload and
-        // releases the buffer as soon as k_digits has consumed it
-        H2B_CUDA(cudaEventRecord(ctx->fork_ev, ks));
-        H2B_CUDA(cudaStreamWaitEvent(cs, ctx->fork_ev, 0));
-        for (int l = 0; l < nl; l++) H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork_ev, 0));
+    };
+    {
+        Join join{ctx, ks, nl};
         for (size_t j = 0; j < m; j++) {
             const int l = (int)(j % nl);
-            H2B_REQUIRE(scalars[j], "msm: null scalar column");
             if (j >= (size_t)nl) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->lane_consumed[l], 0));
             H2B_CUDA(cudaMemcpyAsync(stage[l], scalars[j], n * 32, cudaMemcpyHostToDevice, cs));
             H2B_CUDA(cudaEventRecord(ctx->lane_ready[l], cs));
             H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_ready[l], 0));
-            cudaStream_t saved = ctx->stream;
             ctx->stream = ctx->lane_stream[l];
             ctx->cur_lane = l;
-            try {
-                msm_run(ctx, tables[j], n, srs->c, srs->W, srs->W, stage[l], (char*)d_out + 96 * j, ctx->lane_consumed[l]);
-            } catch (...) {
-                ctx->stream = saved;
-                ctx->cur_lane = 0;
-                throw;
-            }
-            ctx->stream = saved;
-            ctx->cur_lane = 0;
+            msm_run(ctx, tables[j], n, srs->c, srs->W, srs->W, stage[l], (char*)d_out + 96 * j, ctx->lane_consumed[l]);
         }
-        for (int l = 0; l < nl; l++) {
-            H2B_CUDA(cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]));
-            H2B_CUDA(cudaStreamWaitEvent(ks, ctx->lane_done[l], 0));
-        }
-        H2B_CUDA(cudaMemcpyAsync(h_out, d_out, m * 96, cudaMemcpyDeviceToHost, ks));
-        H2B_CUDA(cudaStreamSynchronize(ks));
-        memcpy(out_xyz, h_out, m * 96);
-    });
+    }
+    if (reduce && peer_connected(ctx))
+        for (size_t lo = 0; lo < m; lo += 16) peer_allreduce(ctx, (char*)d_out + 96 * lo, m - lo < 16 ? m - lo : 16);
+    H2B_CUDA(cudaMemcpyAsync(h_out, d_out, m * 96, cudaMemcpyDeviceToHost, ks));
+    H2B_CUDA(cudaStreamSynchronize(ks));
+    memcpy(out_xyz, h_out, m * 96);
+}
+int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
+                     uint64_t* out_xyz) {
+    return guarded(ctx, [&] { msm_batch_host(ctx, srs, basis, scalars, m, n, out_xyz, false); });
+}
+int h2b_msm_g1_batch_reduced(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
+                             uint64_t* out_xyz) {
+    return guarded(ctx, [&] { msm_batch_host(ctx, srs, basis, scalars, m, n, out_xyz, true); });
 }
 int h2b_msm_g1(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
     const uint64_t* cols[1] = {scalars};

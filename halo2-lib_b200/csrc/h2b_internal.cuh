@@ -180,6 +180,7 @@ void peer_create(h2b_ctx* ctx, int rank, int nranks, uint8_t* handle_out);
 void peer_connect(h2b_ctx* ctx, const uint8_t* handles);
 void peer_allreduce(h2b_ctx* ctx, void* d_points, size_t m);
 void peer_destroy(h2b_ctx* ctx);
+bool peer_connected(const h2b_ctx* ctx);
 // ---- quotient.cu
 void flex_gate_fold_run(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k, uint32_t ext_k,
                         void* d_acc);

@@ -655,13 +655,18 @@ void msm_run_batch(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, i
     H2B_CUDA(cudaEventRecord(ctx->fork_ev, main));
     const int nl = (int)(m < (size_t)h2b_ctx::NLANES ? m : (size_t)h2b_ctx::NLANES);
     for (int l = 0; l < nl; l++) H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork_ev, 0));
+    struct Join {  // the lanes are joined back onto the caller's stream on every exit path (a throw included)
+        h2b_ctx* c; cudaStream_t main; int nl;
+        ~Join() {
+            for (int l = 0; l < nl; l++) {
+                cudaEventRecord(c->lane_done[l], c->lane_stream[l]);
+                cudaStreamWaitEvent(main, c->lane_done[l], 0);
+            }
+        }
+    } join{ctx, main, nl};
     for (size_t j = 0; j < m; j++) {
         LaneScope scope(ctx, (int)(j % nl));
         msm_run(ctx, d_tables[j], n, c, W, W, d_scalars[j], (char*)d_out + 96 * j);
-    }
-    for (int l = 0; l < nl; l++) {
-        H2B_CUDA(cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]));
-        H2B_CUDA(cudaStreamWaitEvent(main, ctx->lane_done[l], 0));
     }
 }
 

@@ -60,7 +60,17 @@ __global__ void __launch_bounds__(256) k_g1_allreduce(PeerPtrs peers, int rank, 
     // 2. wait until every rank has published this epoch in MY mailbox
     if (t < nranks) {
         volatile uint64_t* f = &peers.box[rank]->flags[par][t];
-        while (*f != epoch) { }
+        // bounded wait: a peer that never arrives (failed launch, dead process) must not hang the GPU; after ~10 s the
+        // kernel traps, which surfaces as H2B_ERR_CUDA on the next call instead of a wedged device
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        while (*f != epoch) {
+            if ((++spins & 0xfffu) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > 10000000000ull) __trap();
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -133,8 +143,13 @@ void peer_allreduce(h2b_ctx* ctx, void* d_points, size_t m) {
     PeerState* st = (PeerState*)ctx->peer;
     H2B_REQUIRE(st && st->connected, "peer: mailboxes are not connected");
     H2B_REQUIRE(m >= 1 && m <= (size_t)PEER_MAX_POINTS, "peer: 1..16 points per call");
+    // the epoch only advances once the launch has been accepted: a failed launch must not desynchronise the ranks
+    H2B_LAUNCH(ctx, k_g1_allreduce, 1, 256, 0, st->ptrs, st->rank, st->nranks, st->epoch + 1, (uint64_t*)d_points, (int)m);
     st->epoch++;
-    H2B_LAUNCH(ctx, k_g1_allreduce, 1, 256, 0, st->ptrs, st->rank, st->nranks, st->epoch, (uint64_t*)d_points, (int)m);
+}
+bool peer_connected(const h2b_ctx* ctx) {
+    const PeerState* st = (const PeerState*)ctx->peer;
+    return st && st->connected && st->nranks > 1;
 }
 
 void peer_destroy(h2b_ctx* ctx) {

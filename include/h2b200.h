@@ -109,6 +109,11 @@ int h2b_msm_g1(h2b_ctx* ctx, const h2b_srs* srs, int basis, const uint64_t* scal
  * are pipelined against the kernels and the MSMs are spread over the context's lanes (see h2b_msm_g1_batch_dev). */
 int h2b_msm_g1_batch(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m,
                      size_t n, uint64_t* out_xyz);
+/* Same as h2b_msm_g1_batch, but when the context's NVLink mailboxes are connected (h2b_peer_connect) the m partial
+ * sums of all GPUs are combined on the device by the fused all-reduce kernel before the single device-to-host copy:
+ * out = the m FULL commitments on every rank.  Without peers it is h2b_msm_g1_batch. */
+int h2b_msm_g1_batch_reduced(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m,
+                             size_t n, uint64_t* out_xyz);
 /* Ad-hoc bases (n x 8 limbs on the host), no precomputation. */
 int h2b_msm_g1_bases(h2b_ctx* ctx, const uint64_t* bases, const uint64_t* scalars, size_t n,
                      uint64_t out_xyz[12]);

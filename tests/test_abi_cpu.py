@@ -62,8 +62,9 @@ def test_product_does_not_reference_the_oracle():
 
 def test_bench_schedule_shape():
     import bench
-    assert len(bench.MSM_SCHEDULE) == 12  # 12 MSMs x 2^19 for the ECDSA circuit
-    assert sorted(j for p in bench.MSM_PHASES for j in p) == list(range(12))
+    s = bench.Schedule(3)
+    assert len(s.msm) == 12  # 12 MSMs x 2^19 for the ECDSA circuit
+    assert sorted(j for p in s.phases for j in p) == list(range(12))
     a = bench.witness_like(np.random.default_rng(0), 4096)
     frac0 = float((a == 0).all(axis=1).mean())
     assert 0.30 < frac0 < 0.40
