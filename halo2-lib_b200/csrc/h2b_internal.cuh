@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <array>
+#include <algorithm>
 
 #include "../../include/h2b200.h"
 
@@ -60,6 +61,8 @@ enum WsSlot {
     WS_ASSIGN_OUT,
     WS_MISC,
     WS_MISC2,
+    WS_RED_A,         // batch-affine group sums (ping)
+    WS_RED_B,         // batch-affine group sums (pong)
     WS_COUNT
 };
 
@@ -80,6 +83,7 @@ struct h2b_ctx {
     std::string err;
     uint64_t launches = 0;
     bool ntt_attr_set = false;
+    bool ba_attr_set = false;
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
     bool reduce_counter_zeroed = false;
     void* reduce_counter_ptr = nullptr;

@@ -22,6 +22,7 @@
 // windows of a scalar fall into ONE bucket set: no per-window reduction and no final doublings.
 #include "curve.cuh"
 #include "quad.cuh"
+#include "batch_affine.cuh"
 #include "h2b_internal.cuh"
 
 namespace h2b {
@@ -117,12 +118,13 @@ __global__ void __launch_bounds__(256) k_digits(const uint64_t* __restrict__ sca
 // k_scan_tiles: off[b] = exclusive prefix inside the tile, tile_sums[tile] = tile total.
 // k_scan_apply: adds the sum of the preceding tile totals; cursor[b] = off[b]; off[nb] = grand total.
 static constexpr int SCAN_TILE = 2048;
+// `gmask` = G - 1: every bucket's run is padded to a multiple of G = 2^R slots (batch_affine.cuh); 0 = no padding.
 __global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ hist, u32 nb, u32* __restrict__ off,
-                                                    u32* __restrict__ tile_sums) {
+                                                    u32* __restrict__ tile_sums, u32 gmask) {
     __shared__ u32 sh[SCAN_TILE];
     __shared__ u32 wsum[8];
     const u32 base = blockIdx.x * SCAN_TILE, t = threadIdx.x;
-    for (u32 e = t; e < SCAN_TILE; e += 256) sh[e] = (base + e < nb) ? hist[base + e] : 0;  // coalesced
+    for (u32 e = t; e < SCAN_TILE; e += 256) sh[e] = (base + e < nb) ? ((hist[base + e] + gmask) & ~gmask) : 0;  // coalesced
     __syncthreads();
     u32 v[8], sum = 0;
 #pragma unroll
@@ -147,9 +149,12 @@ __global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ hist
         if (base + e < nb) off[base + e] = sh[e];
     if (t == 255) tile_sums[blockIdx.x] = run;
 }
+// With padding (shift = R > 0) the slots [off[b] + hist[b], off[b + 1]) of every bucket are filled with BA_PAD here, and the
+// chunk length is chosen for the M' >> R group sums k_accumulate will walk.
 __global__ void __launch_bounds__(256) k_scan_apply(u32 nb, u32 ntiles, const u32* __restrict__ tile_sums,
                                                     u32* __restrict__ off, u32* __restrict__ cursor, u32 slots,
-                                                    u32 l_min, u32 l_max, u32* __restrict__ d_L) {
+                                                    u32 l_min, u32 l_max, u32* __restrict__ d_L, const u32* __restrict__ hist,
+                                                    u32* __restrict__ vals, int shift) {
     __shared__ u32 red[256];
     const u32 t = threadIdx.x;
     u32 s = 0;
@@ -166,10 +171,15 @@ __global__ void __launch_bounds__(256) k_scan_apply(u32 nb, u32 ntiles, const u3
             u32 o = off[base + e] + add;
             off[base + e] = o;
             cursor[base + e] = o;
+            if (shift) {
+                const u32 h = hist[base + e], gm = (1u << shift) - 1u;
+                for (u32 p = o + h; p < o + ((h + gm) & ~gm); p++) vals[p] = BA_PAD;
+            }
         }
     if (blockIdx.x == ntiles - 1 && t == 0) {
-        const u32 mv = add + tile_sums[ntiles - 1];
-        off[nb] = mv;
+        const u32 mv_all = add + tile_sums[ntiles - 1];
+        off[nb] = mv_all;
+        const u32 mv = mv_all >> shift;
         // chunk length for k_accumulate: whole waves of equally long chunks (see k_accumulate)
         u32 L = l_max;
         if (mv < l_max * slots) {  // less than one full wave of l_max-chunks: spread the entries over every slot
@@ -187,12 +197,15 @@ __device__ __forceinline__ Affine load_signed(const Affine* __restrict__ table, 
     return p;
 }
 
+// Offsets are stored in units of sorted entries; with batch-affine reduction k_accumulate and the collect kernels walk
+// group sums, i.e. positions in units of 2^sh entries (every offset is a multiple of 2^sh then).
+__device__ __forceinline__ u32 offs(const u32* __restrict__ off, u32 b, int sh) { return __ldg(off + b) >> sh; }
 // first bucket b in [lo, nb) with off[b + 1] > pos  (the bucket that owns sorted position pos)
-__device__ __forceinline__ u32 bucket_of(const u32* __restrict__ off, u32 lo, u32 nb, u32 pos) {
+__device__ __forceinline__ u32 bucket_of(const u32* __restrict__ off, u32 lo, u32 nb, u32 pos, int sh) {
     u32 hi = nb;
     while (lo < hi) {
         u32 mid = (lo + hi) >> 1;
-        if (__ldg(off + mid + 1) > pos) hi = mid; else lo = mid + 1;
+        if (offs(off, mid + 1, sh) > pos) hi = mid; else lo = mid + 1;
     }
     return lo;
 }
@@ -202,30 +215,37 @@ __device__ __forceinline__ u32 bucket_of(const u32* __restrict__ off, u32 lo, u3
 // 32-entry chunks (sparse witness columns, small shards) L = ceil(entries / slots), slots = resident threads of
 // this kernel, so that every SM is busy.  (Whole-wave balancing of dense columns was measured: no gain, the
 // kernel is multiplier-bound and a partially filled last wave simply runs faster.)
+// DIRECT = false: entry i is the table point vals[i] (index | sign).  DIRECT = true: entry i is the affine point pts[i]
+// (the group sums left by the batch-affine passes), positions in units of 2^sh sorted entries.
+template <bool DIRECT>
 __global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ vals, const u32* __restrict__ off,
                                                        u32 nb_total, const u32* __restrict__ d_L,
                                                        const Affine* __restrict__ table,
-                                                       XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials) {
+                                                       XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials, int sh) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 L = __ldg(d_L);
-    const u32 mv = __ldg(off + nb_total);  // number of (non-zero-digit) entries
+    const u32 mv = offs(off, nb_total, sh);  // number of entries (non-zero digits, or group sums)
     const u64 cs64 = (u64)t * L;
     if (cs64 >= mv) return;
     const u32 cs = (u32)cs64;
     const u32 ce = (mv - cs < (u32)L) ? mv : cs + L;
+    auto fetch = [&](u32 i) -> Affine {
+        if (DIRECT) return Affine::load(table + i);
+        return load_signed(table, __ldg(vals + i));
+    };
 
-    u32 cur = bucket_of(off, 0, nb_total, cs);
-    u32 run_end = __ldg(off + cur + 1);
+    u32 cur = bucket_of(off, 0, nb_total, cs, sh);
+    u32 run_end = offs(off, cur + 1, sh);
     XYZZ acc = XYZZ::identity();
-    Affine p = load_signed(table, __ldg(vals + cs));
+    Affine p = fetch(cs);
     for (u32 i = cs; i < ce; i++) {
         Affine pn;
         const bool more = (i + 1 < ce);
-        if (more) pn = load_signed(table, __ldg(vals + i + 1));  // prefetch the next gather while this add runs
+        if (more) pn = fetch(i + 1);  // prefetch the next point while this add runs
         xyzz_madd(acc, p);
         if (!more || i + 1 == run_end) {
             // the run of bucket `cur` ends here (inside this chunk or at its border)
-            const u32 s = __ldg(off + cur);
+            const u32 s = offs(off, cur, sh);
             if (s >= cs && run_end - cs <= (u32)L) acc.store(buckets + cur);    // bucket lies inside the chunk
             else if (s <= cs) acc.store(partials + 2 * (size_t)t);              // covers the chunk start
             else acc.store(partials + 2 * (size_t)t + 1);                        // starts inside, runs past the end
@@ -233,12 +253,12 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ v
             if (more) {  // next non-empty bucket: a few linear steps, then binary search (long empty gaps)
                 u32 b = cur + 1;
                 int steps = 0;
-                while (__ldg(off + b + 1) <= i + 1) {
+                while (offs(off, b + 1, sh) <= i + 1) {
                     b++;
-                    if (++steps == 4) { b = bucket_of(off, b, nb_total, i + 1); break; }
+                    if (++steps == 4) { b = bucket_of(off, b, nb_total, i + 1, sh); break; }
                 }
                 cur = b;
-                run_end = __ldg(off + cur + 1);
+                run_end = offs(off, cur + 1, sh);
             }
         }
         if (more) p = pn;
@@ -252,11 +272,11 @@ __device__ __forceinline__ const XYZZ* partial_of(const XYZZ* partials, u32 s, u
 // one thread per bucket: empty -> identity; spans several chunks -> add their partials
 __global__ void __launch_bounds__(128) k_collect(const u32* __restrict__ off, u32 nb_total, const u32* __restrict__ d_L,
                                                  const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets,
-                                                 u32* __restrict__ big_list, u32* __restrict__ big_count) {
+                                                 u32* __restrict__ big_list, u32* __restrict__ big_count, int sh) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb_total) return;
     const u32 L = __ldg(d_L);
-    const u32 s = __ldg(off + b), e = __ldg(off + b + 1);
+    const u32 s = offs(off, b, sh), e = offs(off, b + 1, sh);
     if (s == e) {
         XYZZ::identity().store(buckets + b);
         return;
@@ -279,7 +299,7 @@ __global__ void __launch_bounds__(128) k_collect(const u32* __restrict__ off, u3
 static constexpr int BIG_SEG = 64;
 __global__ void __launch_bounds__(256) k_collect_big1(const u32* __restrict__ off, const u32* __restrict__ d_L, const XYZZ* __restrict__ partials,
                                                       const u32* __restrict__ big_list, const u32* __restrict__ big_count,
-                                                      XYZZ* __restrict__ seg) {
+                                                      XYZZ* __restrict__ seg, int shf) {
     __shared__ XYZZ sh[8];
     const u32 nbig = *big_count;
     const u32 L = __ldg(d_L);
@@ -288,7 +308,7 @@ __global__ void __launch_bounds__(256) k_collect_big1(const u32* __restrict__ of
     u32 g = blockIdx.x;  // next segment of this CTA (segments are numbered across all big buckets)
     for (u32 j = 0; j < nbig; j++) {
         const u32 b = big_list[j];
-        const u32 s = __ldg(off + b), e = __ldg(off + b + 1);
+        const u32 s = offs(off, b, shf), e = offs(off, b + 1, shf);
         const u32 t_lo = s / L, t_hi = (e - 1) / L;
         const u32 cnt = t_hi - t_lo + 1, nseg = (cnt + BIG_SEG - 1) / BIG_SEG;
         for (; g < seg_base + nseg; g += gridDim.x) {
@@ -304,7 +324,7 @@ __global__ void __launch_bounds__(256) k_collect_big1(const u32* __restrict__ of
 }
 __global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ off, const u32* __restrict__ d_L, const XYZZ* __restrict__ seg,
                                                       XYZZ* __restrict__ buckets, const u32* __restrict__ big_list,
-                                                      const u32* __restrict__ big_count) {
+                                                      const u32* __restrict__ big_count, int shf) {
     __shared__ XYZZ sh[8];
     const u32 nbig = *big_count;
     const u32 L = __ldg(d_L);
@@ -312,7 +332,7 @@ __global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ of
     u32 seg_base = 0;
     for (u32 j = 0; j < nbig; j++) {
         const u32 b = big_list[j];
-        const u32 s = __ldg(off + b), e = __ldg(off + b + 1);
+        const u32 s = offs(off, b, shf), e = offs(off, b + 1, shf);
         const u32 cnt = (e - 1) / L - s / L + 1, nseg = (cnt + BIG_SEG - 1) / BIG_SEG;
         if (j % gridDim.x == blockIdx.x) {
             XYZZ acc = XYZZ::identity();
@@ -548,17 +568,49 @@ void msm_build_table(h2b_ctx* ctx, const void* d_bases, size_t count, int c, int
                    t + (size_t)w * count, (u32)count, c);
 }
 
+// number of batch-affine halving passes for a table-mode MSM with `e` sorted entries per bucket on average
+static int msm_choose_levels(size_t M, size_t nb_total, int q_is_table) {
+    static const int forced = [] {
+        const char* e = getenv("H2B_AFF_LEVELS");
+        return e ? atoi(e) : -1;
+    }();
+    if (forced >= 0 && forced <= 4) return forced;
+    if (!q_is_table) return 0;
+    const size_t e = M / (nb_total ? nb_total : 1);
+    if (e >= 40) return 3;   // groups of 8: 3.5 padding slots per bucket on >= 40 entries
+    if (e >= 14) return 2;
+    return 0;
+}
+
+template <int K>
+static void launch_batch_affine(h2b_ctx* ctx, bool level1, const u32* vals, const Affine* table, const Affine* in, Affine* out,
+                                const u32* d_entries, int level, size_t max_pairs) {
+    const size_t smem = ((size_t)K * 8 * BA_T + 2 * BA_T * 8) * 4;
+    if (!ctx->ba_attr_set) {
+        H2B_CUDA(cudaFuncSetAttribute(k_batch_affine<true, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        H2B_CUDA(cudaFuncSetAttribute(k_batch_affine<false, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->ba_attr_set = true;
+    }
+    const unsigned grid = ceil_div(max_pairs, (size_t)BA_T * K);
+    if (level1) H2B_LAUNCH(ctx, (k_batch_affine<true, K>), grid, BA_T, smem, vals, table, in, out, d_entries, level);
+    else H2B_LAUNCH(ctx, (k_batch_affine<false, K>), grid, BA_T, smem, vals, table, in, out, d_entries, level);
+}
+
 void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out,
              cudaEvent_t after_digits) {
     H2B_REQUIRE(n >= 1 && n <= ((size_t)1 << 27), "msm: n out of range");
-    H2B_REQUIRE((size_t)W * n < ((size_t)1 << 31), "msm: n * windows exceeds the 31-bit table index");
+    H2B_REQUIRE((size_t)W * n < ((size_t)1 << 31) - 8, "msm: n * windows exceeds the 31-bit table index");
     const u32 nbw = 1u << (c - 1);
     const u32 nsets = (u32)((W + q - 1) / q);
     const u32 nb_total = nsets * nbw;
     const size_t M = (size_t)W * n;
     cudaStream_t st = ctx->stream;
+    const int R = msm_choose_levels(M, nb_total, q == W);  // batch-affine halving passes; groups of G = 2^R entries
+    const size_t G = (size_t)1 << R;
+    const size_t Mp = M + (G - 1) * nb_total;  // upper bound of the padded entry count
+    H2B_REQUIRE(Mp < ((size_t)1 << 32), "msm: padded entry count exceeds 32 bits");
 
-    u32* vals = (u32*)ctx->get(WS_VALS_A, M * 4);
+    u32* vals = (u32*)ctx->get(WS_VALS_A, Mp * 4 + 16);
     u32* cnt = (u32*)ctx->get(WS_KEYS_A, (2 * ((size_t)nb_total + 2) + nb_total / SCAN_TILE + 4) * 4);  // histogram, cursors, tile sums, L
     u32* hist = cnt;
     u32* cursor = cnt + nb_total + 2;
@@ -570,28 +622,47 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
         return (v >= 8 && v <= 64) ? v : 0;
     }();
     const u32 l_min = L_MAX ? (u32)L_MAX : 12u, l_max = L_MAX ? (u32)L_MAX : (u32)ACC_L_DEFAULT;
-    const size_t n_chunks = (M + l_min - 1) / l_min;  // worst case; threads beyond the entries exit at once
+    const u32 slots = (u32)ctx->sm_count * 512u;  // k_accumulate: 128 registers -> 4 CTAs x 128 threads per SM
+    // chunks of k_accumulate: L < l_max is only chosen when the entries do not fill one wave, i.e. at most `slots` chunks
+    const size_t Macc = Mp >> R;
+    const size_t n_chunks = L_MAX ? (Macc + l_min - 1) / l_min : std::max((Macc + l_max - 1) / l_max, (size_t)slots) + 1;
     XYZZ* partials = (XYZZ*)ctx->get(WS_PARTIALS, 2 * n_chunks * sizeof(XYZZ));
     u32* big = (u32*)ctx->get(WS_BIGLIST, ((size_t)nb_total + 1) * 4);  // [0] = counter, list follows
+    Affine* red_a = nullptr;
+    Affine* red_b = nullptr;
+    if (R >= 1) red_a = (Affine*)ctx->get(WS_RED_A, (Mp / 2) * sizeof(Affine));
+    if (R >= 2) red_b = (Affine*)ctx->get(WS_RED_B, (Mp / 4) * sizeof(Affine));
 
     // counting sort by bucket: histogram -> exclusive scan -> scatter (digits are recomputed, not stored)
     H2B_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nb_total + 1) * 4, st));
     H2B_LAUNCH(ctx, k_digits<0>, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, hist, (u32*)nullptr);
     const u32 ntiles = (nb_total + SCAN_TILE - 1) / SCAN_TILE;
     u32* tile_sums = cursor + nb_total + 2;
-    H2B_LAUNCH(ctx, k_scan_tiles, ntiles, 256, 0, hist, nb_total, off, tile_sums);
+    H2B_LAUNCH(ctx, k_scan_tiles, ntiles, 256, 0, hist, nb_total, off, tile_sums, (u32)(G - 1));
     u32* d_L = tile_sums + ntiles + 1;
-    const u32 slots = (u32)ctx->sm_count * 512u;  // k_accumulate: 128 registers -> 4 CTAs x 128 threads per SM
-    H2B_LAUNCH(ctx, k_scan_apply, ntiles, 256, 0, nb_total, ntiles, tile_sums, off, cursor, slots, l_min, l_max, d_L);
+    H2B_LAUNCH(ctx, k_scan_apply, ntiles, 256, 0, nb_total, ntiles, tile_sums, off, cursor, slots, l_min, l_max, d_L, hist, vals, R);
     H2B_LAUNCH(ctx, k_digits<1>, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, cursor, vals);
     if (after_digits) H2B_CUDA(cudaEventRecord(after_digits, st));
 
     H2B_CUDA(cudaMemsetAsync(big, 0, 4, st));
-    H2B_LAUNCH(ctx, k_accumulate, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, d_L, (const Affine*)d_table, buckets, partials);
-    H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, d_L, partials, buckets, big + 1, big);
+    if (R == 0) {
+        H2B_LAUNCH(ctx, k_accumulate<false>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, d_L, (const Affine*)d_table, buckets, partials, 0);
+    } else {
+        // R halving passes in affine coordinates (one shared inversion per CTA), ping-ponging between two buffers
+        const u32* d_entries = off + nb_total;
+        Affine* src = nullptr;
+        Affine* dst = red_a;
+        for (int lv = 1; lv <= R; lv++) {
+            launch_batch_affine<16>(ctx, lv == 1, vals, (const Affine*)d_table, src, dst, d_entries, lv, Mp >> lv);
+            src = dst;
+            dst = (dst == red_a) ? red_b : red_a;
+        }
+        H2B_LAUNCH(ctx, k_accumulate<true>, ceil_div(n_chunks, 128), 128, 0, (const u32*)nullptr, off, nb_total, d_L, (const Affine*)src, buckets, partials, R);
+    }
+    H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, d_L, partials, buckets, big + 1, big, R);
     XYZZ* seg = (XYZZ*)ctx->get(WS_POOL, (2 * (n_chunks / BIG_SEG) + 64) * sizeof(XYZZ));
-    H2B_LAUNCH(ctx, k_collect_big1, 2 * ctx->sm_count, 256, 0, off, d_L, partials, big + 1, big, seg);
-    H2B_LAUNCH(ctx, k_collect_big2, 64, 256, 0, off, d_L, seg, buckets, big + 1, big);
+    H2B_LAUNCH(ctx, k_collect_big1, 2 * ctx->sm_count, 256, 0, off, d_L, partials, big + 1, big, seg, R);
+    H2B_LAUNCH(ctx, k_collect_big2, 64, 256, 0, off, d_L, seg, buckets, big + 1, big, R);
 
     // bucket reduction: row/column sums of the 2^mh x 2^ml bucket grid, small scalar multiples, final combine
     const int m = c - 1, ml = (m + 1) / 2, mh = m - ml;
