@@ -44,6 +44,7 @@ SIGNATURES = {
     "h2b_ctx_destroy": (None, [_vp]),
     "h2b_ctx_set_stream": (_int, [_vp, _vp]),
     "h2b_ctx_synchronize": (_int, [_vp]),
+    "h2b_ctx_set_option": (_int, [_vp, C.c_char_p, C.c_int64]),
     "h2b_last_error": (C.c_char_p, [_vp]),
     "h2b_kernel_launches": (C.c_uint64, [_vp]),
     "h2b_profile_enable": (_int, [_vp, C.c_char_p]),

@@ -2,19 +2,27 @@
 // of bucket accumulation (msm.cu).
 //
 // After the counting sort every bucket's run of entries is padded to a multiple of G = 2^R slots, so the sorted array
-// splits into aligned groups of G entries that all belong to ONE bucket.  R passes of this kernel halve the array:
-// pass r adds the points of every aligned pair (2p, 2p+1) in affine coordinates,
+// splits into aligned groups of G entries that all belong to ONE bucket.  R levels halve the array: level l adds the
+// points of every aligned pair (2p, 2p+1) in affine coordinates,
 //     lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1,
 // which costs 5 products + 1 squaring per addition once the inversion is shared (an XYZZ mixed addition costs the
-// equivalent of 9.06 products).  After R passes every group is ONE affine point and k_accumulate only has M / G
+// equivalent of 9.06 products).  After R levels every group is ONE affine point and k_accumulate only has M / G
 // mixed additions left.
 //
-// One CTA = BA_T threads x K pairs.  Forward sweep: every thread multiplies the denominators of its K pairs into a
-// running prefix product kept in shared memory (only the x coordinates are read).  The BA_T thread totals are
-// combined by a product tree in shared memory, ONE lane inverts the root with the product-free binary Euclid
-// (Fp::inv_bgcd, ~35 us of add/shift work that does not occupy the multiplier pipe the other resident CTAs are using),
-// the tree is walked back down to per-thread inverses, and the backward sweep turns prefix products into the
-// individual inverses, finishes the additions and stores the sums (coalesced 64-byte records).
+// One launch, persistent CTAs.  A CTA repeatedly claims a TILE of BA_T x k aligned level-1 pairs (an atomic cursor hands
+// out contiguous ranges; the first tile of a CTA is shortened by blockIdx so that the CTAs of an SM do not reach their
+// inversions in lock step, and tiles shrink towards the end of the array so that all CTAs finish together) and takes it
+// through all R levels (level l has BA_T x k / 2^(l-1) pairs; the sums of one level are read back by the same CTA for
+// the next one, so they mostly stay in L2).  Per level:
+//   forward sweep — every thread multiplies the denominators of its pairs into a running prefix product (only the x
+//     coordinates are read; the prefixes go to a global scratch array, 32 B per pair, read back by the same thread);
+//   the BA_T thread totals are combined by a product tree in shared memory; ONE lane inverts the root with the
+//     product-free binary Euclid (Fp::inv_bgcd: add/shift work that does not occupy the multiplier pipe the other
+//     resident CTAs are using); the tree is walked back down to per-thread inverses;
+//   backward sweep — prefix products become the individual inverses, the additions are finished and the sums stored
+//     (coalesced 64-byte records).
+// Both sweeps are software-pipelined: the operands of the next pair (and, at level 1, the index words of the pair after
+// it) are in flight while the products of the current pair execute.  Only the 8 KB tree lives in shared memory.
 //
 // Completeness: padding slots and identity bases (0,0) are copied through; P + P uses the tangent (3 x^2 / 2 y);
 // P + (-P) yields the identity.  Those pairs contribute the factor 1 to the shared product.
@@ -38,97 +46,84 @@ __device__ __forceinline__ void ba_smem_store(u32* base, int stride, const Fq& v
     for (int l = 0; l < 8; l++) base[l * stride] = v.l[l];
 }
 
-// kind of a pair: 0 = chord addition, 1 = tangent (P == Q), 2 = trivial (an operand is the identity, or P == -Q)
-struct BaPair {
-    Affine p, q;
-    int kind;
-    Fq den;
+// Operand addresses of a pair.  Level 1: table points selected by the (index | sign) words; later levels: the sums of
+// the previous level, written by this kernel (coherent loads, not the read-only path).
+template <bool LEVEL1>
+struct BaSrc {
+    const u32* vals;
+    const Affine* table;
+    const Affine* in;
+    __device__ __forceinline__ uint2 words(u32 pair, bool live) const {
+        if (!LEVEL1) return make_uint2(live ? 0u : BA_PAD, live ? 0u : BA_PAD);
+        return live ? __ldg(reinterpret_cast<const uint2*>(vals) + pair) : make_uint2(BA_PAD, BA_PAD);
+    }
+    __device__ __forceinline__ const char* addr(u32 pair, u32 word, int which) const {
+        if (LEVEL1) return reinterpret_cast<const char*>(table + (word & ~BA_SIGN));
+        return reinterpret_cast<const char*>(in + 2 * (size_t)pair + which);
+    }
+    __device__ __forceinline__ Fq ld(const char* a) const { return LEVEL1 ? Fq::load_nc(a) : Fq::load(a); }
+    // y with the sign of the digit applied
+    __device__ __forceinline__ Fq ld_y(u32 pair, u32 word, int which) const {
+        Fq y = ld(addr(pair, word, which) + 32);
+        if (LEVEL1 && (word & BA_SIGN)) y = y.neg();
+        return y;
+    }
 };
 
+// kind of a pair: 0 = chord addition, 1 = tangent (P == Q), 2 = trivial (an operand is the identity, or P == -Q)
+// Forward sweep: from the x coordinates alone in the common case; y is fetched on the rare paths that need it.
 template <bool LEVEL1>
-__device__ __forceinline__ void ba_load_x(const u32* __restrict__ vals, const Affine* __restrict__ table,
-                                          const Affine* __restrict__ in, u32 pair, bool live, BaPair& r, u32& va, u32& vb) {
-    // x coordinates only (one 32-byte sector per point); y is fetched on the rare paths that need it
-    r.p.x = Fq::zero(); r.q.x = Fq::zero();
-    bool pid = true, qid = true;
-    va = BA_PAD; vb = BA_PAD;
-    if (live) {
-        if (LEVEL1) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(vals) + pair);
-            va = v.x; vb = v.y;
-            if (va != BA_PAD) { r.p.x = Fq::load_nc(table + (va & ~BA_SIGN)); pid = false; }
-            if (vb != BA_PAD) { r.q.x = Fq::load_nc(table + (vb & ~BA_SIGN)); qid = false; }
-        } else {
-            r.p.x = Fq::load_nc(in + 2 * (size_t)pair);
-            r.q.x = Fq::load_nc(in + 2 * (size_t)pair + 1);
-            pid = qid = false;
-        }
-    }
+__device__ __forceinline__ int ba_classify_x(const BaSrc<LEVEL1>& src, u32 pair, uint2 w, const Fq& px, const Fq& qx, Fq& den) {
+    bool pid = w.x == BA_PAD, qid = w.y == BA_PAD;
     // x == 0 may be the identity (0,0): look at y
-    auto y_of = [&](bool first) -> Fq {
-        const Affine* src = LEVEL1 ? table + ((first ? va : vb) & ~BA_SIGN) : in + 2 * (size_t)pair + (first ? 0 : 1);
-        return Fq::load_nc(reinterpret_cast<const char*>(src) + 32);
-    };
-    if (!pid && r.p.x.is_zero()) pid = y_of(true).is_zero();
-    if (!qid && r.q.x.is_zero()) qid = y_of(false).is_zero();
-    if (pid || qid) { r.kind = 2; return; }
-    if (!(r.p.x == r.q.x)) { r.kind = 0; r.den = r.q.x - r.p.x; return; }
-    Fq yp = y_of(true), yq = y_of(false);
-    if (LEVEL1) {
-        if (va & BA_SIGN) yp = yp.neg();
-        if (vb & BA_SIGN) yq = yq.neg();
-    }
-    if (yp == yq && !yp.is_zero()) { r.kind = 1; r.den = yp.dbl(); return; }
-    r.kind = 2;
+    if (!pid && px.is_zero()) pid = src.ld(src.addr(pair, w.x, 0) + 32).is_zero();
+    if (!qid && qx.is_zero()) qid = src.ld(src.addr(pair, w.y, 1) + 32).is_zero();
+    if (pid || qid) return 2;
+    if (!(px == qx)) { den = qx - px; return 0; }
+    const Fq yp = src.ld_y(pair, w.x, 0), yq = src.ld_y(pair, w.y, 1);
+    if (yp == yq && !yp.is_zero()) { den = yp.dbl(); return 1; }
+    return 2;
+}
+__device__ __forceinline__ int ba_classify_full(const Affine& p, const Affine& q, Fq& den) {
+    if (p.is_identity() || q.is_identity()) return 2;
+    if (!(p.x == q.x)) { den = q.x - p.x; return 0; }
+    if (p.y == q.y && !p.y.is_zero()) { den = p.y.dbl(); return 1; }
+    return 2;
 }
 
+// One level of one tile: `kk` pairs per thread, pair index = base + i * BA_T + tid, npairs = total pairs of the level.
 template <bool LEVEL1>
-__device__ __forceinline__ void ba_load_full(const u32* __restrict__ vals, const Affine* __restrict__ table,
-                                             const Affine* __restrict__ in, u32 pair, bool live, BaPair& r) {
-    const Affine idn = {Fq::zero(), Fq::zero()};
-    r.p = idn; r.q = idn;
-    if (live) {
-        if (LEVEL1) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(vals) + pair);
-            if (v.x != BA_PAD) { r.p = Affine::load(table + (v.x & ~BA_SIGN)); if (v.x & BA_SIGN) r.p.y = r.p.y.neg(); }
-            if (v.y != BA_PAD) { r.q = Affine::load(table + (v.y & ~BA_SIGN)); if (v.y & BA_SIGN) r.q.y = r.q.y.neg(); }
-        } else {
-            r.p = Affine::load(in + 2 * (size_t)pair);
-            r.q = Affine::load(in + 2 * (size_t)pair + 1);
-        }
-    }
-    if (r.p.is_identity() || r.q.is_identity()) { r.kind = 2; return; }
-    if (!(r.p.x == r.q.x)) { r.kind = 0; r.den = r.q.x - r.p.x; return; }
-    if (r.p.y == r.q.y && !r.p.y.is_zero()) { r.kind = 1; r.den = r.p.y.dbl(); return; }
-    r.kind = 2;
-}
-
-// n_entries_ptr: number of (padded) sorted entries M' on the device; this pass handles M' >> level pairs.
-// shared memory: K * 8 * BA_T words of prefix products + 2 * BA_T * 8 words for the product tree (inverted in place).
-template <bool LEVEL1, int K>
-__global__ void __launch_bounds__(BA_T, 3) k_batch_affine(const u32* __restrict__ vals, const Affine* __restrict__ table,
-                                                          const Affine* __restrict__ in, Affine* __restrict__ out,
-                                                          const u32* __restrict__ n_entries_ptr, int level) {
-    extern __shared__ u32 ba_sh[];
-    u32* pref = ba_sh;                          // [K][8][BA_T]
-    u32* node = ba_sh + K * 8 * BA_T;           // [8][2 * BA_T]  heap order: leaves at BA_T + tid, root at 1
-    const u32 npairs = __ldg(n_entries_ptr) >> level;
-    const u32 base = blockIdx.x * (u32)(BA_T * K);
-    if (base >= npairs) return;
+__device__ __forceinline__ void ba_level(const BaSrc<LEVEL1> src, Affine* __restrict__ out, Fq* __restrict__ pref,
+                                         u32 base, u32 npairs, int kk, u32* node) {
     const int tid = threadIdx.x;
-
+    const Fq zero = Fq::zero();
     // ---- forward sweep: prefix products of the denominators of this thread's pairs
-    Fq run = Fq::one();
+    {
+        Fq run = Fq::one();
+        u32 pair = base + tid;
+        uint2 w = src.words(pair, pair < npairs);
+        uint2 w_next = src.words(pair + BA_T, kk > 1 && pair + BA_T < npairs);
+        Fq px = w.x != BA_PAD ? src.ld(src.addr(pair, w.x, 0)) : zero;
+        Fq qx = w.y != BA_PAD ? src.ld(src.addr(pair, w.y, 1)) : zero;
 #pragma unroll 1
-    for (int i = 0; i < K; i++) {
-        const u32 pair = base + (u32)i * BA_T + tid;
-        BaPair pr;
-        u32 va, vb;
-        ba_load_x<LEVEL1>(vals, table, in, pair, pair < npairs, pr, va, vb);
-        if (pr.kind != 2) run = run * pr.den;
-        ba_smem_store(pref + (size_t)i * 8 * BA_T + tid, BA_T, run);
+        for (int i = 0; i < kk; i++) {
+            // operands of pair i + 1 and index words of pair i + 2 in flight during the product of pair i
+            const u32 pair_n = pair + BA_T;
+            const uint2 wn = w_next;
+            Fq pxn = zero, qxn = zero;
+            if (i + 1 < kk) {
+                if (wn.x != BA_PAD) pxn = src.ld(src.addr(pair_n, wn.x, 0));
+                if (wn.y != BA_PAD) qxn = src.ld(src.addr(pair_n, wn.y, 1));
+                w_next = src.words(pair_n + BA_T, i + 2 < kk && pair_n + BA_T < npairs);
+            }
+            Fq den;
+            const int kind = ba_classify_x<LEVEL1>(src, pair, w, px, qx, den);
+            if (kind != 2) run = run * den;
+            if (pair < npairs) run.store(pref + pair);
+            pair = pair_n; w = wn; px = pxn; qx = qxn;
+        }
+        ba_smem_store(node + BA_T + tid, 2 * BA_T, run);
     }
-    ba_smem_store(node + BA_T + tid, 2 * BA_T, run);
     __syncthreads();
     // ---- product tree of the thread totals, one inversion, back down to per-thread inverses
 #pragma unroll 1
@@ -156,31 +151,104 @@ __global__ void __launch_bounds__(BA_T, 3) k_batch_affine(const u32* __restrict_
         __syncthreads();
     }
     // ---- backward sweep: individual inverses, the additions, coalesced stores
-    Fq inv_run = ba_smem_load(node + BA_T + tid, 2 * BA_T);  // 1 / (product of all denominators of this thread)
+    {
+        Fq inv_run = ba_smem_load(node + BA_T + tid, 2 * BA_T);  // 1 / (product of all denominators of this thread)
+        auto fetch = [&](u32 pr, uint2 ww, Affine& p, Affine& q) {
+            p.x = zero; p.y = zero; q.x = zero; q.y = zero;
+            if (ww.x != BA_PAD) { const char* a = src.addr(pr, ww.x, 0); p.x = src.ld(a); p.y = src.ld(a + 32); }
+            if (ww.y != BA_PAD) { const char* a = src.addr(pr, ww.y, 1); q.x = src.ld(a); q.y = src.ld(a + 32); }
+        };
+        u32 pair = base + (u32)(kk - 1) * BA_T + tid;
+        uint2 w = src.words(pair, pair < npairs);
+        uint2 w_next = src.words(pair - BA_T, kk > 1 && pair - BA_T < npairs);
+        Affine p, q;
+        fetch(pair, w, p, q);
+        Fq pf = (kk > 1 && pair - BA_T < npairs) ? Fq::load(pref + pair - BA_T) : zero;  // prefix after this thread's pair i - 1
 #pragma unroll 1
-    for (int i = K - 1; i >= 0; i--) {
-        const u32 pair = base + (u32)i * BA_T + tid;
-        const bool live = pair < npairs;
-        BaPair pr;
-        ba_load_full<LEVEL1>(vals, table, in, pair, live, pr);
-        Affine sum;
-        if (pr.kind == 2) {
-            // identity operand -> the other one; P + (-P) (both non-identity) -> identity
-            if (pr.p.is_identity()) sum = pr.q;
-            else if (pr.q.is_identity()) sum = pr.p;
-            else { sum.x = Fq::zero(); sum.y = Fq::zero(); }
-        } else {
-            Fq inv = inv_run;
-            if (i > 0) inv = inv * ba_smem_load(pref + (size_t)(i - 1) * 8 * BA_T + tid, BA_T);
-            inv_run = inv_run * pr.den;
-            Fq num;
-            if (pr.kind == 0) num = pr.q.y - pr.p.y;
-            else { const Fq xx = pr.p.x.sqr(); num = xx.dbl() + xx; }
-            const Fq lam = num * inv;
-            sum.x = lam.sqr() - pr.p.x - pr.q.x;
-            sum.y = lam * (pr.p.x - sum.x) - pr.p.y;
+        for (int i = kk - 1; i >= 0; i--) {
+            const u32 pair_n = pair - BA_T;  // this thread's pair i - 1 (only used when i > 0)
+            const uint2 wn = w_next;
+            Affine pn, qn;
+            Fq pfn = zero;
+            pn.x = zero; pn.y = zero; qn.x = zero; qn.y = zero;
+            if (i > 0) {
+                fetch(pair_n, wn, pn, qn);
+                if (i > 1 && pair_n - BA_T < npairs) pfn = Fq::load(pref + pair_n - BA_T);
+                w_next = src.words(pair_n - BA_T, i > 1 && pair_n - BA_T < npairs);
+            }
+            if (LEVEL1) {
+                if (w.x != BA_PAD && (w.x & BA_SIGN)) p.y = p.y.neg();
+                if (w.y != BA_PAD && (w.y & BA_SIGN)) q.y = q.y.neg();
+            }
+            Fq den;
+            const int kind = ba_classify_full(p, q, den);
+            Affine sum;
+            if (kind == 2) {
+                // identity operand -> the other one; P + (-P) (both non-identity) -> identity
+                if (p.is_identity()) sum = q;
+                else if (q.is_identity()) sum = p;
+                else { sum.x = zero; sum.y = zero; }
+            } else {
+                Fq inv = inv_run;
+                if (i > 0) inv = inv * pf;
+                inv_run = inv_run * den;
+                Fq num;
+                if (kind == 0) num = q.y - p.y;
+                else { const Fq xx = p.x.sqr(); num = xx.dbl() + xx; }
+                const Fq lam = num * inv;
+                sum.x = lam.sqr() - p.x - q.x;
+                sum.y = lam * (p.x - sum.x) - p.y;
+            }
+            if (pair < npairs) sum.store(out + pair);
+            pair = pair_n; w = wn; p = pn; q = qn; pf = pfn;
         }
-        if (live) sum.store(out + pair);
+    }
+    __syncthreads();  // the sums of this level are read by other threads of the CTA at the next level; node is reused
+}
+
+// n_entries_ptr: number of (padded) sorted entries M' on the device (a multiple of 2^R).  cursor: level-1 pair cursor,
+// zero at launch.  buf_a / buf_b / buf_c: sums of levels 1, 2, 3 (M'/2, M'/4, M'/8 points); pref: M'/2 prefix products.
+// k_nominal: level-1 pairs per thread and tile (multiple of 4).  R <= 3.
+__global__ void __launch_bounds__(BA_T, 4) k_batch_affine(const u32* __restrict__ vals, const Affine* __restrict__ table,
+                                                          Affine* __restrict__ buf_a, Affine* __restrict__ buf_b,
+                                                          Affine* __restrict__ buf_c, Fq* __restrict__ pref,
+                                                          const u32* __restrict__ n_entries_ptr, u32* __restrict__ cursor,
+                                                          int R, int k_nominal) {
+    __shared__ u32 node[8 * 2 * BA_T];  // [8][2 * BA_T]  heap order: leaves at BA_T + tid, root at 1
+    __shared__ u32 sh_start, sh_k;
+    const u32 m_entries = __ldg(n_entries_ptr);
+    const u32 npairs1 = m_entries >> 1;
+#pragma unroll 1
+    for (int it = 0;; it++) {
+        if (threadIdx.x == 0) {
+            u32 k = (u32)k_nominal;
+            // stagger: the CTAs of an SM start with tiles of different length
+            if (it == 0) k = ((k * (1u + (blockIdx.x & 3u))) >> 2) & ~3u;
+            // guided scheduling: tiles shrink towards the end so that all CTAs finish together
+            const u32 cur = *reinterpret_cast<volatile u32*>(cursor);
+            if (cur < npairs1) {
+                const u32 share = ((npairs1 - cur) / (BA_T * gridDim.x) + 3u) & ~3u;
+                if (share < k) k = share;
+            }
+            if (k < 8) k = 8;
+            sh_k = k;
+            sh_start = atomicAdd(cursor, (u32)BA_T * k);
+        }
+        __syncthreads();
+        const u32 base1 = sh_start;
+        const int k = (int)sh_k;
+        if (base1 >= npairs1) break;
+        const BaSrc<true> s1{vals, table, nullptr};
+        ba_level<true>(s1, buf_a, pref, base1, npairs1, k, node);
+        // the prefix scratch of every level stays inside the tile's own level-1 region [base1, base1 + BA_T * k)
+        if (R >= 2) {
+            const BaSrc<false> s2{nullptr, nullptr, buf_a};
+            ba_level<false>(s2, buf_b, pref + (base1 - (base1 >> 1)), base1 >> 1, m_entries >> 2, k >> 1, node);
+        }
+        if (R >= 3) {
+            const BaSrc<false> s3{nullptr, nullptr, buf_b};
+            ba_level<false>(s3, buf_c, pref + (base1 - (base1 >> 2)), base1 >> 2, m_entries >> 3, k >> 2, node);
+        }
     }
 }
 

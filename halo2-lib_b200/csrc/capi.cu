@@ -97,6 +97,13 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
         H2B_CUDA(cudaSetDevice(device));
         ctx = new h2b_ctx();
         ctx->device = device;
+        {
+            // experiment knob: the MSM gathers 64-byte table points at random; H2B_L2_FETCH=32|64|128 sets the L2 fetch
+            // granularity hint (cudaLimitMaxL2FetchGranularity)
+            const char* e = getenv("H2B_L2_FETCH");
+            const int g = e ? atoi(e) : 0;  // measured: no effect on the MSM at k = 19 (profiles/), so the driver default stays
+            if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+        }
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
@@ -160,6 +167,15 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
 
 int h2b_ctx_set_stream(h2b_ctx* ctx, void* cuda_stream) {
     return guarded(ctx, [&] { ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream; });
+}
+int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(key, "set_option: null key");
+        const std::string k(key);
+        if (k == "msm.affine_levels") { H2B_REQUIRE(value >= -1 && value <= 3, "msm.affine_levels: -1 (default) .. 3"); ctx->opt_affine_levels = (int)value; }
+        else if (k == "msm.affine_k") { H2B_REQUIRE(value == -1 || (value >= 8 && value <= 128 && value % 4 == 0), "msm.affine_k: multiple of 4 in [8, 128]"); ctx->opt_affine_k = (int)value; }
+        else H2B_REQUIRE(false, "set_option: unknown key");
+    });
 }
 int h2b_ctx_synchronize(h2b_ctx* ctx) {
     return guarded(ctx, [&] { H2B_CUDA(cudaStreamSynchronize(ctx->stream)); });

@@ -83,7 +83,8 @@ struct h2b_ctx {
     std::string err;
     uint64_t launches = 0;
     bool ntt_attr_set = false;
-    bool ba_attr_set = false;
+    int opt_affine_levels = -1;  // h2b_ctx_set_option("msm.affine_levels"): -1 = default
+    int opt_affine_k = -1;       // "msm.affine_k"
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
     bool reduce_counter_zeroed = false;
     void* reduce_counter_ptr = nullptr;

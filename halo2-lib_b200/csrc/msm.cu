@@ -568,32 +568,20 @@ void msm_build_table(h2b_ctx* ctx, const void* d_bases, size_t count, int c, int
                    t + (size_t)w * count, (u32)count, c);
 }
 
-// number of batch-affine halving passes for a table-mode MSM with `e` sorted entries per bucket on average
-static int msm_choose_levels(size_t M, size_t nb_total, int q_is_table) {
+// Number of batch-affine halving levels (batch_affine.cuh) in front of k_accumulate.  Measured on B200 (profiles/
+// r02_batch_affine.md): bit-exact, but NOT faster than the plain XYZZ accumulation at any size tried (k = 19 / 21 / 23) —
+// the warps of a CTA wait at the barrier around the single-lane inversion (ncu: barrier is the top stall, SM throughput
+// 43 % against 82 %), and the table points are gathered twice.  It therefore stays an opt-in path:
+// h2b_ctx_set_option("msm.affine_levels", 1..3) or H2B_AFF_LEVELS; default 0.
+static int msm_choose_levels(const h2b_ctx* ctx, int q_is_table) {
     static const int forced = [] {
         const char* e = getenv("H2B_AFF_LEVELS");
         return e ? atoi(e) : -1;
     }();
-    if (forced >= 0 && forced <= 4) return forced;
     if (!q_is_table) return 0;
-    const size_t e = M / (nb_total ? nb_total : 1);
-    if (e >= 40) return 3;   // groups of 8: 3.5 padding slots per bucket on >= 40 entries
-    if (e >= 14) return 2;
+    if (ctx->opt_affine_levels >= 0 && ctx->opt_affine_levels <= 3) return ctx->opt_affine_levels;
+    if (forced >= 0 && forced <= 3) return forced;
     return 0;
-}
-
-template <int K>
-static void launch_batch_affine(h2b_ctx* ctx, bool level1, const u32* vals, const Affine* table, const Affine* in, Affine* out,
-                                const u32* d_entries, int level, size_t max_pairs) {
-    const size_t smem = ((size_t)K * 8 * BA_T + 2 * BA_T * 8) * 4;
-    if (!ctx->ba_attr_set) {
-        H2B_CUDA(cudaFuncSetAttribute(k_batch_affine<true, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        H2B_CUDA(cudaFuncSetAttribute(k_batch_affine<false, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->ba_attr_set = true;
-    }
-    const unsigned grid = ceil_div(max_pairs, (size_t)BA_T * K);
-    if (level1) H2B_LAUNCH(ctx, (k_batch_affine<true, K>), grid, BA_T, smem, vals, table, in, out, d_entries, level);
-    else H2B_LAUNCH(ctx, (k_batch_affine<false, K>), grid, BA_T, smem, vals, table, in, out, d_entries, level);
 }
 
 void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out,
@@ -605,13 +593,13 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     const u32 nb_total = nsets * nbw;
     const size_t M = (size_t)W * n;
     cudaStream_t st = ctx->stream;
-    const int R = msm_choose_levels(M, nb_total, q == W);  // batch-affine halving passes; groups of G = 2^R entries
+    const int R = msm_choose_levels(ctx, q == W);  // batch-affine halving passes; groups of G = 2^R entries
     const size_t G = (size_t)1 << R;
     const size_t Mp = M + (G - 1) * nb_total;  // upper bound of the padded entry count
     H2B_REQUIRE(Mp < ((size_t)1 << 32), "msm: padded entry count exceeds 32 bits");
 
     u32* vals = (u32*)ctx->get(WS_VALS_A, Mp * 4 + 16);
-    u32* cnt = (u32*)ctx->get(WS_KEYS_A, (2 * ((size_t)nb_total + 2) + nb_total / SCAN_TILE + 4) * 4);  // histogram, cursors, tile sums, L
+    u32* cnt = (u32*)ctx->get(WS_KEYS_A, (2 * ((size_t)nb_total + 2) + nb_total / SCAN_TILE + 8) * 4);  // histogram, cursors, tile sums, L, tile cursor
     u32* hist = cnt;
     u32* cursor = cnt + nb_total + 2;
     u32* off = (u32*)ctx->get(WS_OFFSETS, ((size_t)nb_total + 2) * 4);
@@ -628,10 +616,16 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     const size_t n_chunks = L_MAX ? (Macc + l_min - 1) / l_min : std::max((Macc + l_max - 1) / l_max, (size_t)slots) + 1;
     XYZZ* partials = (XYZZ*)ctx->get(WS_PARTIALS, 2 * n_chunks * sizeof(XYZZ));
     u32* big = (u32*)ctx->get(WS_BIGLIST, ((size_t)nb_total + 1) * 4);  // [0] = counter, list follows
-    Affine* red_a = nullptr;
-    Affine* red_b = nullptr;
-    if (R >= 1) red_a = (Affine*)ctx->get(WS_RED_A, (Mp / 2) * sizeof(Affine));
-    if (R >= 2) red_b = (Affine*)ctx->get(WS_RED_B, (Mp / 4) * sizeof(Affine));
+    // batch-affine scratch: sums of levels 1..3 and the prefix products of a level (all indexed by pair)
+    Affine* red[3] = {nullptr, nullptr, nullptr};
+    Fq* red_pref = nullptr;
+    if (R >= 1) {
+        char* a = (char*)ctx->get(WS_RED_A, (Mp / 2 + Mp / 4 + Mp / 8 + 8) * sizeof(Affine));
+        red[0] = (Affine*)a;
+        red[1] = red[0] + Mp / 2;
+        red[2] = red[1] + Mp / 4;
+        red_pref = (Fq*)ctx->get(WS_RED_B, (Mp / 2 + 8) * sizeof(Fq));
+    }
 
     // counting sort by bucket: histogram -> exclusive scan -> scatter (digits are recomputed, not stored)
     H2B_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nb_total + 1) * 4, st));
@@ -648,16 +642,23 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     if (R == 0) {
         H2B_LAUNCH(ctx, k_accumulate<false>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, d_L, (const Affine*)d_table, buckets, partials, 0);
     } else {
-        // R halving passes in affine coordinates (one shared inversion per CTA), ping-ponging between two buffers
-        const u32* d_entries = off + nb_total;
-        Affine* src = nullptr;
-        Affine* dst = red_a;
-        for (int lv = 1; lv <= R; lv++) {
-            launch_batch_affine<16>(ctx, lv == 1, vals, (const Affine*)d_table, src, dst, d_entries, lv, Mp >> lv);
-            src = dst;
-            dst = (dst == red_a) ? red_b : red_a;
-        }
-        H2B_LAUNCH(ctx, k_accumulate<true>, ceil_div(n_chunks, 128), 128, 0, (const u32*)nullptr, off, nb_total, d_L, (const Affine*)src, buckets, partials, R);
+        // R halving levels in affine coordinates, one fused launch: every CTA takes its tile through all levels
+        static const int BA_K_ENV = [] {  // nominal level-1 pairs per thread and tile (H2B_BA_K: experiments)
+            const char* e = getenv("H2B_BA_K");
+            const int v = e ? atoi(e) : 32;
+            return (v >= 8 && v <= 128 && v % 4 == 0) ? v : 32;
+        }();
+        const int BA_K = (ctx->opt_affine_k >= 8 && ctx->opt_affine_k <= 128 && ctx->opt_affine_k % 4 == 0) ? ctx->opt_affine_k : BA_K_ENV;
+        static const int BA_CTAS = [] {  // persistent CTAs per SM (register-bound: 4 at 128 registers)
+            const char* e = getenv("H2B_BA_CTAS");
+            const int v = e ? atoi(e) : 4;
+            return (v >= 1 && v <= 8) ? v : 4;
+        }();
+        u32* ba_cursor = d_L + 1;
+        H2B_CUDA(cudaMemsetAsync(ba_cursor, 0, 4, st));
+        H2B_LAUNCH(ctx, k_batch_affine, ctx->sm_count * BA_CTAS, BA_T, 0, vals, (const Affine*)d_table, red[0], red[1], red[2], red_pref,
+                   off + nb_total, ba_cursor, R, BA_K);
+        H2B_LAUNCH(ctx, k_accumulate<true>, ceil_div(n_chunks, 128), 128, 0, (const u32*)nullptr, off, nb_total, d_L, (const Affine*)red[R - 1], buckets, partials, R);
     }
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, d_L, partials, buckets, big + 1, big, R);
     XYZZ* seg = (XYZZ*)ctx->get(WS_POOL, (2 * (n_chunks / BIG_SEG) + 64) * sizeof(XYZZ));

@@ -66,6 +66,10 @@ class Context:
     def synchronize(self):
         self.check(lib.h2b_ctx_synchronize(self.h))
 
+    def set_option(self, key: str, value: int):
+        """tuning / experiment switches (h2b_ctx_set_option); results never depend on them"""
+        self.check(lib.h2b_ctx_set_option(self.h, key.encode(), int(value)))
+
     @property
     def kernel_launches(self) -> int:
         return int(lib.h2b_kernel_launches(self.h))

@@ -52,6 +52,10 @@ void h2b_ctx_destroy(h2b_ctx* ctx);
  * context's own stream. */
 int h2b_ctx_set_stream(h2b_ctx* ctx, void* cuda_stream);
 int h2b_ctx_synchronize(h2b_ctx* ctx);
+/* Tuning / experiment switches (results never depend on them).  Keys:
+ *   "msm.affine_levels"  0..3 (-1 = default 0): batch-affine halving levels in front of the XYZZ bucket accumulation
+ *   "msm.affine_k"       multiple of 4 in [8, 128] (-1 = default 32): pairs per thread and tile of those levels */
+int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value);
 /* Last error message of this context (or of the failed h2b_ctx_create when ctx == NULL). */
 const char* h2b_last_error(const h2b_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */

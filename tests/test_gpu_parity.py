@@ -194,6 +194,53 @@ def test_msm_closed_form_large(ctx, h2b):
     params.close()
 
 
+@pytest.mark.parametrize("levels", [1, 2, 3])
+def test_msm_batch_affine_levels(h2b, levels):
+    """the opt-in batch-affine bucket reduction (csrc/batch_affine.cuh): groups of 2^levels sorted entries are summed in
+    affine coordinates with a shared inversion before the XYZZ accumulation.  Same group element, every edge included:
+    identity bases, repeated bases (tangent case), P + (-P) inside a bucket, hot buckets, witness-like columns."""
+    c = h2b.Context(0)
+    c.set_option("msm.affine_levels", levels)
+    c.set_option("msm.affine_k", 8 if levels == 1 else 32)
+    try:
+        rng = np.random.default_rng(900 + levels)
+        for k, dist in [(6, "uniform"), (10, "witness"), (13, "uniform")]:
+            n = 1 << k
+            B = _bases(c, n, a0=5 + k, delta=3)
+            B[3] = 0            # identity base (0,0)
+            B[11] = B[10]       # repeated base: equal points meet in one bucket
+            sc = rand_ints(rng, n, R) if dist == "uniform" else witness_like_ints(rng, n)
+            sc[10], sc[11] = 777, 777                      # P + P inside a bucket
+            sc[20], sc[21] = 424242, 424242
+            B[21, 4:] = mont([(P - v) % P for v in unmont(B[20, 4:].reshape(1, 4), P)], P)[0]  # B[21] = -B[20]: cancels
+            B[21, :4] = B[20, :4]
+            S = mont(sc, R)
+            params = h2b.ParamsKZG(c, k, g=B)
+            assert np.array_equal(norm(c, params.commit(S)), orc.msm_pippenger(S, B)), (k, dist)
+            params.close()
+        # one value for most of the column: a single bucket of thousands of entries
+        k = 13
+        n = 1 << k
+        B = _bases(c, n, a0=2, delta=3)
+        S = mont([1] * (n - 100) + rand_ints(rng, 100, R), R)
+        params = h2b.ParamsKZG(c, k, g=B)
+        assert np.array_equal(norm(c, params.commit(S)), orc.msm_pippenger(S, B))
+        # all-zero column and a column of one repeated base with one repeated scalar
+        assert jac_limbs_to_affine(norm(c, params.commit(np.zeros((n, 4), dtype=np.uint64)))) is None
+        params.close()
+        Beq = np.repeat(B[:1], 512, axis=0)
+        Seq = mont([123456789] * 512, R)
+        params = h2b.ParamsKZG(c, 9, g=Beq)
+        assert np.array_equal(norm(c, params.commit(Seq)), orc.msm_pippenger(Seq, Beq))
+        params.close()
+        with pytest.raises(h2b.H2BError):
+            c.set_option("msm.affine_levels", 9)
+        with pytest.raises(h2b.H2BError):
+            c.set_option("no.such.option", 1)
+    finally:
+        c.close()
+
+
 # ------------------------------------------------------------------ L2: NTT
 @pytest.mark.parametrize("k", [0, 1, 2, 3, 5, 8, 10, 11, 12, 13, 16, 20, 21])
 def test_ntt_vs_oracle(ctx, h2b, k):
