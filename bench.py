@@ -746,6 +746,44 @@ class Workload:
             self.outs_host[phase] = out
             self._mark("phase%d" % pi)
 
+    # -------------------------------------------------------------------------------------------- resident prover (e2e)
+    def setup_prover(self):
+        """the resident prover path (halo2-lib_b200/prover.py): a SATISFIED synthetic halo2-base circuit of this shape; host
+        side = pinned witness cells + pinned random polynomial, everything else lives behind h2b_poly handles"""
+        rig, s = self.rig, self.s
+        torch, h = rig.torch, rig.h
+        assert s.A == 1 and s.L == 0 and s.n_lk == 1, "the resident prover session covers the 1 advice / q_lookup / 1 fixed shape"
+        rng = np.random.default_rng(0xB2002000 + s.k)
+        a, fixed, sigma, usable = h.synthetic_circuit(rig.ctx, s.k, rng)
+        self.pr_circuit = h.Circuit(rig.ctx, s.k, fixed, sigma)
+        self.pr_session = h.ProverSession(rig.ctx, self.params, self.pr_circuit)
+        if rig.world > 1:
+            self.pr_session.shard(self.begin, self.n_loc, lambda ptr, m: h.allreduce_points(rig.ctx, ptr, m))
+        self.pr_witness = torch.from_numpy(np.ascontiguousarray(a[:usable]).view(np.int64)).pin_memory()
+        self.pr_random = torch.from_numpy(uniform_residues(rng, s.n).view(np.int64)).pin_memory()
+        self.pr_usable = usable
+        self.pr_last = None
+
+    def step_e2e_prover(self):
+        self.pr_last = self.pr_session.prove(self.pr_witness.data_ptr(), self.pr_usable, self.pr_random.data_ptr(), seed=1)
+
+    def verify_prover(self) -> dict:
+        """one untimed proof with the committed polynomials kept: every commitment against the closed form of its
+        polynomial, and the quotient identity at the challenge point (tests/prover_check.py, Python integers)"""
+        import prover_check as pc
+        s, sess = self.s, self.pr_session
+        sess.keep = {}
+        res = sess.prove(self.pr_witness.data_ptr(), self.pr_usable, self.pr_random.data_ptr(), seed=1)
+        kept, sess.keep = sess.keep["committed"], None
+        ok = 0
+        for cm, (basis, poly) in zip(res["commitments"], kept):
+            a0, d = BASES["monomial" if basis == 0 else "lagrange"]
+            scalar = progression_dot(poly, a0, d, 0) * MONT_RINV_R % R_MOD
+            ok += 1 if point_matches(cm, ec_mul_g(scalar)) else 0
+        left, right = pc.quotient_identity(res, s.k, self.pr_circuit.bf)
+        return {"commitments": ok, "of": len(kept), "quotient_identity": left == right,
+                "h2d_bytes": res["h2d_bytes"], "d2h_bytes": res["d2h_bytes"]}
+
     # -------------------------------------------------------------------------------------------- verification
     def verify_commitments(self, arr) -> int:
         """number of the schedule's commitments in `arr` (len(msm) x 12 limbs) that equal the closed form"""
@@ -781,6 +819,9 @@ class Workload:
     def close(self):
         if self.side_pool:
             self.side_pool.shutdown()
+        if getattr(self, "pr_session", None) is not None:
+            self.pr_session.free()
+            self.pr_circuit.free()
         self.params.close()
 
 
@@ -818,7 +859,14 @@ def run_b200(args):
     ms_step, launches, ms_step_seq = res["ms_per_step"], res["gpu_launches"], res["ms_per_step_seq"]
     acc_ms, acc_cnt = res["acc"]
 
-    # ---- end to end through the host-pointer ABI
+    # ---- end to end (the headline): the resident prover path — witness cells and the random polynomial go up from pinned
+    # host memory, commitments and evaluations come down, every column stays in HBM behind h2b_poly handles in between,
+    # and the step contains the quotient / product-column / opening work create_proof does between the commitments
+    wl.setup_prover()
+    ms_e2e, e2e_launches = rig.timed(wl.step_e2e_prover, max(1, min(args.steps, 10)), 2)
+    torch.cuda.synchronize()
+    prover_check = wl.verify_prover()
+    # ---- the round-1 end-to-end path for continuity: every call takes and returns HOST buffers (h2b_* without _dev)
     if os.environ.get("H2B_E2E_TRACE"):
         wl.trace = []
     ms_e2e_ovl, _ = rig.timed(wl.step_e2e, max(1, min(args.steps, 5)), 1)
@@ -831,7 +879,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         t0 = wl.trace[0][1]
         print("e2e trace (ms since start): " + ", ".join("%s=%.2f" % (l, 1e3 * (t - t0)) for l, t in wl.trace[1:]), file=sys.stderr)
-    ms_e2e = min(ms_e2e_ovl, ms_e2e_seq)
+    ms_e2e_host = min(ms_e2e_ovl, ms_e2e_seq)
     ntt_check = wl.verify_ntt()
 
     # per-op device timings (context for the headline; same CUDA-event method, 3 reps each)
@@ -900,10 +948,12 @@ def run_b200(args):
                 pass
 
     ok_all = (res["verified_resident"] == len(sched.msm) and verified_e2e == len(sched.msm)
+              and prover_check["commitments"] == prover_check["of"] and prover_check["quotient_identity"]
               and all(v for kk, v in ntt_check.items() if kk != "points_checked")
               and all(v.get("verified", {}).get("ok", False) for v in sweep.values()))
     ok_all = rig.all_true(ok_all)
-    verified = {"msm": res["verified_resident"], "msm_e2e": verified_e2e, "of": len(sched.msm), "ntt": ntt_check,
+    verified = {"msm": res["verified_resident"], "msm_e2e": prover_check["commitments"], "msm_e2e_host_buffers": verified_e2e, "of": len(sched.msm),
+                "e2e_quotient_identity": prover_check["quotient_identity"], "ntt": ntt_check,
                 "sweep_ok": {kk: v.get("verified", {}).get("ok", False) for kk, v in sweep.items()},
                 "method": "closed form sum_i s_i*(a0+d*i)*G with Python integers (bases are that progression), after the all-reduce at N>1; Horner evaluations for the transforms",
                 "all_ranks_ok": ok_all}
@@ -953,10 +1003,13 @@ def run_b200(args):
         "msm_window_bits": window_bits, "msm_windows": windows,
         "op_ms": op_ms,
         "e2e": {"value": sched.pairs / (ms_e2e / 1e3), "unit": "G1 pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": prover_check["h2d_bytes"], "d2h_bytes_per_step": prover_check["d2h_bytes"], "gpu_launches": e2e_launches,
+                "path": "halo2_lib_b200.ProverSession.prove (h2b_poly handles): pinned witness cells + random polynomial up, 12 commitments + 26 evaluations down; assignment, q_lookup*a, permute_expression_pair, permutation / lookup product columns, 5 x (lagrange_to_coeff + coeff_to_extended), gate + permutation + lookup terms folded on the extended coset, divide_by_vanishing_poly, extended_to_coeff, h pieces, evaluations, SHPLONK-shaped linear combinations and kate divisions all on the device; host: Blake2b transcript + blinding scalars; one synchronisation per commitment phase"},
+        "e2e_host_buffers": {"value": sched.pairs / (ms_e2e_host / 1e3), "unit": "G1 pairs/s", "ms_per_step": ms_e2e_host,
                 "ms_per_step_overlapped": ms_e2e_ovl, "ms_per_step_sequential_calls": ms_e2e_seq,
                 "reported": "overlapped" if ms_e2e_ovl <= ms_e2e_seq else "sequential_calls",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "path": "h2b_assign_columns / h2b_msm_g1_batch_reduced / h2b_lagrange_to_coeff_and_extended_batch / h2b_extended_to_coeff with pinned host buffers; transforms driven by a second host thread + context beside the commitment phases (dependency model of step_resident); the faster of the overlapped and the strictly sequential call order is reported"},
+                "path": "round-1 path kept for continuity: h2b_assign_columns / h2b_msm_g1_batch_reduced / h2b_lagrange_to_coeff_and_extended_batch / h2b_extended_to_coeff, every call with pinned HOST buffers in and out (no quotient work); transforms driven by a second host thread + context; the faster of the overlapped and the strictly sequential call order is reported"},
         "gpu_launches": launches,
         "verified": verified,
         "clocks": clocks,

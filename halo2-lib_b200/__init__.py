@@ -28,3 +28,4 @@ from .evaluation import (  # noqa: F401,E402
     poly_lincomb,
     permute_expression_pair,
 )
+from .prover import Poly, Transcript, Circuit, ProverSession, synthetic_circuit  # noqa: F401,E402

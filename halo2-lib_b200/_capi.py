@@ -119,6 +119,17 @@ SIGNATURES = {
     "h2b_kate_division_dev": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "h2b_poly_lincomb": (_int, [_vp, _vpp, _vp, _sz, _sz, _vp]),
     "h2b_poly_lincomb_dev": (_int, [_vp, _vpp, _vp, _sz, _sz, _vp]),
+    "h2b_poly_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
+    "h2b_poly_free": (None, [_vp, _vp]),
+    "h2b_poly_device_ptr": (_vp, [_vp]),
+    "h2b_poly_len": (_sz, [_vp]),
+    "h2b_poly_zero": (_int, [_vp, _vp]),
+    "h2b_poly_upload": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "h2b_poly_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "h2b_permutation_product_dev": (_int, [_vp, _vpp, _vpp, _sz, _sz, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "h2b_lookup_product_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "h2b_fr_mul_elementwise_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "h2b_eval_polynomial_batch_dev": (_int, [_vp, _vpp, _vp, _sz, _sz, _vp]),
     "h2b_test_field_op": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp]),
 }
 

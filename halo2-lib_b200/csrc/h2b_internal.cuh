@@ -63,6 +63,7 @@ enum WsSlot {
     WS_MISC2,
     WS_RED_A,         // batch-affine group sums (ping)
     WS_RED_B,         // batch-affine group sums (pong)
+    WS_PROD,          // product-column scratch (numerators, denominators, power tables)
     WS_COUNT
 };
 
@@ -102,7 +103,7 @@ struct h2b_ctx {
     cudaEvent_t fork_ev = nullptr;
     int cur_lane = 0;  // workspace set used by get()
     Buf ws[NLANES][h2b::WS_COUNT];
-    Buf pinned[2];
+    Buf pinned[3];
     std::map<std::array<uint64_t, 5>, h2b::NttPlan*> ntt_plans;
 
     // optional per-kernel device timing (h2b_profile_*): event pairs around launches whose name matches
@@ -210,7 +211,15 @@ void kate_division_run(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t z
 void poly_lincomb_run(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* scalars, size_t m, size_t n, void* d_out);
 // ---- scan.cu
 void batch_invert_run(h2b_ctx* ctx, void* d_a, size_t n);
-void grand_product_run(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z);
+// d_start != nullptr: the seed is read from device memory (the previous permutation set's closing value) instead of `start`
+void grand_product_run(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z, const void* d_start = nullptr);
 void eval_rational_batched_run(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
+// ---- prover.cu
+void permutation_product_run(h2b_ctx* ctx, const void* const* d_columns, const void* const* d_sigma, size_t n_cols, size_t first_col,
+                             const uint64_t beta[4], const uint64_t gamma[4], uint32_t k, uint32_t blinding_factors,
+                             const void* d_start, void* d_z);
+void lookup_product_run(h2b_ctx* ctx, const void* d_in, const void* d_tab, const void* d_pin, const void* d_ptab, const uint64_t beta[4],
+                        const uint64_t gamma[4], uint32_t k, uint32_t blinding_factors, void* d_z);
+void fr_mul_elementwise_run(h2b_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* d_out);
 
 }  // namespace h2b

@@ -542,15 +542,19 @@ int msm_choose_c_fixed(size_t n) {
         int v = atoi(e);
         if (v >= 4 && v <= 24) return v;
     }
-    // W = ceil(255 / c) only drops at c = 13, 14, 15, 16, 17, 19, 20, 22; measured on B200 (tools/prof_ops.py):
-    // 2^19: c = 17 (W = 15) beats 16 / 19 / 20; 2^21 and 2^23: c = 20 (W = 13) beats 17 / 19 / 21 / 22
-    // (the bucket-side work grows 2^c while the additions only shrink with W).
-    int lg = ceil_log2(n ? n : 1);
-    int c = lg - 2;
-    if (c < 8) c = 8;
-    if (lg >= 21) c = 20;
-    else if (c > 17) c = 17;
-    return c;
+    // W = ceil(255 / c) only drops at c = 13, 14, 15, 16, 17, 19, 20, 22; measured on B200 (tools/prof_ops.py,
+    // profiles/r02_window_sweep.txt): 2^19: c = 17 (W = 15) beats 16 / 19 / 20; 2^21 and 2^23: c = 20 (W = 13) beats
+    // 17 / 19 / 21 / 22 (the bucket-side work grows 2^c while the additions only shrink with W).  Small domains — the
+    // shards of a multi-GPU run and the k <= 16 configs — want c close to log2(n): the fixed tail is latency-bound and
+    // hardly grows with the bucket count, while fewer table levels shorten everything else (2^15: c = 15 runs in 402 us,
+    // the former c = 13 in 689 us; 2^16: 523 vs 646 us).
+    const int lg = ceil_log2(n ? n : 1);
+    if (lg >= 21) return 20;
+    if (lg >= 17) return 17;
+    if (lg == 16) return 16;
+    if (lg >= 13) return 15;
+    if (lg >= 11) return 13;
+    return lg < 8 ? 8 : lg;
 }
 static int msm_choose_c_adhoc(size_t n) {
     int lg = ceil_log2(n ? n : 1);

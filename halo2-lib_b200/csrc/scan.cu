@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(256) k_gp_tiles(const uint64_t* __restrict__ f
 }
 // exclusive prefix over the tile totals, seeded with `start`: tile_base[j] = start * prod_{j' < j} tile_prod[j']
 __global__ void __launch_bounds__(256) k_gp_scan(const uint64_t* __restrict__ tile_prod, u32 ntiles, Fr start,
-                                                 uint64_t* __restrict__ tile_base) {
+                                                 uint64_t* __restrict__ tile_base, const uint64_t* __restrict__ d_start) {
     __shared__ Fr sh[256];
+    if (d_start) start = Fr::load(d_start);
     const u32 per = (ntiles + 255) / 256;
     const u32 lo = min(threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
     Fr p = Fr::one();
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) k_gp_apply(const uint64_t* __restrict__ f
 }
 
 // z[0] = start, z[i] = z[i-1] * f[i-1], i < n  (f[n-1] is not used, as in halo2)
-void grand_product_run(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z) {
+void grand_product_run(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], size_t n, void* d_z, const void* d_start) {
     if (n == 0) return;
     const size_t n_f = n - 1;
     const u32 ntiles = (u32)((n + GP_TILE - 1) / GP_TILE);
@@ -166,7 +167,7 @@ void grand_product_run(h2b_ctx* ctx, const void* d_f, const uint64_t start[4], s
     Fr s;
     memcpy(&s, start, sizeof(Fr));
     H2B_LAUNCH(ctx, k_gp_tiles, ntiles, 256, 0, (const uint64_t*)d_f, n_f, tp);
-    H2B_LAUNCH(ctx, k_gp_scan, 1, 256, 0, tp, ntiles, s, tb);
+    H2B_LAUNCH(ctx, k_gp_scan, 1, 256, 0, tp, ntiles, s, tb, (const uint64_t*)d_start);
     H2B_LAUNCH(ctx, k_gp_apply, ntiles, 256, 0, (const uint64_t*)d_f, n_f, tb, (uint64_t*)d_z, n);
 }
 

@@ -334,6 +334,39 @@ int h2b_kate_division_dev(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_
 int h2b_poly_lincomb(h2b_ctx* ctx, const uint64_t* const* polys, const uint64_t* scalars, size_t m, size_t n, uint64_t* out);
 int h2b_poly_lincomb_dev(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* scalars, size_t m, size_t n, void* d_out);
 
+/* ---- device-resident polynomials (the resident prover path): a column / polynomial of Fr elements that stays in HBM between
+ * the calls of one proof — assigned by h2b_assign_columns_dev, committed by h2b_msm_g1_dev, transformed by the `_dev`
+ * NTT entry points, consumed by the quotient kernels — so that only commitments, evaluations and blinding scalars cross
+ * PCIe.  Replaces the host-side `Polynomial<Fr, _>` vectors of halo2-axiom 0.5.3 plonk/prover.rs (not vendored).
+ * h2b_poly_device_ptr() is what every `_dev` entry point takes; offsets / lengths are in elements. */
+typedef struct h2b_poly h2b_poly;
+int h2b_poly_alloc(h2b_ctx* ctx, size_t n_elems, h2b_poly** out); /* zero-filled */
+void h2b_poly_free(h2b_ctx* ctx, h2b_poly* poly);
+void* h2b_poly_device_ptr(const h2b_poly* poly);
+size_t h2b_poly_len(const h2b_poly* poly);
+int h2b_poly_zero(h2b_ctx* ctx, h2b_poly* poly);                                                      /* asynchronous */
+int h2b_poly_upload(h2b_ctx* ctx, h2b_poly* poly, size_t offset, const uint64_t* host, size_t n);     /* blocking */
+int h2b_poly_download(h2b_ctx* ctx, const h2b_poly* poly, size_t offset, uint64_t* host, size_t n);   /* blocking */
+
+/* ---- product columns of the permutation and lookup arguments (create_proof step 4), built on the device:
+ * row factors -> one batched inversion -> prefix products.  u = 2^k - (blinding_factors + 1) usable rows; z[0] = start,
+ * z[i + 1] = z[i] * f_i for i < u, z[i] = z[u] above (the caller overwrites rows > u with its blinding scalars).
+ * permutation set of n_cols <= 8 columns whose first column has index `first_col` in the permutation's column order:
+ *   f_i = prod_j (v_j(i) + beta delta^(first_col + j) omega^i + gamma) / prod_j (v_j(i) + beta sigma_j(i) + gamma);
+ *   d_start = NULL for the first set, else a device pointer to the previous set's z[u] (halo2 chains the sets).
+ * lookup: f_i = (input_i + beta)(table_i + gamma) / ((permuted_input_i + beta)(permuted_table_i + gamma)). */
+int h2b_permutation_product_dev(h2b_ctx* ctx, const void* const* d_columns, const void* const* d_sigma, size_t n_cols,
+                                size_t first_col, const uint64_t beta[4], const uint64_t gamma[4], uint32_t k,
+                                uint32_t blinding_factors, const void* d_start, void* d_z);
+int h2b_lookup_product_dev(h2b_ctx* ctx, const void* d_input, const void* d_table, const void* d_permuted_input,
+                           const void* d_permuted_table, const uint64_t beta[4], const uint64_t gamma[4], uint32_t k,
+                           uint32_t blinding_factors, void* d_z);
+/* out[i] = a[i] * b[i] (out may alias a): compressed lookup input q * a of halo2-base/src/gates/range/mod.rs:131-140 */
+int h2b_fr_mul_elementwise_dev(h2b_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* d_out);
+/* out[j] = polys[j](xs[j]) for m device polynomials of n coefficients; xs, out: host, m x 4 limbs (one synchronisation) */
+int h2b_eval_polynomial_batch_dev(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* xs, size_t m, size_t n,
+                                  uint64_t* out);
+
 /* ---- test hooks (field arithmetic of the kernels, element-wise on the device) --------------------- */
 /* field: 0 = Fq, 1 = Fr; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 from_mont(a), 5 to_mont(a), 6 sqr(a),
  * 7 a*b + (a+b)(a-b) and 8 a*b - b*b through the fused two-product Montgomery routine of the group law,
