@@ -44,6 +44,9 @@ SIGNATURES = {
     "h2b_ctx_destroy": (None, [_vp]),
     "h2b_ctx_set_stream": (_int, [_vp, _vp]),
     "h2b_ctx_synchronize": (_int, [_vp]),
+    "h2b_ctx_side_begin": (_int, [_vp]),
+    "h2b_ctx_side_end": (_int, [_vp]),
+    "h2b_ctx_side_join": (_int, [_vp]),
     "h2b_ctx_set_option": (_int, [_vp, C.c_char_p, C.c_int64]),
     "h2b_last_error": (C.c_char_p, [_vp]),
     "h2b_kernel_launches": (C.c_uint64, [_vp]),
@@ -124,6 +127,8 @@ SIGNATURES = {
     "h2b_poly_device_ptr": (_vp, [_vp]),
     "h2b_poly_len": (_sz, [_vp]),
     "h2b_poly_zero": (_int, [_vp, _vp]),
+    "h2b_poly_upload_async": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "h2b_poly_copy_dev": (_int, [_vp, _vp, _vp, _sz]),
     "h2b_poly_upload": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "h2b_poly_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "h2b_permutation_product_dev": (_int, [_vp, _vpp, _vpp, _sz, _sz, _vp, _vp, _u32, _u32, _vp, _vp]),

@@ -107,6 +107,8 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+        H2B_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->side_ev) H2B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& row : ctx->pipe_ev)
             for (auto& e : row) H2B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& ev : ctx->ev) H2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -159,6 +161,9 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    for (auto& e : ctx->side_ev)
+        if (e) cudaEventDestroy(e);
     for (auto& row : ctx->pipe_ev)
         for (auto& e : row)
             if (e) cudaEventDestroy(e);
@@ -166,7 +171,36 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
 }
 
 int h2b_ctx_set_stream(h2b_ctx* ctx, void* cuda_stream) {
-    return guarded(ctx, [&] { ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream; });
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(!ctx->side_saved, "set_stream: not while the side stream is current");
+        ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    });
+}
+int h2b_ctx_side_begin(h2b_ctx* ctx) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(!ctx->side_saved, "side_begin: the side stream is already current");
+        H2B_CUDA(cudaEventRecord(ctx->side_ev[0], ctx->stream));
+        H2B_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[0], 0));
+        ctx->side_saved = ctx->stream;
+        ctx->stream = ctx->side_stream;
+        ctx->side_saved_lane = ctx->cur_lane;
+        ctx->cur_lane = 1;  // own scratch buffers: the two queues never share a workspace slot
+    });
+}
+int h2b_ctx_side_end(h2b_ctx* ctx) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(ctx->side_saved, "side_end: the side stream is not current");
+        ctx->stream = ctx->side_saved;
+        ctx->side_saved = nullptr;
+        ctx->cur_lane = ctx->side_saved_lane;
+    });
+}
+int h2b_ctx_side_join(h2b_ctx* ctx) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(!ctx->side_saved, "side_join: call h2b_ctx_side_end first");
+        H2B_CUDA(cudaEventRecord(ctx->side_ev[1], ctx->side_stream));
+        H2B_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->side_ev[1], 0));
+    });
 }
 int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value) {
     return guarded(ctx, [&] {

@@ -77,6 +77,10 @@ struct h2b_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t copy_stream2 = nullptr;  // device-to-host leg of the pipelined batch NTT entry points
+    cudaStream_t side_stream = nullptr;   // h2b_ctx_side_begin / _end / _join: work that runs beside the main stream
+    cudaStream_t side_saved = nullptr;    // the main stream while the side stream is current
+    int side_saved_lane = 0;              // the side queue works in the workspace set of lane 1 (its own scratch buffers)
+    cudaEvent_t side_ev[2] = {nullptr, nullptr};
     cudaEvent_t pipe_ev[3][3] = {};       // [buffer][uploaded, computed, downloaded]
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
@@ -207,6 +211,7 @@ void srs_setup_run(h2b_ctx* ctx, const uint64_t tau[4], const uint64_t base_xy[8
 size_t g1_count_off_curve_run(h2b_ctx* ctx, const void* d_points, size_t n);
 // ---- poly.cu
 void eval_polynomial_run(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t x[4], void* d_out);
+void eval_polynomial_batch_run(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* xs, size_t m, size_t n, void* d_out);
 void kate_division_run(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t z[4], void* d_q);
 void poly_lincomb_run(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* scalars, size_t m, size_t n, void* d_out);
 // ---- scan.cu

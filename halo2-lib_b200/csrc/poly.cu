@@ -149,6 +149,79 @@ void kate_division_run(h2b_ctx* ctx, const void* d_a, size_t n, const uint64_t z
     H2B_LAUNCH(ctx, k_pd_apply, ntiles, 256, 0, (const uint64_t*)d_a, n, pw, carry, (uint64_t*)d_q);
 }
 
+// ---------------------------------------------------------------- batched evaluation
+// m (polynomial, point) pairs in three launches: blockIdx.y selects the pair.  The evaluations create_proof writes after
+// the challenge x are ~25 Horner sums over 2^k coefficients each; one at a time they are latency-bound (three small
+// launches per evaluation).
+struct EvalBatch {
+    const uint64_t* const* polys;  // device array of m pointers
+    const uint64_t* xs;            // device, m x 4
+};
+__global__ void k_pow2_table_batch(EvalBatch b, uint64_t* __restrict__ pw /* m x 12 x 4 */) {
+    if (threadIdx.x) return;
+    Fr x = Fr::load(b.xs + 4 * (size_t)blockIdx.x);
+    uint64_t* o = pw + 48 * (size_t)blockIdx.x;
+    for (int j = 0; j < 12; j++) {
+        x.store(o + 4 * j);
+        x = x.sqr();
+    }
+}
+__global__ void __launch_bounds__(256) k_pd_tiles_batch(EvalBatch b, size_t n, u32 ntiles, const uint64_t* __restrict__ pw,
+                                                        uint64_t* __restrict__ tile_val /* m x ntiles x 4 */) {
+    __shared__ Fr sh[256];
+    const uint64_t* a = b.polys[blockIdx.y];
+    const uint64_t* mypw = pw + 48 * (size_t)blockIdx.y;
+    const size_t base = (size_t)blockIdx.x * PD_TILE + (size_t)threadIdx.x * 8;
+    Fr v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = (base + j < n) ? Fr::load_nc(a + 4 * (base + j)) : Fr::zero();
+    const Fr x = Fr::load_nc(mypw), x8 = Fr::load_nc(mypw + 4 * 3);
+    Fr d = block_suffix_affine(chunk_value(v, x), x8, sh);
+    if (threadIdx.x == 0) d.store(tile_val + 4 * ((size_t)blockIdx.y * ntiles + blockIdx.x));
+}
+// one CTA per pair: Horner over the tile values with x^2048 (ntiles is at most a few thousand)
+__global__ void __launch_bounds__(256) k_pd_scan_batch(const uint64_t* __restrict__ tile_val, u32 ntiles, const uint64_t* __restrict__ pw,
+                                                       uint64_t* __restrict__ out /* m x 4 */) {
+    __shared__ Fr sh[256];
+    const uint64_t* tv = tile_val + 4 * (size_t)blockIdx.x * ntiles;
+    const uint64_t* mypw = pw + 48 * (size_t)blockIdx.x;
+    const u32 per = (ntiles + 255) / 256;
+    const u32 lo = min(threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
+    const Fr xt = Fr::load_nc(mypw + 4 * 11);  // x^2048
+    Fr c = Fr::zero();
+    for (u32 j = hi; j > lo; j--) c = c * xt + Fr::load_nc(tv + 4 * (size_t)(j - 1));
+    Fr w = Fr::one(), sq = xt;
+    for (u32 e = per; e; e >>= 1) {
+        if (e & 1) w = w * sq;
+        sq = sq.sqr();
+    }
+    Fr d = block_suffix_affine(c, w, sh);
+    if (threadIdx.x == 0) d.store(out + 4 * (size_t)blockIdx.x);
+}
+
+// d_polys: host array of m device pointers; xs: host, m x 4; d_out: device, m x 4
+void eval_polynomial_batch_run(h2b_ctx* ctx, const void* const* d_polys, const uint64_t* xs, size_t m, size_t n, void* d_out) {
+    if (m == 0) return;
+    if (n == 0) {
+        H2B_CUDA(cudaMemsetAsync(d_out, 0, m * 32, ctx->stream));
+        return;
+    }
+    const u32 ntiles = (u32)((n + PD_TILE - 1) / PD_TILE);
+    // staging block: [pointers m x 8 | points m x 32], then device scratch: pow tables m x 12 x 32, tile values m x ntiles x 32
+    const size_t head = ((m * 8 + 31) & ~(size_t)31), in_bytes = head + m * 32;
+    char* h_in = (char*)ctx->get_pinned(1, in_bytes < 4096 ? 4096 : in_bytes);
+    memcpy(h_in, d_polys, m * 8);
+    memcpy(h_in + head, xs, m * 32);
+    char* ws = (char*)ctx->get(WS_MISC2, in_bytes + m * 12 * 32 + (size_t)m * ntiles * 32 + 64);
+    H2B_CUDA(cudaMemcpyAsync(ws, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    EvalBatch b{(const uint64_t* const*)ws, (const uint64_t*)(ws + head)};
+    uint64_t* pw = (uint64_t*)(ws + ((in_bytes + 31) & ~(size_t)31));
+    uint64_t* tv = pw + 48 * m;
+    H2B_LAUNCH(ctx, k_pow2_table_batch, (unsigned)m, 32, 0, b, pw);
+    H2B_LAUNCH(ctx, k_pd_tiles_batch, dim3(ntiles, (unsigned)m), 256, 0, b, n, ntiles, pw, tv);
+    H2B_LAUNCH(ctx, k_pd_scan_batch, (unsigned)m, 256, 0, tv, ntiles, pw, (uint64_t*)d_out);
+}
+
 // ---------------------------------------------------------------- linear combination
 struct LincombArgs {
     const uint64_t* polys[32];

@@ -246,6 +246,19 @@ int h2b_poly_upload(h2b_ctx* ctx, h2b_poly* poly, size_t offset, const uint64_t*
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffer is the caller's again on return
     });
 }
+int h2b_poly_upload_async(h2b_ctx* ctx, h2b_poly* poly, size_t offset, const uint64_t* pinned_host, size_t n) {
+    return guarded_p(ctx, [&] {
+        H2B_REQUIRE(poly && (pinned_host || n == 0), "poly_upload_async: null pointer");
+        H2B_REQUIRE(offset <= poly->n && n <= poly->n - offset, "poly_upload_async: range outside the polynomial");
+        if (n) H2B_CUDA(cudaMemcpyAsync((char*)poly->p + offset * 32, pinned_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    });
+}
+int h2b_poly_copy_dev(h2b_ctx* ctx, void* d_dst, const void* d_src, size_t n) {
+    return guarded_p(ctx, [&] {
+        H2B_REQUIRE((d_dst && d_src) || n == 0, "poly_copy: null pointer");
+        if (n) H2B_CUDA(cudaMemcpyAsync(d_dst, d_src, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    });
+}
 int h2b_poly_zero(h2b_ctx* ctx, h2b_poly* poly) {
     return guarded_p(ctx, [&] {
         H2B_REQUIRE(poly, "poly_zero: null pointer");
@@ -290,10 +303,8 @@ int h2b_eval_polynomial_batch_dev(h2b_ctx* ctx, const void* const* d_polys, cons
         if (m == 0) return;
         H2B_REQUIRE(m <= 4096, "eval_polynomial_batch: at most 4096 evaluations per call");
         char* d_out = (char*)ctx->get(WS_OUT, m * 32);
-        for (size_t j = 0; j < m; j++) {
-            H2B_REQUIRE(d_polys[j] || n == 0, "eval_polynomial_batch: null polynomial");
-            eval_polynomial_run(ctx, d_polys[j], n, xs + 4 * j, d_out + 32 * j);
-        }
+        for (size_t j = 0; j < m; j++) H2B_REQUIRE(d_polys[j] || n == 0, "eval_polynomial_batch: null polynomial");
+        eval_polynomial_batch_run(ctx, d_polys, xs, m, n, d_out);
         uint64_t* bounce = (uint64_t*)ctx->get_pinned(2, m * 32 < 4096 ? 4096 : m * 32);
         H2B_CUDA(cudaMemcpyAsync(bounce, d_out, m * 32, cudaMemcpyDeviceToHost, ctx->stream));
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -202,7 +202,10 @@ class ProverSession:
         self.zp, self.zl, self.rnd = P(n), P(n), P(n)   # product columns, random polynomial
         self.ext = {name: P(ne) for name in ("a", "pa", "ps", "zp", "zl")}
         self.h = P(ne)                                  # quotient values, then its coefficients (d - 1 pieces of n)
+        # coefficient forms (the Lagrange forms stay alive for the product columns / the commitments running beside)
+        self.ac, self.pac, self.psc, self.zpc, self.zlc = P(n), P(n), P(n), P(n), P(n)
         self.tmp = [P(n) for _ in range(4)]
+        self.tmp_side = [P(n) for _ in range(3)]
         self.d_out = Poly(ctx, 16)                      # commitments of a phase: up to 4 x 12 limbs (12 elements of 32 B)
         self.h2d_bytes = self.d2h_bytes = 0
         self.begin, self.n_loc, self.allreduce = 0, n, None
@@ -236,7 +239,7 @@ class ProverSession:
 
     def _raw_download(self, dev_ptr: int, arr: np.ndarray):
         """device pointer inside one of the session's polynomials -> host (verification only)"""
-        for p in [self.a, self.pa, self.ps, self.zp, self.zl, self.rnd, self.h] + self.tmp:
+        for p in [self.a, self.pa, self.ps, self.zp, self.zl, self.rnd, self.h, self.ac, self.pac, self.psc, self.zpc, self.zlc] + self.tmp + self.tmp_side:
             if p.ptr <= dev_ptr < p.ptr + 32 * p.n:
                 self.ctx.check(lib.h2b_poly_download(self.ctx.h, p.h, (dev_ptr - p.ptr) // 32, C.c_void_p(arr.ctypes.data), len(arr)))
                 return
@@ -257,14 +260,41 @@ class ProverSession:
         tr = Transcript()
         self.h2d_bytes = self.d2h_bytes = 0
         res = {"commitments": []}
-        # ---- phase 0: witness up, assignment, advice commitment
+        import os, time
+        trace = [] if os.environ.get("H2B_PROVER_TRACE") else None
+
+        def mark(label):  # diagnostic: wall clock per phase with a full synchronisation (changes the overlap: not for timing runs)
+            if trace is not None:
+                ctx.synchronize()
+                trace.append((label, time.perf_counter()))
+        mark("start")
+        def side_transforms(pairs):
+            """beside the main queue: copy Lagrange -> coefficient buffer, lagrange_to_coeff, coeff_to_extended"""
+            ctx.check(lib.h2b_ctx_side_begin(ctx.h))
+            try:
+                for src, dst, name in pairs:
+                    if src is not dst:
+                        ctx.check(lib.h2b_poly_copy_dev(ctx.h, vp(dst.ptr), vp(src.ptr), n))
+                    ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(dst.ptr), k))
+                    ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(dst.ptr), n, ext_k, vp(self.ext[name].ptr)))
+            finally:
+                ctx.check(lib.h2b_ctx_side_end(ctx.h))
+
+        # ---- phase 0: witness up, assignment, advice commitment (the random polynomial goes up beside it)
         self.v.upload_ptr(witness_ptr, n_cells)
         self.h2d_bytes += n_cells * 32
+        ctx.check(lib.h2b_ctx_side_begin(ctx.h))
+        ctx.check(lib.h2b_poly_upload_async(ctx.h, self.rnd.h, 0, vp(random_poly_ptr), n))
+        ctx.check(lib.h2b_ctx_side_end(ctx.h))
+        self.h2d_bytes += n * 32
         ctx.check(lib.h2b_assign_columns_dev(ctx.h, vp(self.v.ptr), n_cells, None, 0, k, 1, vp(self.a.ptr)))
         self._blind(self.a, u, rng)
         cm = self._commit([(BASIS_LAGRANGE, self.a.ptr)])
         res["commitments"] += list(cm); tr.absorb(cm)
         theta = tr.squeeze()
+        mark("phase0 advice")
+        ctx.check(lib.h2b_ctx_side_join(ctx.h))  # the random polynomial arrived while phase 0 ran
+        side_transforms([(self.a, self.ac, "a")])
         # ---- lookup: compressed input q_lookup * a, permuted pair
         ctx.check(lib.h2b_fr_mul_elementwise_dev(ctx.h, vp(cs.lagr["q_lookup"].ptr), vp(self.a.ptr), n, vp(self.inp.ptr)))
         ctx.check(lib.h2b_permute_expression_pair_dev(ctx.h, vp(self.inp.ptr), vp(cs.lagr["table"].ptr), k, bf, vp(self.pa.ptr), vp(self.ps.ptr)))
@@ -274,6 +304,8 @@ class ProverSession:
         res["commitments"] += list(cm); tr.absorb(cm)
         beta, gamma = tr.squeeze(), tr.squeeze()
         bl, gl = to_limbs(beta), to_limbs(gamma)
+        mark("phase1 lookup permuted")
+        side_transforms([(self.pa, self.pac, "pa"), (self.ps, self.psc, "ps")])
         # ---- product columns + the vanishing argument's random polynomial
         cols = (C.c_void_p * 2)(cs.lagr["c"].ptr, self.a.ptr)
         sig = (C.c_void_p * 2)(cs.lagr["sigma_c"].ptr, cs.lagr["sigma_a"].ptr)
@@ -282,17 +314,14 @@ class ProverSession:
                                              vp(bl.ctypes.data), vp(gl.ctypes.data), k, bf, vp(self.zl.ptr)))
         self._blind(self.zp, u + 1, rng)
         self._blind(self.zl, u + 1, rng)
-        self.rnd.upload_ptr(random_poly_ptr, n)
-        self.h2d_bytes += n * 32
+        side_transforms([(self.zp, self.zpc, "zp"), (self.zl, self.zlc, "zl")])  # beside the commitments below
         cm = self._commit([(BASIS_LAGRANGE, self.zp.ptr), (BASIS_LAGRANGE, self.zl.ptr), (BASIS_MONOMIAL, self.rnd.ptr)])
         res["commitments"] += list(cm); tr.absorb(cm)
         y = tr.squeeze()
         yl = to_limbs(y)
-        # ---- coefficients and extended-coset evaluations of the five prover columns (in place: Lagrange -> coefficients)
-        work = {"a": self.a, "pa": self.pa, "ps": self.ps, "zp": self.zp, "zl": self.zl}
-        for name, p in work.items():
-            ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, vp(p.ptr), k))
-            ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(p.ptr), n, ext_k, vp(self.ext[name].ptr)))
+        mark("phase2 products+random")
+        ctx.check(lib.h2b_ctx_side_join(ctx.h))  # all five columns are now in coefficient and extended form
+        mark("transforms")
         # ---- quotient: gate, permutation and lookup terms folded with y on the extended coset
         kw = dict(beta=bl, gamma=gl, theta=to_limbs(theta), y=yl)
         ctx.check(lib.h2b_poly_zero(ctx.h, self.h.h))
@@ -309,19 +338,21 @@ class ProverSession:
                                           vp(cs.ext["l0"].ptr), vp(cs.ext["l_last"].ptr), vp(cs.ext["l_active"].ptr), k, ext_k, vp(self.h.ptr)))
         ctx.check(lib.h2b_divide_by_vanishing_poly_dev(ctx.h, vp(self.h.ptr), k, ext_k))
         ctx.check(lib.h2b_extended_to_coeff_dev(ctx.h, vp(self.h.ptr), ext_k))
+        mark("quotient")
         pieces = cs.degree - 1
         cm = self._commit([(BASIS_MONOMIAL, self.h.at(j * n)) for j in range(pieces)])
         res["commitments"] += list(cm); tr.absorb(cm)
         x = tr.squeeze()
+        mark("phase3 h pieces")
         # ---- evaluations at x and its rotations
         w = pow(ROOT_OF_UNITY, 1 << (28 - k), R_MOD)
         rot = lambda r: x * pow(w, r % n, R_MOD) % R_MOD
         last = -(bf + 1)
-        queries = ([("a", self.a.ptr, r) for r in (0, 1, 2, 3)]
+        queries = ([("a", self.ac.ptr, r) for r in (0, 1, 2, 3)]
                    + [(nm, cs.coeff[nm].ptr, 0) for nm in ("q", "q_lookup", "table", "c", "sigma_c", "sigma_a")]
-                   + [("zp", self.zp.ptr, r) for r in (0, 1, last)]
-                   + [("pa", self.pa.ptr, 0), ("pa", self.pa.ptr, -1), ("ps", self.ps.ptr, 0)]
-                   + [("zl", self.zl.ptr, 0), ("zl", self.zl.ptr, 1)]
+                   + [("zp", self.zpc.ptr, r) for r in (0, 1, last)]
+                   + [("pa", self.pac.ptr, 0), ("pa", self.pac.ptr, -1), ("ps", self.psc.ptr, 0)]
+                   + [("zl", self.zlc.ptr, 0), ("zl", self.zlc.ptr, 1)]
                    + [("h%d" % j, self.h.at(j * n), 0) for j in range(pieces)] + [("rnd", self.rnd.ptr, 0)])
         m = len(queries)
         polys = (C.c_void_p * m)(*[p for _, p, _ in queries])
@@ -332,38 +363,53 @@ class ProverSession:
         tr.absorb(ev_out)
         res["evals"] = {(nm, r): ev_out[i] for i, (nm, _, r) in enumerate(queries)}
         res["challenges"] = dict(theta=theta, beta=beta, gamma=gamma, y=y, x=x)
+        mark("evaluations")
         # ---- SHPLONK-shaped opening: per rotation set sum_i v^i p_i, divided by (X - point) for every point of the set
         v_ch, mu = tr.squeeze(), tr.squeeze()
         sets = [
-            ([0], [cs.coeff[nm].ptr for nm in ("q", "q_lookup", "table", "c", "sigma_c", "sigma_a")] + [self.ps.ptr, self.rnd.ptr]
+            ([0], [cs.coeff[nm].ptr for nm in ("q", "q_lookup", "table", "c", "sigma_c", "sigma_a")] + [self.psc.ptr, self.rnd.ptr]
              + [self.h.at(j * n) for j in range(pieces)]),
-            ([0, 1, 2, 3], [self.a.ptr]),
-            ([0, 1, last], [self.zp.ptr]),
-            ([0, -1], [self.pa.ptr]),
-            ([0, 1], [self.zl.ptr]),
+            ([0, 1, 2, 3], [self.ac.ptr]),
+            ([0, 1, last], [self.zpc.ptr]),
+            ([0, -1], [self.pac.ptr]),
+            ([0, 1], [self.zlc.ptr]),
         ]
-        qs = []
-        for si, (rots, plist) in enumerate(sets):
-            f, qd = self.tmp[0], self.tmp[1]
-            mm = len(plist)
-            pp = (C.c_void_p * mm)(*plist)
-            sc = np.stack([to_limbs(pow(v_ch, i, R_MOD)) for i in range(mm)])
-            ctx.check(lib.h2b_poly_lincomb_dev(ctx.h, pp, vp(sc.ctypes.data), mm, n, vp(f.ptr)))
-            src, dst = f, qd
-            for r in rots:  # successive divisions by (X - point): the quotient by the set's vanishing polynomial
-                z = to_limbs(rot(r))
-                ctx.check(lib.h2b_kate_division_dev(ctx.h, vp(src.ptr), n, vp(z.ctypes.data), vp(dst.ptr)))
-                src, dst = dst, src
-            # accumulate mu^s * q_s into tmp[2]
-            acc = self.tmp[2]
-            if si == 0:
-                one = np.stack([to_limbs(1)])
-                p1 = (C.c_void_p * 1)(src.ptr)
-                ctx.check(lib.h2b_poly_lincomb_dev(ctx.h, p1, vp(one.ctypes.data), 1, n, vp(acc.ptr)))
-            else:
-                p2 = (C.c_void_p * 2)(acc.ptr, src.ptr)
-                sc2 = np.stack([to_limbs(1), to_limbs(pow(mu, si, R_MOD))])
-                ctx.check(lib.h2b_poly_lincomb_dev(ctx.h, p2, vp(sc2.ctypes.data), 2, n, vp(acc.ptr)))
+        def run_sets(which, bufs):
+            """sum over the given rotation sets of mu^s * (sum_i v^i p_i) / prod (X - point); result in bufs[2]"""
+            f, qd, acc = bufs
+            first = True
+            for si in which:
+                rots, plist = sets[si]
+                mm = len(plist)
+                pp = (C.c_void_p * mm)(*plist)
+                sc = np.stack([to_limbs(pow(v_ch, i, R_MOD)) for i in range(mm)])
+                ctx.check(lib.h2b_poly_lincomb_dev(ctx.h, pp, vp(sc.ctypes.data), mm, n, vp(f.ptr)))
+                src, dst = f, qd
+                for r in rots:  # successive divisions by (X - point): the quotient by the set's vanishing polynomial
+                    z = to_limbs(rot(r))
+                    ctx.check(lib.h2b_kate_division_dev(ctx.h, vp(src.ptr), n, vp(z.ctypes.data), vp(dst.ptr)))
+                    src, dst = dst, src
+                mu_s = to_limbs(pow(mu, si, R_MOD))
+                if first:
+                    p1 = (C.c_void_p * 1)(src.ptr)
+                    ctx.check(lib.h2b_poly_lincomb_dev(ctx.h, p1, vp(np.stack([mu_s]).ctypes.data), 1, n, vp(acc.ptr)))
+                    first = False
+                else:
+                    p2 = (C.c_void_p * 2)(acc.ptr, src.ptr)
+                    ctx.check(lib.h2b_poly_lincomb_dev(ctx.h, p2, vp(np.stack([to_limbs(1), mu_s]).ctypes.data), 2, n, vp(acc.ptr)))
+
+        # the rotation sets are independent: three of them on the side queue (own scratch), two on the main queue
+        ctx.check(lib.h2b_ctx_side_begin(ctx.h))
+        try:
+            run_sets([0, 2, 4], self.tmp_side)
+        finally:
+            ctx.check(lib.h2b_ctx_side_end(ctx.h))
+        run_sets([1, 3], self.tmp[:3])
+        ctx.check(lib.h2b_ctx_side_join(ctx.h))
+        p2 = (C.c_void_p * 2)(self.tmp[2].ptr, self.tmp_side[2].ptr)
+        ones = np.stack([to_limbs(1), to_limbs(1)])
+        ctx.check(lib.h2b_poly_lincomb_dev(ctx.h, p2, vp(ones.ctypes.data), 2, n, vp(self.tmp[2].ptr)))
+        mark("shplonk arithmetic")
         cm = self._commit([(BASIS_MONOMIAL, self.tmp[2].ptr)])
         res["commitments"] += list(cm); tr.absorb(cm)
         u_ch = tr.squeeze()
@@ -373,8 +419,12 @@ class ProverSession:
         cm = self._commit([(BASIS_MONOMIAL, self.tmp[3].ptr)])
         res["commitments"] += list(cm)
         res["h2d_bytes"], res["d2h_bytes"] = self.h2d_bytes, self.d2h_bytes
+        mark("phase4-5 openings")
+        if trace is not None:
+            import sys
+            print("prover trace (ms): " + ", ".join("%s=%.2f" % (l, 1e3 * (t - trace[i][1])) for i, (l, t) in enumerate(trace[1:])), file=sys.stderr)
         return res
 
     def free(self):
-        for p in [self.v, self.a, self.inp, self.pa, self.ps, self.zp, self.zl, self.rnd, self.h, self.d_out] + self.tmp + list(self.ext.values()):
+        for p in [self.v, self.a, self.inp, self.pa, self.ps, self.zp, self.zl, self.rnd, self.h, self.d_out, self.ac, self.pac, self.psc, self.zpc, self.zlc] + self.tmp + self.tmp_side + list(self.ext.values()):
             p.free()

@@ -52,6 +52,15 @@ void h2b_ctx_destroy(h2b_ctx* ctx);
  * context's own stream. */
 int h2b_ctx_set_stream(h2b_ctx* ctx, void* cuda_stream);
 int h2b_ctx_synchronize(h2b_ctx* ctx);
+/* A second in-order queue of the same context: between h2b_ctx_side_begin and h2b_ctx_side_end every `_dev` call is
+ * enqueued on the context's side stream, which first waits for everything enqueued so far on the main stream;
+ * h2b_ctx_side_join makes the main stream wait for the side work enqueued so far.  The resident prover runs the
+ * lagrange_to_coeff / coeff_to_extended of the columns that already exist beside the next phase's commitments this way.
+ * The side queue has its own scratch workspaces; the caller keeps the two queues on disjoint polynomials, and must not run
+ * a batched MSM (which uses all workspace sets) on the main queue while side work that is not a transform is in flight. */
+int h2b_ctx_side_begin(h2b_ctx* ctx);
+int h2b_ctx_side_end(h2b_ctx* ctx);
+int h2b_ctx_side_join(h2b_ctx* ctx);
 /* Tuning / experiment switches (results never depend on them).  Keys:
  *   "msm.affine_levels"  0..3 (-1 = default 0): batch-affine halving levels in front of the XYZZ bucket accumulation
  *   "msm.affine_k"       multiple of 4 in [8, 128] (-1 = default 32): pairs per thread and tile of those levels */
@@ -345,6 +354,9 @@ void h2b_poly_free(h2b_ctx* ctx, h2b_poly* poly);
 void* h2b_poly_device_ptr(const h2b_poly* poly);
 size_t h2b_poly_len(const h2b_poly* poly);
 int h2b_poly_zero(h2b_ctx* ctx, h2b_poly* poly);                                                      /* asynchronous */
+/* enqueue only: `pinned_host` must be page-locked and stay untouched until the stream has been synchronised */
+int h2b_poly_upload_async(h2b_ctx* ctx, h2b_poly* poly, size_t offset, const uint64_t* pinned_host, size_t n);
+int h2b_poly_copy_dev(h2b_ctx* ctx, void* d_dst, const void* d_src, size_t n);                         /* asynchronous, n elements */
 int h2b_poly_upload(h2b_ctx* ctx, h2b_poly* poly, size_t offset, const uint64_t* host, size_t n);     /* blocking */
 int h2b_poly_download(h2b_ctx* ctx, const h2b_poly* poly, size_t offset, uint64_t* host, size_t n);   /* blocking */
 

@@ -59,8 +59,8 @@ def test_resident_proof_commitments_and_quotient_identity(ctx, h2b, k):
     # the evaluations are what Horner gives on the downloaded coefficients (advice column, a product column, an h piece)
     x = res["challenges"]["x"]
     w = pyref.omega_for(k)
-    assert pc.fr(res["evals"][("a", 2)]) == pc.horner(sess.a.download(), x * pow(w, 2, R) % R)
-    assert pc.fr(res["evals"][("zp", -(cs.bf + 1))]) == pc.horner(sess.zp.download(), x * pow(w, n - (cs.bf + 1), R) % R)
+    assert pc.fr(res["evals"][("a", 2)]) == pc.horner(sess.ac.download(), x * pow(w, 2, R) % R)
+    assert pc.fr(res["evals"][("zp", -(cs.bf + 1))]) == pc.horner(sess.zpc.download(), x * pow(w, n - (cs.bf + 1), R) % R)
     assert pc.fr(res["evals"][("h1", 0)]) == pc.horner(sess.h.download(n, n), x)
     # PCIe accounting: witness + random polynomial + blinding rows up, commitments + evaluations down
     assert res["h2d_bytes"] <= (usable + n) * 32 + 64 * 32 * 5 and res["d2h_bytes"] <= 12 * 96 + 64 * 32
