@@ -13,6 +13,7 @@ from .host import (  # noqa: F401
     best_multiexp,
     best_fft,
     assign_witnesses,
+    assign_witnesses_assigned,
     assign_lookups,
     omega,
 )

@@ -89,6 +89,8 @@ SIGNATURES = {
     "h2b_extended_to_coeff_dev": (_int, [_vp, _vp, _u32]),
     "h2b_assign_columns": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _sz, _vp]),
     "h2b_assign_columns_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _sz, _vp]),
+    "h2b_assign_columns_assigned": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _sz, _vp]),
+    "h2b_assign_columns_assigned_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _u32, _sz, _vp]),
     "h2b_assign_lookups": (_int, [_vp, _vp, _sz, _u32, _sz, _vp]),
     "h2b_assign_lookups_dev": (_int, [_vp, _vp, _sz, _u32, _sz, _vp]),
     "h2b_eval_rational": (_int, [_vp, _vp, _vp, _sz, _vp]),

@@ -35,6 +35,55 @@ __global__ void __launch_bounds__(256) k_assign_columns(const uint4* __restrict_
     cols[g] = v;
 }
 
+struct ColSpans64 {
+    ColSpan s[64];
+};
+// same gather with the spans passed by value (no staging copy, no host synchronisation): up to 64 columns
+__global__ void __launch_bounds__(256) k_assign_columns_v(const uint4* __restrict__ vcol, ColSpans64 spans, u32 rows_log, u32 ncols,
+                                                          uint4* __restrict__ cols) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = ((size_t)ncols << rows_log) * 2;
+    if (g >= total) return;
+    size_t cell = g >> 1;
+    u32 half = (u32)(g & 1);
+    u32 c = (u32)(cell >> rows_log);
+    size_t r = cell & (((size_t)1 << rows_log) - 1);
+    const ColSpan sp = spans.s[c];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < sp.len) v = __ldg(vcol + 2 * (sp.start + r) + half);
+    cols[g] = v;
+}
+
+// `Assigned<Fr>` staging records (72 bytes: tag, numerator, denominator; halo2-base/src/lib.rs:157-188 re-exports the
+// prover crate's Assigned::{Zero, Trivial(F), Rational(F, F)}): split into a numerator and a denominator array.
+// tag 0 -> (0, 1), 1 -> (num, 1), 2 -> (num, den).  stats[0] counts the Rational cells, stats[1] the invalid tags.
+__global__ void __launch_bounds__(256) k_assigned_split(const uint64_t* __restrict__ recs, size_t N, uint64_t* __restrict__ num,
+                                                        uint64_t* __restrict__ den, u32* __restrict__ stats) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint64_t* r = recs + 9 * i;
+    const uint64_t tag = __ldg(r);
+    Fr nu = Fr::zero(), de = Fr::one();
+    if (tag == 1 || tag == 2) {
+        uint64_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = __ldg(r + 1 + j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { nu.l[2 * j] = (u32)w[j]; nu.l[2 * j + 1] = (u32)(w[j] >> 32); }
+    }
+    if (tag == 2) {
+        uint64_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = __ldg(r + 5 + j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { de.l[2 * j] = (u32)w[j]; de.l[2 * j + 1] = (u32)(w[j] >> 32); }
+        atomicAdd(stats, 1u);
+    }
+    if (tag > 2) atomicAdd(stats + 1, 1u);
+    nu.store(num + 4 * i);
+    de.store(den + 4 * i);
+}
+
 __global__ void __launch_bounds__(256) k_assign_lookups(const uint4* __restrict__ vals, size_t N, u32 rows_log, u32 L,
                                                         uint4* __restrict__ cols) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,13 +142,34 @@ void assign_columns_run(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64
             rem = 0;
         }
     }
+    size_t total = ncols * rows * 2;
+    if (ncols <= 64) {  // the usual case: spans travel as a kernel argument, the call stays asynchronous
+        ColSpans64 sv;
+        memset(&sv, 0, sizeof(sv));
+        for (size_t i = 0; i < ncols; i++) sv.s[i] = spans[i];
+        H2B_LAUNCH(ctx, k_assign_columns_v, ceil_div(total, 256), 256, 0, (const uint4*)d_vcol, sv, k, (u32)ncols, (uint4*)d_cols);
+        return;
+    }
     ColSpan* d_spans = (ColSpan*)ctx->get(WS_MISC, ncols * sizeof(ColSpan));
     ColSpan* h_spans = (ColSpan*)ctx->get_pinned(1, ncols * sizeof(ColSpan));
-    H2B_CUDA(cudaStreamSynchronize(ctx->stream));  // pinned staging block may still be in flight
+    H2B_CUDA(cudaStreamSynchronize(ctx->stream));  // > 64 columns: the pinned staging block may still be in flight
     memcpy(h_spans, spans.data(), ncols * sizeof(ColSpan));
     H2B_CUDA(cudaMemcpyAsync(d_spans, h_spans, ncols * sizeof(ColSpan), cudaMemcpyHostToDevice, ctx->stream));
-    size_t total = ncols * rows * 2;
     H2B_LAUNCH(ctx, k_assign_columns, ceil_div(total, 256), 256, 0, (const uint4*)d_vcol, d_spans, k, (u32)ncols, (uint4*)d_cols);
+}
+
+// d_recs: N staging records of 72 bytes.  d_values (N x 32 B) receives what the prover's `batch_invert_assigned` yields:
+// Zero -> 0, Trivial(x) -> x, Rational(n, d) -> n / d (d = 0 -> 0).  `stats` (device, 2 x u32, zeroed here): see above.
+// invert: 0 = never (the caller knows there is no Rational cell), 1 = always (asynchronous).
+void assigned_flatten_run(h2b_ctx* ctx, const void* d_recs, size_t N, void* d_values, u32* d_stats, int invert) {
+    if (N == 0) return;
+    uint64_t* den = (uint64_t*)ctx->get(WS_PROD, N * 32);
+    H2B_CUDA(cudaMemsetAsync(d_stats, 0, 8, ctx->stream));
+    H2B_LAUNCH(ctx, k_assigned_split, ceil_div(N, 256), 256, 0, (const uint64_t*)d_recs, N, (uint64_t*)d_values, den, d_stats);
+    if (invert) {
+        batch_invert_run(ctx, den, N);
+        fr_mul_elementwise_run(ctx, d_values, den, N, d_values);
+    }
 }
 
 void assign_lookups_run(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols) {

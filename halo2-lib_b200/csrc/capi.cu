@@ -691,6 +691,44 @@ int h2b_assign_columns(h2b_ctx* ctx, const uint64_t* vcol, size_t N, const uint6
         H2B_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
+// `Assigned<Fr>` records in, columns out: flatten (Zero / Trivial / Rational with one batched inversion) + the gather
+int h2b_assign_columns_assigned_dev(h2b_ctx* ctx, const void* d_cells, size_t N, const uint64_t* break_points, size_t nbp, uint32_t k,
+                                    size_t ncols, void* d_cols) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((d_cells || N == 0) && (d_cols || ncols == 0) && (break_points || nbp == 0), "assign: null pointer");
+        void* d_vals = ctx->get(WS_ASSIGN_IN, N * 32 + 64);
+        uint32_t* d_stats = (uint32_t*)((char*)d_vals + ((N * 32 + 31) & ~(size_t)31));
+        assigned_flatten_run(ctx, d_cells, N, d_vals, d_stats, 1);
+        assign_columns_run(ctx, d_vals, N, break_points, nbp, k, ncols, d_cols);
+    });
+}
+int h2b_assign_columns_assigned(h2b_ctx* ctx, const uint64_t* cells, size_t N, const uint64_t* break_points, size_t nbp, uint32_t k,
+                                size_t ncols, uint64_t* cols) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE((cells || N == 0) && (cols || ncols == 0) && (break_points || nbp == 0), "assign: null pointer");
+        H2B_REQUIRE(k <= 28, "assign: k out of range");
+        const size_t out_bytes = (ncols << k) * 32;
+        char* d_in = (char*)ctx->get(WS_ASSIGN_IN, N * 72 + N * 32 + 128);
+        void* d_vals = d_in + ((N * 72 + 31) & ~(size_t)31);
+        uint32_t* d_stats = (uint32_t*)((char*)d_vals + N * 32 + 32);
+        void* d_out = ctx->get(WS_ASSIGN_OUT, out_bytes);
+        if (N) H2B_CUDA(cudaMemcpyAsync(d_in, cells, N * 72, cudaMemcpyHostToDevice, ctx->stream));
+        assigned_flatten_run(ctx, d_in, N, d_vals, d_stats, 0);
+        uint32_t st[2] = {0, 0};
+        if (N) {
+            uint32_t* bounce = (uint32_t*)ctx->get_pinned(2, 4096);
+            H2B_CUDA(cudaMemcpyAsync(bounce, d_stats, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+            st[0] = bounce[0];
+            st[1] = bounce[1];
+        }
+        H2B_REQUIRE(st[1] == 0, "assign: a cell record carries a tag other than 0 (Zero), 1 (Trivial), 2 (Rational)");
+        if (st[0]) assigned_flatten_run(ctx, d_in, N, d_vals, d_stats, 1);  // Rational cells present: with the batched inversion
+        assign_columns_run(ctx, d_vals, N, break_points, nbp, k, ncols, d_out);
+        if (out_bytes) H2B_CUDA(cudaMemcpyAsync(cols, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
 int h2b_assign_lookups_dev(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols) {
     return guarded(ctx, [&] {
         H2B_REQUIRE((d_vals || N == 0) && (d_cols || L == 0), "assign: null pointer");

@@ -183,6 +183,7 @@ void domain_omega(uint32_t k, uint64_t out[4], bool inverse);
 // ---- assign.cu
 void assign_columns_run(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64_t* break_points, size_t nbp,
                         uint32_t k, size_t ncols, void* d_cols);
+void assigned_flatten_run(h2b_ctx* ctx, const void* d_recs, size_t N, void* d_values, uint32_t* d_stats, int invert);
 void assign_lookups_run(h2b_ctx* ctx, const void* d_vals, size_t N, uint32_t k, size_t L, void* d_cols);
 void eval_rational_run(h2b_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_out);
 // ---- peer.cu

@@ -317,6 +317,17 @@ def assign_witnesses(ctx: Context, threads, break_points, k: int, ncols: int) ->
     return cols
 
 
+def assign_witnesses_assigned(ctx: Context, cells, break_points, k: int, ncols: int) -> np.ndarray:
+    """`assign_witnesses` fed with `Assigned<Fr>` staging records: cells = N x 9 uint64 (tag, numerator[4], denominator[4]),
+    tag 0 Zero / 1 Trivial / 2 Rational (halo2-base/src/lib.rs:157-188); the Rational cells are batch-inverted on the GPU"""
+    c = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 9)
+    bp = np.ascontiguousarray(break_points, dtype=np.uint64).reshape(-1)
+    cols = np.empty((ncols, 1 << k, 4), dtype=np.uint64)
+    ctx.check(lib.h2b_assign_columns_assigned(ctx.h, _ptr(c) if len(c) else None, len(c), _ptr(bp) if len(bp) else None, len(bp), k, ncols,
+                                              _ptr(cols) if ncols else None))
+    return cols
+
+
 def assign_lookups(ctx: Context, values, k: int, L: int) -> np.ndarray:
     v = _u64(values, 4)
     cols = np.empty((L, 1 << k, 4), dtype=np.uint64)

@@ -207,6 +207,15 @@ int h2b_assign_columns(h2b_ctx* ctx, const uint64_t* vcol, size_t N, const uint6
                        uint32_t k, size_t ncols, uint64_t* cols);
 int h2b_assign_columns_dev(h2b_ctx* ctx, const void* d_vcol, size_t N, const uint64_t* break_points,
                            size_t nbp, uint32_t k, size_t ncols, void* d_cols);
+/* The same, fed with what halo2-base actually holds: `Vec<Assigned<Fr>>` (halo2-base/src/lib.rs:157-188; enum
+ * Zero | Trivial(F) | Rational(F, F)), staged as N records of 72 bytes = 9 x u64: { tag (0 Zero, 1 Trivial, 2 Rational),
+ * numerator[4], denominator[4] } (Montgomery limbs; fields a tag does not use are ignored).  The library flattens the
+ * cells itself — Rational cells through ONE batched inversion, denominator 0 -> 0 as `batch_invert_assigned` does — and
+ * then lays the columns out as h2b_assign_columns.  H2B_ERR_ARG for any other tag (host-pointer form). */
+int h2b_assign_columns_assigned(h2b_ctx* ctx, const uint64_t* cells, size_t N, const uint64_t* break_points, size_t nbp,
+                                uint32_t k, size_t ncols, uint64_t* cols);
+int h2b_assign_columns_assigned_dev(h2b_ctx* ctx, const void* d_cells, size_t N, const uint64_t* break_points,
+                                    size_t nbp, uint32_t k, size_t ncols, void* d_cols);
 /* LookupAnyManager::assign_raw (halo2-base/src/virtual_region/lookups.rs:130-155): value j -> lookup
  * column j mod L, row j div L.  cols = L x 2^k x 4 limbs. */
 int h2b_assign_lookups(h2b_ctx* ctx, const uint64_t* vals, size_t N, uint32_t k, size_t L, uint64_t* cols);

@@ -86,3 +86,25 @@ def test_graph_struct_layout_matches_the_header(tmp_path):
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert got[0] == C.sizeof(Graph)
     assert got[1:] == [getattr(Graph, f).offset for f in fields]
+
+
+def test_rust_ffi_declares_every_header_symbol():
+    """rust/halo2-b200/src/ffi.rs is generated from include/h2b200.h (tools/gen_rust_ffi.py): it must be up to date, declare
+    every exported function exactly once, and agree with the ctypes table on the number of arguments (no Rust toolchain
+    exists in this image, so this is the structural check)."""
+    import subprocess, sys
+    from halo2_lib_b200._capi import SIGNATURES, header_symbols
+    path = os.path.join(ROOT, "rust", "halo2-b200", "src", "ffi.rs")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py")], stdout=subprocess.DEVNULL)
+    assert open(path).read() == before, "ffi.rs is stale: run tools/gen_rust_ffi.py"
+    decl = dict(re.findall(r"pub fn (h2b_[a-z0-9_]+)\(([^)]*)\)", before))
+    assert sorted(decl) == header_symbols()
+    for name, args in decl.items():
+        n_args = 0 if not args.strip() else len(args.split(","))
+        assert n_args == len(SIGNATURES[name][1]), name
+    for f in ("Cargo.toml", "build.rs", "src/lib.rs", "src/backend.rs"):
+        assert os.path.exists(os.path.join(ROOT, "rust", "halo2-b200", f))
+    # every ffi function the safe wrappers call is declared
+    used = set(re.findall(r"\b(h2b_[a-z0-9_]+)\(", open(os.path.join(ROOT, "rust", "halo2-b200", "src", "backend.rs")).read()))
+    assert used <= set(decl), used - set(decl)

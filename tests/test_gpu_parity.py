@@ -463,3 +463,42 @@ def test_errors_do_not_cross_the_abi(ctx, h2b):
             h2b.lib.h2b_ntt_fr(ctx.h, None, 3, None, 0))
     with pytest.raises(h2b.H2BError):
         ctx.check(h2b.lib.h2b_msm_g1(ctx.h, None, 0, None, 4, None))
+
+
+def test_assign_witnesses_from_assigned_records(ctx, h2b):
+    """`Vec<Assigned<Fr>>` staging records (Zero / Trivial / Rational, halo2-base/src/lib.rs:157-188) in, columns out: the
+    Rational cells go through the GPU's batched inversion (denominator 0 -> 0), then the literal walk's layout"""
+    rng = np.random.default_rng(4100)
+    k, ncols = 9, 3
+    n = 1 << k
+    N = 1200
+    tags = rng.integers(0, 3, size=N)
+    nums, dens = rand_ints(rng, N, R), rand_ints(rng, N, R)
+    dens[5] = 0
+    tags[5] = 2      # Rational with a zero denominator
+    tags[6] = 0      # Zero whose payload fields hold garbage
+    cells = np.zeros((N, 9), dtype=np.uint64)
+    cells[:, 0] = tags
+    cells[:, 1:5] = mont(nums, R)
+    cells[:, 5:9] = mont(dens, R)
+    want_vals = [0 if t == 0 else (v if t == 1 else (v * pow(d, -1, R) % R if d else 0)) for t, v, d in zip(tags, nums, dens)]
+    bp = np.array([n - 21, n - 22], dtype=np.uint64)
+    rc, want = orc.assign_witnesses(mont(want_vals, R), bp, k, ncols)
+    assert rc == 0
+    got = h2b.assign_witnesses_assigned(ctx, cells, bp, k, ncols)
+    assert np.array_equal(got, want)
+    # all-Trivial input takes the path without the inversion
+    cells[:, 0] = 1
+    rc, want = orc.assign_witnesses(mont(nums, R), bp, k, ncols)
+    assert np.array_equal(h2b.assign_witnesses_assigned(ctx, cells, bp, k, ncols), want)
+    # an unknown tag is rejected
+    cells[7, 0] = 3
+    with pytest.raises(h2b.H2BError):
+        h2b.assign_witnesses_assigned(ctx, cells, bp, k, ncols)
+    # many columns (> 64: the staged-span path) still match the walk
+    k2, nc2 = 5, 70
+    V = mont(rand_ints(rng, 31 * 40, R), R)
+    bp2 = np.array([30] * 40, dtype=np.uint64)
+    rc, want = orc.assign_witnesses(V, bp2, k2, nc2)
+    assert rc == 0
+    assert np.array_equal(h2b.assign_witnesses(ctx, [V], bp2, k2, nc2), want)
