@@ -107,6 +107,10 @@ SIGNATURES = {
     "h2b_srs_setup_dev": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "h2b_g1_check_on_curve": (_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "h2b_g1_check_on_curve_dev": (_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "h2b_g1_decompress": (_int, [_vp, _vp, _sz, _vp, C.POINTER(_sz)]),
+    "h2b_g1_decompress_dev": (_int, [_vp, _vp, _sz, _vp, C.POINTER(_sz)]),
+    "h2b_params_processed_view": (_int, [_vp, _sz, C.POINTER(_u32), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "h2b_srs_read_processed": (_int, [_vp, _vp, _sz, _sz, _sz, C.POINTER(_vp)]),
     "h2b_params_raw_view": (_int, [_vp, _sz, C.POINTER(_u32), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "h2b_permute_expression_pair": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "h2b_permute_expression_pair_dev": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),

@@ -877,6 +877,59 @@ int h2b_g1_check_on_curve(h2b_ctx* ctx, const uint64_t* points_xy, size_t n, siz
         *off_curve = g1_count_off_curve_run(ctx, d, n);
     });
 }
+int h2b_g1_decompress_dev(h2b_ctx* ctx, const void* d_bytes, size_t n, void* d_out_xy, size_t* invalid) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(((d_bytes && d_out_xy) || n == 0) && invalid, "g1_decompress: null pointer");
+        *invalid = g1_decompress_run(ctx, d_bytes, n, d_out_xy);
+    });
+}
+int h2b_g1_decompress(h2b_ctx* ctx, const uint8_t* bytes, size_t n, uint64_t* out_xy, size_t* invalid) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(((bytes && out_xy) || n == 0) && invalid, "g1_decompress: null pointer");
+        *invalid = 0;
+        if (n == 0) return;
+        char* d = (char*)ctx->get(WS_BASES, n * 96);
+        H2B_CUDA(cudaMemcpyAsync(d, bytes, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        *invalid = g1_decompress_run(ctx, d, n, d + n * 32);
+        H2B_CUDA(cudaMemcpyAsync(out_xy, d + n * 32, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int h2b_params_processed_view(const uint8_t* bytes, size_t len, uint32_t* k, size_t* g_offset, size_t* g_lagrange_offset,
+                              size_t* g2_offset, size_t* s_g2_offset) {
+    if (!bytes || !k || len < 4) return H2B_ERR_ARG;
+    const uint32_t kk = (uint32_t)bytes[0] | ((uint32_t)bytes[1] << 8) | ((uint32_t)bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
+    if (kk > 28) return H2B_ERR_ARG;
+    const size_t n = (size_t)1 << kk;
+    if (len < 4 + 2 * n * 32 + 2 * 64) return H2B_ERR_ARG;
+    *k = kk;
+    if (g_offset) *g_offset = 4;
+    if (g_lagrange_offset) *g_lagrange_offset = 4 + n * 32;
+    if (g2_offset) *g2_offset = 4 + 2 * n * 32;
+    if (s_g2_offset) *s_g2_offset = 4 + 2 * n * 32 + 64;
+    return H2B_OK;
+}
+// `ParamsKZG::read` of a SerdeFormat::Processed image, device side: decompress g and g_lagrange (every point is thereby
+// on the curve), build the MSM tables.  H2B_ERR_ARG on a malformed image or an invalid point encoding.
+int h2b_srs_read_processed(h2b_ctx* ctx, const uint8_t* bytes, size_t len, size_t begin, size_t count, h2b_srs** out) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(bytes && out, "srs_read: null pointer");
+        uint32_t k = 0;
+        size_t og = 0, ol = 0;
+        H2B_REQUIRE(h2b_params_processed_view(bytes, len, &k, &og, &ol, nullptr, nullptr) == H2B_OK, "srs_read: not a SerdeFormat::Processed params image");
+        const size_t n = (size_t)1 << k;
+        if (count == 0 && begin == 0) count = n;
+        H2B_REQUIRE(count >= 1 && begin + count <= n, "srs_read: shard outside the 2^k bases");
+        char* d = (char*)ctx->get(WS_BASES, count * (64 + 128));
+        char* d_g = d + count * 64;
+        char* d_gl = d_g + count * 64;
+        H2B_CUDA(cudaMemcpyAsync(d, bytes + og + 32 * begin, count * 32, cudaMemcpyHostToDevice, ctx->stream));
+        H2B_CUDA(cudaMemcpyAsync(d + count * 32, bytes + ol + 32 * begin, count * 32, cudaMemcpyHostToDevice, ctx->stream));
+        const size_t bad = g1_decompress_run(ctx, d, count, d_g) + g1_decompress_run(ctx, d + count * 32, count, d_gl);
+        H2B_REQUIRE(bad == 0, "srs_read: the params image holds an invalid G1 encoding");
+        srs_build(ctx, d_g, d_gl, k, begin, count, out);
+    });
+}
 int h2b_params_raw_view(const uint8_t* bytes, size_t len, uint32_t* k, size_t* g_offset, size_t* g_lagrange_offset, size_t* g2_offset,
                         size_t* s_g2_offset) {
     if (!bytes || !k || len < 4) return H2B_ERR_ARG;

@@ -16,6 +16,73 @@
 
 namespace h2b {
 
+// ---------------------------------------------------------------- compressed points (SerdeFormat::Processed)
+// halo2curves `G1Affine::from_bytes` as `ParamsKZG::read` applies it to a `kzg_bn254_{k}.srs` file written in
+// SerdeFormat::Processed (reference call sites halo2-base/src/utils/mod.rs:401-435): 32 bytes = x, little-endian,
+// canonical; the two spare bits of the last byte carry bit 7 = point at infinity, bit 6 = parity of y (LSB of the
+// canonical y).  [halo2curves-axiom 0.7.3 is not vendored: the flag positions are recalled, see DESIGN.md §2.]
+// y = sqrt(x^3 + 3) = (x^3 + 3)^((p + 1) / 4) since p = 3 mod 4; a non-residue, an x >= p, or an infinity flag on a
+// non-zero x is an invalid encoding.  out = (x, y) Montgomery, (0, 0) for the identity; invalid -> (0, 0) and counted.
+__device__ __forceinline__ Fq fq_sqrt_candidate(const Fq& a) {
+    // (p + 1) / 4, little-endian 32-bit limbs
+    const u32 e[8] = {0xb61f3f52u, 0x4f082305u, 0x5a1c72a3u, 0x65e05aa4u, 0xa0605617u, 0x6e14116du, 0xb84c680au, 0x0c19139cu};
+    Fq acc = Fq::one();
+#pragma unroll 1
+    for (int limb = 7; limb >= 0; limb--) {
+        u32 v = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            if (t == limb) v = e[t];
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = acc.sqr();
+            if ((v >> bit) & 1) acc = acc * a;
+        }
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict__ bytes, size_t n, Affine* __restrict__ out,
+                                                       unsigned long long* __restrict__ invalid) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(bytes + 32 * i);
+    const uint4 lo = __ldg(q), hi = __ldg(q + 1);
+    Fq x;
+    x.l[0] = lo.x; x.l[1] = lo.y; x.l[2] = lo.z; x.l[3] = lo.w;
+    x.l[4] = hi.x; x.l[5] = hi.y; x.l[6] = hi.z; x.l[7] = hi.w;
+    const bool inf = (x.l[7] >> 31) & 1, odd = (x.l[7] >> 30) & 1;
+    x.l[7] &= 0x3fffffffu;
+    Affine r;
+    r.x = Fq::zero();
+    r.y = Fq::zero();
+    bool bad = false;
+    if (inf) {
+        bad = !x.is_zero() || odd;
+    } else {
+        // canonical: x < p
+        bool lt = false;
+        for (int t = 7; t >= 0; t--) {
+            if (x.l[t] != FqParams::MOD(t)) { lt = x.l[t] < FqParams::MOD(t); break; }
+        }
+        if (!lt) bad = true;
+        else {
+            const Fq xm = x.to_mont();
+            Fq three = Fq::one();
+            three = three + three + Fq::one();
+            const Fq rhs = xm.sqr() * xm + three;
+            Fq y = fq_sqrt_candidate(rhs);
+            if (!(y.sqr() == rhs)) bad = true;
+            else {
+                if ((y.from_mont().l[0] & 1u) != (odd ? 1u : 0u)) y = y.neg();
+                r.x = xm;
+                r.y = y;
+            }
+        }
+    }
+    if (bad) atomicAdd(invalid, 1ull);
+    r.store(out + i);
+}
+
 // s * p, s canonical (non-Montgomery) limbs; MSB-first double-and-add (doubling the identity is free)
 static __device__ __noinline__ XYZZ xyzz_scalar_mul(const XYZZ& p, const Fr& s) {
     XYZZ acc = XYZZ::identity();
@@ -162,6 +229,18 @@ size_t g1_count_off_curve_run(h2b_ctx* ctx, const void* d_points, size_t n) {
     H2B_CUDA(cudaMemcpyAsync(bounce, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     H2B_CUDA(cudaStreamSynchronize(ctx->stream));
     return bounce[0];
+}
+
+// bytes: n x 32 on the device; returns the number of invalid encodings (synchronises the stream)
+size_t g1_decompress_run(h2b_ctx* ctx, const void* d_bytes, size_t n, void* d_out_xy) {
+    if (n == 0) return 0;
+    unsigned long long* d_cnt = (unsigned long long*)ctx->get(WS_MISC, 8);
+    H2B_CUDA(cudaMemsetAsync(d_cnt, 0, 8, ctx->stream));
+    H2B_LAUNCH(ctx, k_g1_decompress, ceil_div(n, 128), 128, 0, (const uint8_t*)d_bytes, n, (Affine*)d_out_xy, d_cnt);
+    unsigned long long* bounce = (unsigned long long*)ctx->get_pinned(2, 4096);
+    H2B_CUDA(cudaMemcpyAsync(bounce, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (size_t)bounce[0];
 }
 
 }  // namespace h2b

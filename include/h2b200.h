@@ -110,6 +110,19 @@ int h2b_g1_check_on_curve(h2b_ctx* ctx, const uint64_t* points_xy, size_t n, siz
 int h2b_g1_check_on_curve_dev(h2b_ctx* ctx, const void* d_points_xy, size_t n, size_t* off_curve);
 int h2b_params_raw_view(const uint8_t* bytes, size_t len, uint32_t* k, size_t* g_offset, size_t* g_lagrange_offset,
                         size_t* g2_offset, size_t* s_g2_offset);
+/* SerdeFormat::Processed (what `ParamsKZG::write` emits by default and `gen_srs` caches as ./params/kzg_bn254_{k}.srs,
+ * halo2-base/src/utils/mod.rs:413-435): compressed G1 = 32 bytes, x little-endian, bit 7 of the last byte = point at
+ * infinity, bit 6 = parity of y.  h2b_g1_decompress: n encodings -> n affine points (Montgomery, identity (0,0)) through a
+ * square root in Fq per point; *invalid = encodings that are no point (x >= p, x^3 + 3 a non-residue, bad flags; their
+ * output is (0,0)).  h2b_params_processed_view: offsets of the image (u32 LE k, 2^k x 32 B g, 2^k x 32 B g_lagrange,
+ * 64 B g2, 64 B s_g2).  h2b_srs_read_processed: the device side of `ParamsKZG::read` — decompress the shard
+ * [begin, begin + count) (count = 0: everything) of both bases and build the SRS handle; H2B_ERR_ARG if the image is
+ * malformed or holds an invalid encoding. */
+int h2b_g1_decompress(h2b_ctx* ctx, const uint8_t* bytes, size_t n, uint64_t* out_xy, size_t* invalid);
+int h2b_g1_decompress_dev(h2b_ctx* ctx, const void* d_bytes, size_t n, void* d_out_xy, size_t* invalid);
+int h2b_params_processed_view(const uint8_t* bytes, size_t len, uint32_t* k, size_t* g_offset, size_t* g_lagrange_offset,
+                              size_t* g2_offset, size_t* s_g2_offset);
+int h2b_srs_read_processed(h2b_ctx* ctx, const uint8_t* bytes, size_t len, size_t begin, size_t count, h2b_srs** out);
 
 /* ---- MSM: replaces halo2curves-axiom 0.7.3 msm::best_multiexp(coeffs, bases) -> G1, as reached from
  *      ParamsKZG::commit / commit_lagrange inside create_proof ------------- */

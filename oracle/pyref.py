@@ -86,6 +86,34 @@ def g1_neg(a):
     return None if a is None else (a[0], (-a[1]) % P)
 
 
+def g1_compress(pt) -> bytes:
+    """halo2curves `G1Affine::to_bytes` as `ParamsKZG::write` emits it in SerdeFormat::Processed (reference call sites
+    halo2-base/src/utils/mod.rs:401-435; halo2curves-axiom 0.7.3 not vendored — flag positions recalled): 32 bytes, x
+    little-endian; last byte bit 7 = identity, bit 6 = parity of y."""
+    if pt is None:
+        return bytes(31) + bytes([0x80])
+    b = bytearray(pt[0].to_bytes(32, "little"))
+    b[31] |= (pt[1] & 1) << 6
+    return bytes(b)
+
+
+def g1_decompress(b: bytes):
+    """inverse of g1_compress; returns (point, ok).  y = (x^3 + 3)^((p+1)/4) since p = 3 mod 4."""
+    inf, odd = b[31] >> 7, (b[31] >> 6) & 1
+    x = int.from_bytes(b[:31] + bytes([b[31] & 0x3F]), "little")
+    if inf:
+        return None, (x == 0 and odd == 0)
+    if x >= P:
+        return None, False
+    rhs = (x * x * x + B) % P
+    y = pow(rhs, (P + 1) // 4, P)
+    if y * y % P != rhs:
+        return None, False
+    if (y & 1) != odd:
+        y = P - y
+    return (x, y), True
+
+
 def g1_mul(k: int, a):
     k %= R
     acc = None

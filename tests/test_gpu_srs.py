@@ -89,3 +89,54 @@ def test_two_routes_to_the_lagrange_basis_agree_at_2_16(ctx, h2b):
     b = ctx.g1_normalize(params.commit(coeffs).reshape(1, 12))
     assert np.array_equal(a, b)
     params.close()
+
+
+def test_g1_decompress_and_processed_params_image(ctx, h2b):
+    """SerdeFormat::Processed: the Fq square-root kernel against Python integers (both parities, identity, invalid encodings)
+    and the device side of `ParamsKZG::read` on a whole params image (halo2-base/src/utils/mod.rs:401-435)"""
+    from halo2_lib_b200._capi import lib
+    from util import limbs_to_ints
+    rng = np.random.default_rng(2900)
+    P = pyref.P
+    pts = [pyref.g1_mul(s, pyref.G1) for s in rand_ints(rng, 40, R)] + [None, pyref.G1, pyref.g1_neg(pyref.G1)]
+    enc = [pyref.g1_compress(p) for p in pts]
+    for e, p in zip(enc, pts):
+        assert pyref.g1_decompress(e) == (p, True)
+    # invalid encodings: x >= p, x^3 + 3 a non-residue, infinity flag with x != 0, infinity flag with the sign bit
+    nonres = next(x for x in range(2, 100) if pow((x ** 3 + 3) % P, (P - 1) // 2, P) != 1)
+    bad = [P.to_bytes(32, "little"), nonres.to_bytes(32, "little"), (5).to_bytes(31, "little") + bytes([0x80]), bytes(31) + bytes([0xC0])]
+    for e in bad:
+        assert pyref.g1_decompress(e)[1] is False
+    blob = np.frombuffer(b"".join(enc + bad), dtype=np.uint8).copy()
+    n = len(enc) + len(bad)
+    out = np.empty((n, 8), dtype=np.uint64)
+    inv = C.c_size_t()
+    ctx.check(lib.h2b_g1_decompress(ctx.h, C.c_void_p(blob.ctypes.data), n, C.c_void_p(out.ctypes.data), C.byref(inv)))
+    assert inv.value == len(bad)
+    assert np.array_equal(out[: len(enc)], affine_to_limbs(pts)) and not out[len(enc):].any()
+    # a whole image: k, g, g_lagrange, g2, s_g2 (G2 parts are opaque to this library)
+    k = 6
+    tau = rand_ints(rng, 1, R)[0]
+    g, gl = setup(ctx, tau, k)
+
+    def aff(arr):
+        v = [pyref.from_mont(x, P) for x in limbs_to_ints(arr.reshape(-1, 4))]
+        return [None if (v[2 * i] == 0 and v[2 * i + 1] == 0) else (v[2 * i], v[2 * i + 1]) for i in range(len(arr))]
+    image = (k).to_bytes(4, "little") + b"".join(pyref.g1_compress(p) for p in aff(g)) + b"".join(pyref.g1_compress(p) for p in aff(gl)) + bytes(128)
+    img = np.frombuffer(image, dtype=np.uint8).copy()
+    kk, og, ol = C.c_uint32(), C.c_size_t(), C.c_size_t()
+    assert lib.h2b_params_processed_view(C.c_void_p(img.ctypes.data), len(img), C.byref(kk), C.byref(og), C.byref(ol), None, None) == 0
+    assert (kk.value, og.value, ol.value) == (k, 4, 4 + 32 * (1 << k))
+    assert lib.h2b_params_processed_view(C.c_void_p(img.ctypes.data), len(img) - 1, C.byref(kk), None, None, None, None) == -1
+    hsrs = C.c_void_p()
+    ctx.check(lib.h2b_srs_read_processed(ctx.h, C.c_void_p(img.ctypes.data), len(img), 0, 0, C.byref(hsrs)))
+    sc = mont(rand_ints(rng, 1 << k, R), R)
+    for basis, bases in ((0, g), (1, gl)):
+        got = np.empty(12, dtype=np.uint64)
+        ctx.check(lib.h2b_msm_g1(ctx.h, hsrs, basis, C.c_void_p(sc.ctypes.data), 1 << k, C.c_void_p(got.ctypes.data)))
+        assert np.array_equal(ctx.g1_normalize(got.reshape(1, 12))[0], orc.msm_pippenger(sc, bases))
+    lib.h2b_srs_destroy(ctx.h, hsrs)
+    # a corrupted point makes the read fail (H2B_ERR_ARG), as ParamsKZG::read rejects it
+    img2 = img.copy()
+    img2[4:36] = np.frombuffer(nonres.to_bytes(32, "little"), dtype=np.uint8)
+    assert lib.h2b_srs_read_processed(ctx.h, C.c_void_p(img2.ctypes.data), len(img2), 0, 0, C.byref(hsrs)) == -1

@@ -69,3 +69,16 @@ def test_params_raw_view_is_host_only():
     assert lib.h2b_params_raw_view(C.c_void_p(blob.ctypes.data), len(blob) - 1, C.byref(kk), *[C.byref(x) for x in o]) == -1  # truncated
     blob[0] = 29
     assert lib.h2b_params_raw_view(C.c_void_p(blob.ctypes.data), len(blob), C.byref(kk), *[C.byref(x) for x in o]) == -1
+
+
+def test_compressed_point_roundtrip_python():
+    """SerdeFormat::Processed encoding restated in oracle/pyref.py: round trip, parity flag, invalid encodings"""
+    rng = np.random.default_rng(77)
+    for s in rand_ints(rng, 30, pyref.R):
+        p = pyref.g1_mul(s, pyref.G1)
+        e = pyref.g1_compress(p)
+        assert len(e) == 32 and (e[31] >> 6) & 1 == p[1] & 1 and e[31] >> 7 == 0
+        assert pyref.g1_decompress(e) == (p, True)
+        assert pyref.g1_decompress(pyref.g1_compress(pyref.g1_neg(p))) == (pyref.g1_neg(p), True)
+    assert pyref.g1_decompress(pyref.g1_compress(None)) == (None, True)
+    assert pyref.g1_decompress(pyref.P.to_bytes(32, "little"))[1] is False
