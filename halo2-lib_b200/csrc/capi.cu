@@ -208,6 +208,7 @@ int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value) {
         const std::string k(key);
         if (k == "msm.affine_levels") { H2B_REQUIRE(value >= -1 && value <= 3, "msm.affine_levels: -1 (default) .. 3"); ctx->opt_affine_levels = (int)value; }
         else if (k == "msm.affine_k") { H2B_REQUIRE(value == -1 || (value >= 8 && value <= 128 && value % 4 == 0), "msm.affine_k: multiple of 4 in [8, 128]"); ctx->opt_affine_k = (int)value; }
+        else if (k == "lookup.leftover_order") { H2B_REQUIRE(value == 0 || value == 1, "lookup.leftover_order: 0 (front to back) or 1 (zcash: from the back)"); ctx->opt_lookup_backward = (int)value; }
         else H2B_REQUIRE(false, "set_option: unknown key");
     });
 }

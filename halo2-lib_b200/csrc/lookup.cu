@@ -3,9 +3,15 @@
 // algorithm).  Given the compressed input column A and table column S over the usable rows u = n - (blinding + 1):
 //     A' = A sorted by Fr's `Ord` (integer order of the canonical value);
 //     S'[row] = A'[row]                         where A' starts a new run (first occurrence of the value),
-//     S'[row] = a left-over table value         elsewhere: the table values not consumed by a first occurrence, taken
-//                                               in ascending order and written to the repeated rows from the LAST one
-//                                               backwards (`repeated_input_rows.pop()` while iterating the BTreeMap).
+//     S'[row] = a left-over table value         elsewhere: the sorted table minus the first instance of every distinct
+//                                               input value, in ascending order.
+// WHICH repeated row receives which left-over value is not determined by the protocol, and the forks differ:
+//   * the sorted-table walk of PSE halo2 >= 2023 and the forks derived from it — which is what halo2-axiom 0.5.3 is
+//     recalled to carry (not vendored, cannot be confirmed here: DESIGN.md §2) — fills the unfilled rows FRONT TO BACK
+//     (two cursors over the sorted table and the distinct inputs): the default here;
+//   * zcash halo2 iterates a BTreeMap of left-over counts and pops the repeated rows from the BACK
+//     (`repeated_input_rows.pop()`): h2b_ctx_set_option("lookup.leftover_order", 1).
+// Either column satisfies the argument; only proof BYTES depend on the choice.
 // An input value that is not in the table is `Error::ConstraintSystemFailure` (H2B_ERR_UNSATISFIED here).
 //
 // Sorting 254-bit keys: LSD radix sort of a row permutation over the four 64-bit limbs of the canonical values with
@@ -97,11 +103,12 @@ __global__ void __launch_bounds__(256) k_lookup_rep_rows(const u32* __restrict__
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && rep[i]) rep_rows[rep_pos[i]] = i;
 }
-// S' : first occurrences copy A'; left-over number q (ascending) goes to the repeated row of rank R-1-q
+// S' : first occurrences copy A'; left-over number q (ascending) goes to the repeated row of rank q (front to back), or of
+// rank R-1-q when `backward` (the zcash order)
 __global__ void __launch_bounds__(256) k_lookup_fill(const uint64_t* __restrict__ a_sorted, const uint64_t* __restrict__ t_sorted,
                                                      const u32* __restrict__ rep, const u32* __restrict__ rep_pos, const u32* __restrict__ left,
                                                      const u32* __restrict__ left_pos, const u32* __restrict__ rep_rows, u32 n,
-                                                     uint64_t* __restrict__ s_out, u32* __restrict__ missing) {
+                                                     uint64_t* __restrict__ s_out, u32* __restrict__ missing, int backward) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u32 n_rep = rep_pos[n - 1] + rep[n - 1], n_left = left_pos[n - 1] + left[n - 1];
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(256) k_lookup_fill(const uint64_t* __restrict_
         return;
     }
     if (!rep[i]) Fr::load_nc(a_sorted + 4 * (size_t)i).store(s_out + 4 * (size_t)i);
-    if (left[i]) Fr::load_nc(t_sorted + 4 * (size_t)i).store(s_out + 4 * (size_t)rep_rows[n_rep - 1 - left_pos[i]]);
+    if (left[i]) Fr::load_nc(t_sorted + 4 * (size_t)i).store(s_out + 4 * (size_t)rep_rows[backward ? n_rep - 1 - left_pos[i] : left_pos[i]]);
 }
 
 // sorts one column: out = src sorted by canonical value, out_canon = the canonical values in that order
@@ -174,7 +181,7 @@ bool permute_expression_pair_run(h2b_ctx* ctx, const void* d_input, const void* 
     ctx->launches += 4;
     H2B_LAUNCH(ctx, k_lookup_rep_rows, ceil_div(n, 256), 256, 0, rep, rep_pos, n, rep_rows);
     H2B_LAUNCH(ctx, k_lookup_fill, ceil_div(n, 256), 256, 0, (const uint64_t*)d_permuted_input, t_sorted, rep, rep_pos, left, left_pos, rep_rows, n,
-               (uint64_t*)d_permuted_table, missing);
+               (uint64_t*)d_permuted_table, missing, ctx->opt_lookup_backward);
     u32* bounce = (u32*)ctx->get_pinned(0, 4096);
     H2B_CUDA(cudaMemcpyAsync(bounce, missing, 4, cudaMemcpyDeviceToHost, ctx->stream));
     H2B_CUDA(cudaStreamSynchronize(ctx->stream));

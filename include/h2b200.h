@@ -63,7 +63,9 @@ int h2b_ctx_side_end(h2b_ctx* ctx);
 int h2b_ctx_side_join(h2b_ctx* ctx);
 /* Tuning / experiment switches (results never depend on them).  Keys:
  *   "msm.affine_levels"  0..3 (-1 = default 0): batch-affine halving levels in front of the XYZZ bucket accumulation
- *   "msm.affine_k"       multiple of 4 in [8, 128] (-1 = default 32): pairs per thread and tile of those levels */
+ *   "msm.affine_k"       multiple of 4 in [8, 128] (-1 = default 32): pairs per thread and tile of those levels
+ * and one switch that selects between two equally valid outputs (see h2b_permute_expression_pair):
+ *   "lookup.leftover_order"  0 (default): left-over table values fill the repeated rows front to back; 1: from the back */
 int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value);
 /* Last error message of this context (or of the failed h2b_ctx_create when ctx == NULL). */
 const char* h2b_last_error(const h2b_ctx* ctx);
@@ -250,9 +252,11 @@ int h2b_grand_product_fr_dev(h2b_ctx* ctx, const void* d_f, const uint64_t start
 /* The lookup argument's permuted columns: halo2-axiom 0.5.3 plonk/lookup/prover.rs `permute_expression_pair` (not
  * vendored; restated).  input / table: the compressed expressions, 2^k rows (Lagrange form).  Over the usable rows
  * u = 2^k - (blinding_factors + 1): permuted_input = input sorted by Fr's Ord (canonical integer order);
- * permuted_table[row] = permuted_input[row] where a run starts, and the left-over table values — ascending — on the
- * repeated rows from the last one backwards.  Rows >= u of both outputs are NOT written (the prover puts its blinding
- * scalars there).  Outputs must not alias inputs.  H2B_ERR_UNSATISFIED when an input value is missing from the table.
+ * permuted_table[row] = permuted_input[row] where a run starts, and the left-over table values (the sorted table minus the
+ * first instance of every distinct input value) — ascending — on the repeated rows, front to back (the sorted-table walk
+ * of PSE halo2 and its forks, recalled for halo2-axiom 0.5.3) or, with option "lookup.leftover_order" = 1, from the last
+ * repeated row backwards (zcash halo2's BTreeMap + pop).  Both satisfy the argument; the choice only shows in the proof
+ * bytes.  Rows >= u of both outputs are NOT written (the prover puts its blinding scalars there).  Outputs must not alias inputs.  H2B_ERR_UNSATISFIED when an input value is missing from the table.
  * The `_dev` form synchronises the stream (it has to read the verdict). */
 int h2b_permute_expression_pair(h2b_ctx* ctx, const uint64_t* input, const uint64_t* table, uint32_t k, uint32_t blinding_factors,
                                 uint64_t* permuted_input, uint64_t* permuted_table);

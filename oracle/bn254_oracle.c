@@ -803,9 +803,13 @@ void orc_srs_setup(const u64 *tau, const u64 *base_xy, unsigned k, u64 *g_xy, u6
     }
     free(sc);
 }
-/* ---- lookup argument: halo2-axiom 0.5.3 plonk/lookup/prover.rs `permute_expression_pair` (not vendored), walked the
- * way the Rust code does: sort the inputs, count the table values in an ordered map, give every first occurrence its own
- * value, then hand the left-over table values (ascending) to the repeated rows popped from the back.
+/* ---- lookup argument: `permute_expression_pair` of plonk/lookup/prover.rs (halo2-axiom 0.5.3 is not vendored), walked the
+ * way the Rust code does, in the two variants that exist upstream:
+ *   zcash_order = 1  zcash halo2: sort the inputs, count the table values in an ordered map, give every first occurrence
+ *                    its own value, then hand the left-over table values (ascending) to the repeated rows popped from the back;
+ *   zcash_order = 0  PSE halo2 >= 2023 and the forks derived from it (recalled for halo2-axiom): sort inputs AND table, mark
+ *                    first occurrences, then walk the rows front to back with two cursors (distinct inputs / sorted table),
+ *                    skipping matched pairs and giving every unfilled row the next table value.
  * Returns 0, or -1 for Error::ConstraintSystemFailure (an input value that the table does not hold).  Only the usable
  * rows [0, 2^k - (blinding_factors + 1)) of the outputs are written. */
 static int canon_cmp(const void *a, const void *b) { /* Fr::cmp: canonical value, most significant limb first */
@@ -813,8 +817,8 @@ static int canon_cmp(const void *a, const void *b) { /* Fr::cmp: canonical value
     for (int i = 3; i >= 0; i--) { if (x[i] < y[i]) return -1; if (x[i] > y[i]) return 1; }
     return 0;
 }
-int orc_permute_expression_pair(const u64 *input, const u64 *table, unsigned k, unsigned blinding_factors, u64 *permuted_input,
-                                u64 *permuted_table) {
+static int permute_zcash(const u64 *input, const u64 *table, unsigned k, unsigned blinding_factors, u64 *permuted_input,
+                         u64 *permuted_table) {
     size_t usable = ((size_t)1 << k) - (blinding_factors + 1);
     u64 *a = (u64 *)malloc(usable * 32), *t = (u64 *)malloc(usable * 32);
     size_t *count = (size_t *)calloc(usable, sizeof(size_t)), *repeated = (size_t *)malloc(usable * sizeof(size_t));
@@ -848,6 +852,51 @@ int orc_permute_expression_pair(const u64 *input, const u64 *table, unsigned k, 
     if (rc == 0 && n_rep != 0) rc = -1; /* assert!(repeated_input_rows.is_empty()) */
     free(a); free(t); free(count); free(repeated);
     return rc;
+}
+static int permute_sorted_table(const u64 *input, const u64 *table, unsigned k, unsigned blinding_factors, u64 *permuted_input,
+                                u64 *permuted_table) {
+    size_t usable = ((size_t)1 << k) - (blinding_factors + 1);
+    u64 *a = (u64 *)malloc(usable * 32), *t = (u64 *)malloc(usable * 32), *uniq = (u64 *)malloc(usable * 32);
+    unsigned char *filled = (unsigned char *)calloc(usable, 1);
+    for (size_t i = 0; i < usable; i++) { f_from_mont(&FR, a + 4 * i, input + 4 * i); f_from_mont(&FR, t + 4 * i, table + 4 * i); }
+    qsort(a, usable, 32, canon_cmp); /* permuted_input_expression.sort() */
+    qsort(t, usable, 32, canon_cmp); /* sorted_table_coeffs.sort() */
+    size_t n_uniq = 0;
+    for (size_t row = 0; row < usable; row++) { /* first occurrences: *table_value = Some(*input_value) */
+        f_to_mont(&FR, permuted_input + 4 * row, a + 4 * row);
+        if (row == 0 || canon_cmp(a + 4 * row, a + 4 * (row - 1)) != 0) {
+            memcpy(permuted_table + 4 * row, permuted_input + 4 * row, 32);
+            filled[row] = 1;
+            memcpy(uniq + 4 * n_uniq++, a + 4 * row, 32);
+        }
+    }
+    int rc = 0;
+    size_t iu = 0, it = 0;
+    for (size_t row = 0; row < usable && rc == 0; row++) {
+        while (iu < n_uniq && it < usable && canon_cmp(uniq + 4 * iu, t + 4 * it) == 0) { iu++; it++; }
+        if (!filled[row]) {
+            /* a distinct input the table does not hold leaves the cursors stuck: the Rust code would index out of
+             * range / build an unsatisfiable column; reported as ConstraintSystemFailure like the zcash walk */
+            if (it >= usable || (iu < n_uniq && canon_cmp(uniq + 4 * iu, t + 4 * it) < 0)) { rc = -1; break; }
+            f_to_mont(&FR, permuted_table + 4 * row, t + 4 * it);
+            it++;
+        }
+    }
+    if (rc == 0) {
+        while (iu < n_uniq && it < usable && canon_cmp(uniq + 4 * iu, t + 4 * it) == 0) { iu++; it++; }
+        if (iu != n_uniq || it != usable) rc = -1;
+    }
+    free(a); free(t); free(uniq); free(filled);
+    return rc;
+}
+int orc_permute_expression_pair_ordered(const u64 *input, const u64 *table, unsigned k, unsigned blinding_factors, u64 *permuted_input,
+                                        u64 *permuted_table, int zcash_order) {
+    return zcash_order ? permute_zcash(input, table, k, blinding_factors, permuted_input, permuted_table)
+                       : permute_sorted_table(input, table, k, blinding_factors, permuted_input, permuted_table);
+}
+int orc_permute_expression_pair(const u64 *input, const u64 *table, unsigned k, unsigned blinding_factors, u64 *permuted_input,
+                                u64 *permuted_table) {
+    return permute_sorted_table(input, table, k, blinding_factors, permuted_input, permuted_table);
 }
 /* EvaluationDomain::divide_by_vanishing_poly (halo2-axiom 0.5.3 poly/domain.rs, restated): the table of
  * t(zeta * extended_omega^i) = zeta^n * (extended_omega^n)^i - 1 is built by walking until it repeats, inverted, and

@@ -281,12 +281,14 @@ def poly_lincomb(polys, scalars):
     return out
 
 
-def permute_expression_pair(input_col, table_col, k, blinding_factors):
-    """returns (rc, permuted_input, permuted_table); rows >= usable are zero-filled here (the prover writes randoms)"""
+def permute_expression_pair(input_col, table_col, k, blinding_factors, zcash_order=False):
+    """returns (rc, permuted_input, permuted_table); rows >= usable are zero-filled here (the prover writes randoms).
+    zcash_order: left-over table values to the repeated rows from the back (zcash halo2) instead of front to back"""
     a = np.ascontiguousarray(input_col, dtype=np.uint64).reshape(-1, 4)
     t = np.ascontiguousarray(table_col, dtype=np.uint64).reshape(-1, 4)
     pa, pt = np.zeros_like(a), np.zeros_like(t)
-    rc = lib().orc_permute_expression_pair(_p(a), _p(t), C.c_uint(k), C.c_uint(blinding_factors), _p(pa), _p(pt))
+    rc = lib().orc_permute_expression_pair_ordered(_p(a), _p(t), C.c_uint(k), C.c_uint(blinding_factors), _p(pa), _p(pt),
+                                                   C.c_int(1 if zcash_order else 0))
     return rc, pa, pt
 
 

@@ -341,8 +341,10 @@ def graph_row(program, n_calc, result, constants, rotations, fixed, advice, inst
     return fetch(result)
 
 
-def permute_expression_pair(inputs, table):
-    """usable rows only, plain integers; returns (A', S') or None for ConstraintSystemFailure"""
+def permute_expression_pair(inputs, table, zcash_order=False):
+    """usable rows only, plain integers; returns (A', S') or None for ConstraintSystemFailure.  Left-over table values
+    (ascending) fill the repeated rows front to back (PSE / axiom sorted-table walk, the default) or, with zcash_order,
+    from the last repeated row backwards (zcash halo2: BTreeMap + pop)."""
     a = sorted(inputs)
     left = {}
     for v in table:
@@ -356,8 +358,10 @@ def permute_expression_pair(inputs, table):
             left[v] -= 1
         else:
             repeated.append(row)
-    for v in sorted(left):
-        for _ in range(left[v]):
-            s_perm[repeated.pop()] = v
-    assert not repeated
+    leftovers = [v for v in sorted(left) for _ in range(left[v])]
+    if len(leftovers) != len(repeated):
+        return None
+    rows = reversed(repeated) if zcash_order else repeated
+    for row, v in zip(rows, leftovers):
+        s_perm[row] = v
     return a, s_perm

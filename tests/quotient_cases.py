@@ -82,7 +82,7 @@ def lookup_case(k: int, blinding_factors: int, beta: int, gamma: int, seed: int,
         if i == 0 or a_perm[i] != a_perm[i - 1]:
             s_perm.append(a_perm[i])
         else:
-            s_perm.append(leftover.pop())
+            s_perm.append(leftover.pop(0))
     z = [1]
     for i in range(u):
         num = (inputs[i] + beta) * (table[i] + gamma) % R

@@ -340,6 +340,29 @@ def test_permute_expression_pair(ctx, h2b, kind, k):
     assert not pa[u:].any() and not pt[u:].any()  # blinding rows are the caller's
 
 
+def test_permute_expression_pair_zcash_order_option(h2b):
+    """option "lookup.leftover_order" = 1: left-over table values go to the repeated rows from the back (zcash halo2)"""
+    from test_oracle_quotient import lookup_columns
+    c = h2b.Context(0)
+    try:
+        c.set_option("lookup.leftover_order", 1)
+        for kind, k in (("range", 8), ("dup_table", 9), ("wide", 10)):
+            bf = 5
+            rng = np.random.default_rng(2250 + k)
+            inputs, table = lookup_columns(rng, k, bf, kind)
+            pad = rand_ints(rng, bf + 1, R)
+            A, T = mont(inputs + pad, R), mont(table + pad, R)
+            pa, pt = h2b.permute_expression_pair(c, A, T, k, bf)
+            rc, wa, wt = orc.permute_expression_pair(A, T, k, bf, zcash_order=True)
+            assert rc == 0 and np.array_equal(pa, wa) and np.array_equal(pt, wt)
+        c.set_option("lookup.leftover_order", 0)
+        pa, pt = h2b.permute_expression_pair(c, A, T, k, bf)
+        rc, wa, wt = orc.permute_expression_pair(A, T, k, bf)
+        assert np.array_equal(pa, wa) and np.array_equal(pt, wt)
+    finally:
+        c.close()
+
+
 def test_permute_expression_pair_missing_value_and_bad_arguments(ctx, h2b):
     k, bf = 8, 5
     u = (1 << k) - (bf + 1)

@@ -173,6 +173,28 @@ def lookup_columns(rng, k, bf, kind):
     return inputs, table
 
 
+@pytest.mark.parametrize("kind", ["range", "dup_table", "wide", "all_same"])
+def test_permute_expression_pair_both_upstream_orders(kind):
+    """the two walks that exist upstream (zcash: BTreeMap + pop from the back; PSE / axiom: two cursors front to back) give
+    the same A', the same multiset on the repeated rows, and mirror-image orders there; the C walks agree with the
+    closed forms in pyref for both"""
+    k, bf = 7, 5
+    rng = np.random.default_rng(48)
+    u = (1 << k) - (bf + 1)
+    inputs, table = lookup_columns(rng, k, bf, kind)
+    pad = rand_ints(rng, bf + 1, R)
+    A, T = mont(inputs + pad, R), mont(table + pad, R)
+    rc0, pa0, pt0 = orc.permute_expression_pair(A, T, k, bf)
+    rc1, pa1, pt1 = orc.permute_expression_pair(A, T, k, bf, zcash_order=True)
+    assert rc0 == 0 and rc1 == 0 and np.array_equal(pa0, pa1)
+    w0, w1 = pyref.permute_expression_pair(inputs, table), pyref.permute_expression_pair(inputs, table, zcash_order=True)
+    assert unmont(pt0[:u], R) == w0[1] and unmont(pt1[:u], R) == w1[1]
+    rep = [i for i in range(u) if i > 0 and w0[0][i] == w0[0][i - 1]]
+    assert [w0[1][i] for i in rep] == [w1[1][i] for i in rep][::-1]
+    if len(set(w0[1][i] for i in rep)) > 1:
+        assert w0[1] != w1[1]
+
+
 @pytest.mark.parametrize("kind", ["range", "dup_table", "wide", "all_same", "perm"])
 def test_permute_expression_pair_vs_python(kind):
     k, bf = 7, 5
