@@ -1027,6 +1027,108 @@ def run_b200(args):
         rig.dist.destroy_process_group()
 
 
+def run_single_process(args):
+    """ONE process drives --gpus N devices through a device-group context (h2b_ctx_create_multi): the host-buffer schedule
+    (assignment, per-phase h2b_msm_g1_batch over the internally sharded SRS, batched transforms dealt over the devices).
+    Every call is synchronous, so the CUDA events on the lead device's stream bracket all devices' work."""
+    import ctypes as C
+    import torch
+    import halo2_lib_b200 as h
+    from halo2_lib_b200._capi import lib
+    N = args.gpus
+    sched = Schedule(args.config, args.k)
+    assert sched.A == 1 and sched.L == 0, "--single-process covers the single-advice-column shapes (configs 1, 3, 5)"
+    k, n, ext_k = sched.k, sched.n, sched.ext_k
+    torch.cuda.set_device(0)
+    grp = h.Context(list(range(N)))
+    stream = torch.cuda.Stream(device=0)
+    torch.cuda.set_stream(stream)
+    grp.set_stream(stream.cuda_stream)
+    vp = C.c_void_p
+    rng = np.random.default_rng(0xB2000000 + 97 * sched.cfg_id + k)
+    gbase = np.array([0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f,
+                      0xa6ba871b8b1e1b3a, 0x14f1d651eb8e167b, 0xccdd46def0f28c58, 0x1c14ef83340fbe5e], dtype=np.uint64)
+    host_bases = {}
+    for name, (a0, d) in BASES.items():
+        sc = np.zeros((n, 4), dtype=np.uint64)
+        sc[:, 0] = (a0 + d * np.arange(n, dtype=np.uint64)).astype(np.uint64)
+        host_bases[name] = grp.g1_fixed_base_mul(gbase, grp.field_op(1, 5, sc))
+    params = h.ParamsKZG(grp, k, g=host_bases["monomial"], g_lagrange=host_bases["lagrange"])
+    del host_bases
+    pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).pin_memory()
+    usable = n - UNUSABLE_ROWS
+    n_cells = usable - 5
+    v_host = grp.field_op(1, 5, witness_like(rng, n_cells))
+    vcol = pin(v_host)
+    acol = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    cols, expect = [], []
+    basis_id = [0 if b == "monomial" else 1 for b, _, _ in sched.msm]
+    for j, (basis, cls, tag) in enumerate(sched.msm):
+        a0, d = BASES[basis]
+        if tag == "advice":
+            full = np.zeros((n, 4), dtype=np.uint64)
+            full[:n_cells] = v_host
+            cols.append(acol)
+        else:
+            full = uniform_residues(rng, n) if cls == "uniform" else grp.field_op(1, 5, witness_like(rng, n))
+            cols.append(pin(full))
+        expect.append(ec_mul_g(progression_dot(full, a0, d, 0) * MONT_RINV_R % R_MOD))
+    polys = [pin(uniform_residues(rng, n)) for _ in range(sched.n_poly)]
+    exts = [torch.empty((1 << ext_k, 4), dtype=torch.int64).pin_memory() for _ in range(sched.n_poly)]
+    outs = np.zeros((len(sched.msm), 12), dtype=np.uint64)
+
+    def step():
+        grp.check(lib.h2b_assign_columns(grp.h, vp(vcol.data_ptr()), n_cells, None, 0, k, 1, vp(acol.data_ptr())))
+        for pi, phase in enumerate(sched.phases):
+            if pi == sched.h_phase:
+                pa = (C.c_void_p * sched.n_poly)(*[p.data_ptr() for p in polys])
+                pe = (C.c_void_p * sched.n_poly)(*[e.data_ptr() for e in exts])
+                grp.check(lib.h2b_lagrange_to_coeff_and_extended_batch(grp.h, pa, sched.n_poly, k, ext_k, pe))
+                grp.check(lib.h2b_extended_to_coeff(grp.h, vp(exts[0].data_ptr()), ext_k))
+            m = len(phase)
+            ptrs = (C.c_void_p * m)(*[cols[j].data_ptr() for j in phase])
+            bs = (C.c_int * m)(*[basis_id[j] for j in phase])
+            out = np.empty((m, 12), dtype=np.uint64)
+            grp.check(lib.h2b_msm_g1_batch(grp.h, params.h, bs, ptrs, m, n, vp(out.ctypes.data)))
+            outs[phase] = out
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = grp.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = grp.kernel_launches - l0
+    ok = sum(1 for j in range(len(sched.msm)) if point_matches(outs[j], expect[j]))
+    h2d = n_cells * 32 + len(sched.msm) * n * 32 + sched.n_poly * n * 32 + (1 << ext_k) * 32
+    d2h = n * 32 + len(sched.msm) * 96 + sched.n_poly * (n + (1 << ext_k)) * 32 + (1 << ext_k) * 32
+    cfg = sched.describe(N)
+    cfg["parallelism"] = f"ONE process, {N} devices through a device-group context (h2b_ctx_create_multi): SRS sharded inside h2b_srs_upload, partial sums combined by the fused all-reduce kernel over in-process peer mappings, transforms dealt round-robin"
+    cfg["overlap"] = "strictly sequential host calls (no side thread); uploads pipelined against the kernels inside each call"
+    value = sched.pairs / (ms / 1e3)
+    line = {"metric": metric_name(sched), "value": value, "unit": "G1 pairs/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)",
+            "data": "synthetic", "config": cfg, "single_process": True,
+            "e2e": {"value": value, "unit": "G1 pairs/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "h2b_assign_columns / h2b_msm_g1_batch / h2b_lagrange_to_coeff_and_extended_batch / h2b_extended_to_coeff on a device-group context, pinned HOST buffers in and out"},
+            "gpu_launches": launches, "verified": {"msm_e2e": ok, "of": len(sched.msm)}, "clocks": clocks,
+            "roofline": None, "cpu_baseline": None}
+    params.close()
+    grp.close()
+    if ok != len(sched.msm):
+        print("VERIFICATION FAILED: " + json.dumps(line["verified"]), file=sys.stderr)
+        sys.exit(3)
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1038,10 +1140,13 @@ def main():
     ap.add_argument("--sweep", default="1,2,4,5", help="other BASELINE configs run as extras (comma list, or 'none')")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--inject-fault", default=None, choices=["skip_allreduce"], help="testing: break the multi-GPU exchange; the run must exit 3")
+    ap.add_argument("--single-process", action="store_true", help="one process drives --gpus N devices through a device-group context (no torchrun)")
     args = ap.parse_args()
     args.sweep_ids = [] if args.sweep in ("none", "") else [int(x) for x in args.sweep.split(",")]
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_b200(args)
 

@@ -41,6 +41,8 @@ _vpp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "h2b_version": (C.c_char_p, []),
     "h2b_ctx_create": (_int, [_int, C.POINTER(_vp)]),
+    "h2b_ctx_create_multi": (_int, [C.POINTER(_int), _int, C.POINTER(_vp)]),
+    "h2b_ctx_device_count": (_int, [_vp]),
     "h2b_ctx_destroy": (None, [_vp]),
     "h2b_ctx_set_stream": (_int, [_vp, _vp]),
     "h2b_ctx_synchronize": (_int, [_vp]),

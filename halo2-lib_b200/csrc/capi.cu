@@ -78,6 +78,22 @@ static int guarded(h2b_ctx* ctx, Fn&& body) {
     }
 }
 
+// ---- device group helpers (h2b_ctx_create_multi): run `fn(member, index)` with the member's device current
+template <class Fn>
+static void group_each(h2b_ctx* ctx, Fn&& fn) {
+    for (size_t i = 0; i < ctx->members.size(); i++) {
+        H2B_CUDA(cudaSetDevice(ctx->members[i]->device));
+        fn(ctx->members[i], i);
+    }
+    H2B_CUDA(cudaSetDevice(ctx->device));
+}
+template <class T>
+static std::vector<T> every_gth(T const* v, size_t m, size_t g, size_t G) {
+    std::vector<T> r;
+    for (size_t j = g; j < m; j += G) r.push_back(v[j]);
+    return r;
+}
+
 extern "C" {
 
 const char* h2b_version(void) { return "h2b200 0.1.0 (sm_100a)"; }
@@ -136,8 +152,55 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
     }
 }
 
+// One process, several GPUs (h2b_ctx_create(const int* dev_ids, int n_dev, ...)): the returned handle is
+// an ordinary context on dev_ids[0] that additionally owns one private context per further device.  h2b_srs_upload shards
+// the bases over the devices by contiguous index range, the host-pointer MSM entry points commit every shard on its own
+// device and combine the partial sums with the fused all-reduce kernel over in-process peer mappings (no IPC, no NCCL),
+// the batched transform entry points deal the polynomials round-robin.  Everything else runs on dev_ids[0].
+int h2b_ctx_create_multi(const int* dev_ids, int n_dev, h2b_ctx** out) {
+    if (!out || !dev_ids || n_dev < 1 || n_dev > 16) return H2B_ERR_ARG;
+    *out = nullptr;
+    std::vector<h2b_ctx*> made;
+    for (int i = 0; i < n_dev; i++) {
+        for (int j = 0; j < i; j++)
+            if (dev_ids[j] == dev_ids[i]) {
+                std::lock_guard<std::mutex> lock(g_create_mu);
+                g_create_error = "ctx_create_multi: duplicate device id";
+                for (auto* c : made) h2b_ctx_destroy(c);
+                return H2B_ERR_ARG;
+            }
+        h2b_ctx* c = nullptr;
+        int rc = h2b_ctx_create(dev_ids[i], &c);
+        if (rc != H2B_OK) {
+            for (auto* m : made) h2b_ctx_destroy(m);
+            return rc;
+        }
+        made.push_back(c);
+    }
+    h2b_ctx* lead = made[0];
+    lead->members = made;
+    if (n_dev > 1) {
+        int rc = guarded(lead, [&] { peer_connect_local(lead->members); });
+        if (rc != H2B_OK) {
+            std::lock_guard<std::mutex> lock(g_create_mu);
+            g_create_error = lead->err;
+            lead->members.clear();
+            for (auto* m : made) h2b_ctx_destroy(m);
+            return rc;
+        }
+    }
+    *out = lead;
+    return H2B_OK;
+}
+int h2b_ctx_device_count(const h2b_ctx* ctx) { return ctx ? (int)(ctx->members.empty() ? 1 : ctx->members.size()) : 0; }
+
 void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->members.size() > 1) {  // a device group: the private member contexts go first
+        std::vector<h2b_ctx*> others(ctx->members.begin() + 1, ctx->members.end());
+        ctx->members.clear();
+        for (auto* m : others) h2b_ctx_destroy(m);
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ntt_free_plans(ctx);
@@ -227,7 +290,12 @@ const char* h2b_last_error(const h2b_ctx* ctx) {
     }
     return tl.c_str();
 }
-uint64_t h2b_kernel_launches(const h2b_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t h2b_kernel_launches(const h2b_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (size_t i = 1; i < ctx->members.size(); i++) n += ctx->members[i]->launches;
+    return n;
+}
 
 // ------------------------------------------------------------------------------------------------ profiling
 int h2b_profile_enable(h2b_ctx* ctx, const char* filter) {
@@ -291,6 +359,46 @@ int h2b_srs_upload(h2b_ctx* ctx, const uint64_t* g, const uint64_t* g_lagrange, 
                    h2b_srs** out) {
     return guarded(ctx, [&] {
         H2B_REQUIRE(k <= 27 && count >= 1 && begin + count <= ((size_t)1 << k), "srs: bad shard");
+        if (ctx->members.size() > 1) {  // device group: contiguous index ranges, one per device
+            H2B_REQUIRE(out, "srs: null output handle");
+            const size_t G = ctx->members.size();
+            H2B_REQUIRE(count >= G, "srs: fewer bases than devices");
+            h2b_srs* top = new h2b_srs();
+            top->k = k;
+            top->begin = begin;
+            top->count = count;
+            try {
+                group_each(ctx, [&](h2b_ctx* mb, size_t i) {
+                    const size_t lo = begin + count * i / G, hi = begin + count * (i + 1) / G;
+                    const uint64_t* host[2] = {g, g_lagrange};
+                    void* dev[2] = {nullptr, nullptr};
+                    int slot[2] = {WS_BASES, WS_MISC2};
+                    for (int b = 0; b < 2; b++) {
+                        if (!host[b]) continue;
+                        dev[b] = mb->get(slot[b], (hi - lo) * 64);
+                        H2B_CUDA(cudaMemcpyAsync(dev[b], host[b] + 8 * lo, (hi - lo) * 64, cudaMemcpyHostToDevice, mb->stream));
+                    }
+                    h2b_srs* part = nullptr;
+                    srs_build(mb, dev[0], dev[1], k, lo, hi - lo, &part);
+                    top->parts.push_back(part);
+                });
+            } catch (...) {
+                cudaSetDevice(ctx->device);
+                for (size_t i = 0; i < top->parts.size(); i++) {
+                    cudaSetDevice(ctx->members[i]->device);
+                    for (auto& t : top->parts[i]->table)
+                        if (t) cudaFree(t);
+                    delete top->parts[i];
+                }
+                cudaSetDevice(ctx->device);
+                delete top;
+                throw;
+            }
+            top->c = top->parts[0]->c;
+            top->W = top->parts[0]->W;
+            *out = top;
+            return;
+        }
         const uint64_t* host[2] = {g, g_lagrange};
         void* dev[2] = {nullptr, nullptr};
         int slot[2] = {WS_BASES, WS_MISC2};
@@ -314,6 +422,19 @@ int h2b_srs_info(const h2b_srs* srs, int* window_bits, int* windows) {
 }
 void h2b_srs_destroy(h2b_ctx* ctx, h2b_srs* srs) {
     if (!srs) return;
+    if (!srs->parts.empty() && ctx && ctx->members.size() == srs->parts.size()) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        for (size_t i = 0; i < srs->parts.size(); i++) {
+            cudaSetDevice(ctx->members[i]->device);
+            cudaDeviceSynchronize();
+            for (auto& t : srs->parts[i]->table)
+                if (t) cudaFree(t);
+            delete srs->parts[i];
+        }
+        cudaSetDevice(ctx->device);
+        delete srs;
+        return;
+    }
     if (ctx) {
         std::lock_guard<std::mutex> lock(ctx->mu);
         cudaSetDevice(ctx->device);
@@ -361,10 +482,10 @@ int h2b_msm_g1_batch_dev(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, con
 // host columns -> m commitments on the host.  Uploads run on the copy stream into per-lane staging buffers; lane l's MSM
 // waits for its upload and releases the buffer as soon as the scatter pass has consumed it.  `reduce`: combine the
 // partial sums of all connected GPUs with the fused NVLink all-reduce kernel before the one device-to-host copy.
-static void msm_batch_host(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
-                           uint64_t* out_xyz, bool reduce) {
-    H2B_REQUIRE(basis && scalars && out_xyz, "msm: null pointer");
-    if (m == 0) return;
+// Enqueue only: the m partial commitments of this context's shard end up in its WS_OUT buffer (returned), lanes joined
+// onto the context's stream.  `row0`: first row of the shard inside the caller's columns.
+static void* msm_batch_enqueue(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
+                               size_t row0) {
     // validate everything before any stream is forked (a throw after the fork would leave the lanes unjoined)
     std::vector<const void*> tables(m);
     for (size_t j = 0; j < m; j++) {
@@ -380,7 +501,6 @@ static void msm_batch_host(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, c
     }
     ctx->cur_lane = 0;
     void* d_out = ctx->get(WS_OUT, m * 96);
-    uint64_t* h_out = (uint64_t*)ctx->get_pinned(0, m * 96);
     cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
     H2B_CUDA(cudaEventRecord(ctx->fork_ev, ks));
     H2B_CUDA(cudaStreamWaitEvent(cs, ctx->fork_ev, 0));
@@ -396,19 +516,48 @@ static void msm_batch_host(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, c
             }
         }
     };
-    {
-        Join join{ctx, ks, nl};
-        for (size_t j = 0; j < m; j++) {
-            const int l = (int)(j % nl);
-            if (j >= (size_t)nl) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->lane_consumed[l], 0));
-            H2B_CUDA(cudaMemcpyAsync(stage[l], scalars[j], n * 32, cudaMemcpyHostToDevice, cs));
-            H2B_CUDA(cudaEventRecord(ctx->lane_ready[l], cs));
-            H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_ready[l], 0));
-            ctx->stream = ctx->lane_stream[l];
-            ctx->cur_lane = l;
-            msm_run(ctx, tables[j], n, srs->c, srs->W, srs->W, stage[l], (char*)d_out + 96 * j, ctx->lane_consumed[l]);
-        }
+    Join join{ctx, ks, nl};
+    for (size_t j = 0; j < m; j++) {
+        const int l = (int)(j % nl);
+        if (j >= (size_t)nl) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->lane_consumed[l], 0));
+        H2B_CUDA(cudaMemcpyAsync(stage[l], scalars[j] + 4 * row0, n * 32, cudaMemcpyHostToDevice, cs));
+        H2B_CUDA(cudaEventRecord(ctx->lane_ready[l], cs));
+        H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_ready[l], 0));
+        ctx->stream = ctx->lane_stream[l];
+        ctx->cur_lane = l;
+        msm_run(ctx, tables[j], n, srs->c, srs->W, srs->W, stage[l], (char*)d_out + 96 * j, ctx->lane_consumed[l]);
     }
+    return d_out;
+}
+// host columns -> m commitments on the host.  Uploads run on the copy stream into per-lane staging buffers; lane l's MSM
+// waits for its upload and releases the buffer as soon as the scatter pass has consumed it.  `reduce`: combine the
+// partial sums of all connected GPUs with the fused NVLink all-reduce kernel before the one device-to-host copy.
+// On a device group (h2b_ctx_create_multi) the SRS handle is sharded over the devices: every device commits its row range
+// of every column, the partial sums meet in the same all-reduce kernel over in-process peer mappings.
+static void msm_batch_host(h2b_ctx* ctx, const h2b_srs* srs, const int* basis, const uint64_t* const* scalars, size_t m, size_t n,
+                           uint64_t* out_xyz, bool reduce) {
+    H2B_REQUIRE(basis && scalars && out_xyz, "msm: null pointer");
+    H2B_REQUIRE(srs, "msm: null SRS handle");
+    if (m == 0) return;
+    uint64_t* h_out = (uint64_t*)ctx->get_pinned(0, m * 96);
+    if (!srs->parts.empty()) {
+        H2B_REQUIRE(srs->parts.size() == ctx->members.size(), "msm: this SRS handle belongs to another device group");
+        H2B_REQUIRE(n == srs->count, "msm: scalar count must equal the SRS size");
+        std::vector<void*> d_outs(ctx->members.size());
+        group_each(ctx, [&](h2b_ctx* mb, size_t g) {
+            const h2b_srs* part = srs->parts[g];
+            d_outs[g] = msm_batch_enqueue(mb, part, basis, scalars, m, part->count, part->begin - srs->begin);
+        });
+        group_each(ctx, [&](h2b_ctx* mb, size_t g) {
+            for (size_t lo = 0; lo < m; lo += 16) peer_allreduce(mb, (char*)d_outs[g] + 96 * lo, m - lo < 16 ? m - lo : 16);
+        });
+        H2B_CUDA(cudaMemcpyAsync(h_out, d_outs[0], m * 96, cudaMemcpyDeviceToHost, ctx->stream));
+        group_each(ctx, [&](h2b_ctx* mb, size_t) { H2B_CUDA(cudaStreamSynchronize(mb->stream)); });
+        memcpy(out_xyz, h_out, m * 96);
+        return;
+    }
+    void* d_out = msm_batch_enqueue(ctx, srs, basis, scalars, m, n, 0);
+    cudaStream_t ks = ctx->stream;
     if (reduce && peer_connected(ctx))
         for (size_t lo = 0; lo < m; lo += 16) peer_allreduce(ctx, (char*)d_out + 96 * lo, m - lo < 16 ? m - lo : 16);
     H2B_CUDA(cudaMemcpyAsync(h_out, d_out, m * 96, cudaMemcpyDeviceToHost, ks));
@@ -580,8 +729,13 @@ int h2b_coeff_to_extended(h2b_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs,
 // m transforms of one kind through three rotating device buffers: the upload of column i+1 (copy stream) and the
 // download of column i-1 (second copy stream) overlap the kernels of column i (context stream).
 // mode: 1 lagrange_to_coeff, 2 coeff_to_lagrange, 3 extended_to_coeff (in place, n_in = 2^log_n), 4 coeff_to_extended.
+static void ntt_batch_finish(h2b_ctx* ctx) {
+    H2B_CUDA(cudaStreamSynchronize(ctx->copy_stream2));
+    H2B_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+// finish = false: enqueue only (the device group enqueues on every device before it waits for any)
 static void ntt_batch_host(h2b_ctx* ctx, int mode, const uint64_t* const* in, uint64_t* const* out, size_t m, size_t n_in,
-                           uint32_t log_n) {
+                           uint32_t log_n, bool finish = true) {
     H2B_REQUIRE(in && out, "ntt batch: null pointer");
     H2B_REQUIRE(log_n <= 28 && n_in <= ((size_t)1 << log_n), "ntt batch: sizes out of range");
     if (m == 0) return;
@@ -612,12 +766,12 @@ static void ntt_batch_host(h2b_ctx* ctx, int mode, const uint64_t* const* in, ui
         H2B_CUDA(cudaMemcpyAsync(out[i], buf[b], bytes, cudaMemcpyDeviceToHost, down));
         H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][2], down));
     }
-    H2B_CUDA(cudaStreamSynchronize(down));
-    H2B_CUDA(cudaStreamSynchronize(ks));
+    if (finish) ntt_batch_finish(ctx);
 }
 // lagrange_to_coeff followed by coeff_to_extended for m columns, fused: the coefficients go up once, stay on the device
 // for the coset transform, and both results come down on the second copy stream while the next column computes.
-static void ntt_fused_batch_host(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k, uint32_t ext_k, uint64_t* const* ext_out) {
+static void ntt_fused_batch_host(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k, uint32_t ext_k, uint64_t* const* ext_out,
+                                 bool finish = true) {
     H2B_REQUIRE(a && ext_out, "ntt batch: null pointer");
     H2B_REQUIRE(k <= ext_k && ext_k <= 28, "ntt batch: sizes out of range");
     if (m == 0) return;
@@ -652,22 +806,55 @@ static void ntt_fused_batch_host(h2b_ctx* ctx, uint64_t* const* a, size_t m, uin
         H2B_CUDA(cudaMemcpyAsync(ext_out[i], big[b], ne * 32, cudaMemcpyDeviceToHost, down));
         H2B_CUDA(cudaEventRecord(ctx->pipe_ev[b][2], down));
     }
-    H2B_CUDA(cudaStreamSynchronize(down));
-    H2B_CUDA(cudaStreamSynchronize(ks));
+    if (finish) ntt_batch_finish(ctx);
+}
+// ---- device group: polynomial j goes to device j mod G ("one column polynomial per device"); every device
+// runs its own upload / transform / download pipeline, all enqueued before the first wait
+static void group_ntt_batch(h2b_ctx* ctx, int mode, const uint64_t* const* in, uint64_t* const* out, size_t m, size_t n_in, uint32_t log_n) {
+    H2B_REQUIRE(in && out, "ntt batch: null pointer");
+    const size_t G = ctx->members.size();
+    group_each(ctx, [&](h2b_ctx* mb, size_t g) {
+        auto vi = every_gth(in, m, g, G);
+        auto vo = every_gth(out, m, g, G);
+        ntt_batch_host(mb, mode, vi.data(), vo.data(), vi.size(), n_in, log_n, false);
+    });
+    group_each(ctx, [&](h2b_ctx* mb, size_t) { ntt_batch_finish(mb); });
+}
+static void group_ntt_fused_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k, uint32_t ext_k, uint64_t* const* ext_out) {
+    H2B_REQUIRE(a && ext_out, "ntt batch: null pointer");
+    const size_t G = ctx->members.size();
+    group_each(ctx, [&](h2b_ctx* mb, size_t g) {
+        auto va = every_gth(a, m, g, G);
+        auto ve = every_gth(ext_out, m, g, G);
+        ntt_fused_batch_host(mb, va.data(), va.size(), k, ext_k, ve.data(), false);
+    });
+    group_each(ctx, [&](h2b_ctx* mb, size_t) { ntt_batch_finish(mb); });
 }
 int h2b_lagrange_to_coeff_and_extended_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k, uint32_t ext_k,
                                              uint64_t* const* ext_out) {
-    return guarded(ctx, [&] { ntt_fused_batch_host(ctx, a, m, k, ext_k, ext_out); });
+    return guarded(ctx, [&] {
+        if (ctx->members.size() > 1) group_ntt_fused_batch(ctx, a, m, k, ext_k, ext_out);
+        else ntt_fused_batch_host(ctx, a, m, k, ext_k, ext_out);
+    });
 }
 int h2b_lagrange_to_coeff_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k) {
-    return guarded(ctx, [&] { ntt_batch_host(ctx, 1, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k); });
+    return guarded(ctx, [&] {
+        if (ctx->members.size() > 1) group_ntt_batch(ctx, 1, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k);
+        else ntt_batch_host(ctx, 1, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k);
+    });
 }
 int h2b_coeff_to_lagrange_batch(h2b_ctx* ctx, uint64_t* const* a, size_t m, uint32_t k) {
-    return guarded(ctx, [&] { ntt_batch_host(ctx, 2, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k); });
+    return guarded(ctx, [&] {
+        if (ctx->members.size() > 1) group_ntt_batch(ctx, 2, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k);
+        else ntt_batch_host(ctx, 2, a, a, m, (size_t)1 << (k <= 28 ? k : 0), k);
+    });
 }
 int h2b_coeff_to_extended_batch(h2b_ctx* ctx, const uint64_t* const* coeffs, size_t m, size_t n_coeffs, uint32_t ext_k,
                                 uint64_t* const* out) {
-    return guarded(ctx, [&] { ntt_batch_host(ctx, 4, coeffs, out, m, n_coeffs, ext_k); });
+    return guarded(ctx, [&] {
+        if (ctx->members.size() > 1) group_ntt_batch(ctx, 4, coeffs, out, m, n_coeffs, ext_k);
+        else ntt_batch_host(ctx, 4, coeffs, out, m, n_coeffs, ext_k);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------ assignment

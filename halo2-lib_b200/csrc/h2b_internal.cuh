@@ -92,6 +92,7 @@ struct h2b_ctx {
     int opt_affine_k = -1;       // "msm.affine_k"
     int opt_lookup_backward = 0; // "lookup.leftover_order": 0 = front to back (PSE / axiom walk), 1 = zcash (pop from the back)
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
+    std::vector<h2b_ctx*> members;  // device group (h2b_ctx_create_multi): members[0] == this, the others are private
     bool reduce_counter_zeroed = false;
     void* reduce_counter_ptr = nullptr;
     struct Buf {
@@ -134,6 +135,7 @@ struct h2b_srs {
     size_t begin = 0, count = 0;
     int c = 0, W = 0;
     void* table[2] = {nullptr, nullptr};  // [basis] -> W x count affine points: table[w*count + i] = 2^(c*w) * P_i
+    std::vector<h2b_srs*> parts;          // device group: one shard handle per member device (tables above unused)
 };
 
 namespace h2b {
@@ -193,6 +195,7 @@ void peer_connect(h2b_ctx* ctx, const uint8_t* handles);
 void peer_allreduce(h2b_ctx* ctx, void* d_points, size_t m);
 void peer_destroy(h2b_ctx* ctx);
 bool peer_connected(const h2b_ctx* ctx);
+void peer_connect_local(const std::vector<h2b_ctx*>& members);  // in-process group: direct peer mappings
 // ---- quotient.cu
 void flex_gate_fold_run(h2b_ctx* ctx, const void* d_q_ext, const void* d_a_ext, const uint64_t y[4], uint32_t k, uint32_t ext_k,
                         void* d_acc);

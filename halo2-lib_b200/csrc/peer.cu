@@ -139,6 +139,38 @@ void peer_connect(h2b_ctx* ctx, const uint8_t* handles) {
     st->connected = true;
 }
 
+// One process, several devices: no IPC — every device enables peer access to the others and the mailboxes are addressed
+// through their ordinary device pointers.
+void peer_connect_local(const std::vector<h2b_ctx*>& members) {
+    const int G = (int)members.size();
+    H2B_REQUIRE(G >= 2 && G <= PEER_MAX_RANKS, "peer: 2..16 devices per group");
+    for (int i = 0; i < G; i++) {
+        H2B_REQUIRE(!members[i]->peer, "peer: mailbox already created");
+        H2B_CUDA(cudaSetDevice(members[i]->device));
+        PeerState* st = new PeerState();
+        st->rank = i;
+        st->nranks = G;
+        members[i]->peer = st;
+        H2B_CUDA(cudaMalloc((void**)&st->own, sizeof(PeerMailbox)));
+        H2B_CUDA(cudaMemset(st->own, 0, sizeof(PeerMailbox)));
+        for (int j = 0; j < G; j++) {
+            if (j == i) continue;
+            int can = 0;
+            H2B_CUDA(cudaDeviceCanAccessPeer(&can, members[i]->device, members[j]->device));
+            H2B_REQUIRE(can, "peer: the devices of the group cannot address each other (no NVLink / P2P path)");
+            cudaError_t e = cudaDeviceEnablePeerAccess(members[j]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else H2B_CUDA(e);
+        }
+    }
+    for (int i = 0; i < G; i++) {
+        PeerState* st = (PeerState*)members[i]->peer;
+        for (int j = 0; j < G; j++) st->ptrs.box[j] = ((PeerState*)members[j]->peer)->own;
+        st->connected = true;
+    }
+    H2B_CUDA(cudaSetDevice(members[0]->device));
+}
+
 void peer_allreduce(h2b_ctx* ctx, void* d_points, size_t m) {
     PeerState* st = (PeerState*)ctx->peer;
     H2B_REQUIRE(st && st->connected, "peer: mailboxes are not connected");

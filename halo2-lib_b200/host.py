@@ -47,9 +47,15 @@ def _u64(a, cols):
 class Context:
     """One per process / GPU (h2b_ctx)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int | list = 0):
+        """device: one index, or a list of indices for a single-process device group (h2b_ctx_create_multi)"""
         h = C.c_void_p()
-        rc = lib.h2b_ctx_create(device, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*device)
+            rc = lib.h2b_ctx_create_multi(ids, len(device), C.byref(h))
+            device = device[0]
+        else:
+            rc = lib.h2b_ctx_create(device, C.byref(h))
         if rc != H2B_OK:
             raise H2BError(rc, lib.h2b_last_error(None).decode())
         self.h = h
@@ -69,6 +75,10 @@ class Context:
     def set_option(self, key: str, value: int):
         """tuning / experiment switches (h2b_ctx_set_option); results never depend on them"""
         self.check(lib.h2b_ctx_set_option(self.h, key.encode(), int(value)))
+
+    @property
+    def device_count(self) -> int:
+        return int(lib.h2b_ctx_device_count(self.h))
 
     @property
     def kernel_launches(self) -> int:

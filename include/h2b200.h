@@ -47,6 +47,16 @@ typedef struct h2b_srs h2b_srs;
 
 /* ---- context -------------------------------------------------------------------------------------- */
 int h2b_ctx_create(int device, h2b_ctx** out);
+/* One process, n_dev GPUs (the reference's create_proof is ONE in-process call, halo2-base/src/utils/testing.rs:40-48): the
+ * handle is an ordinary context on dev_ids[0] that also drives the other devices.  On such a context
+ *   h2b_srs_upload                      shards the bases over the devices by contiguous index range (resident per device),
+ *   h2b_msm_g1 / h2b_msm_g1_batch       commit every shard on its own device and return the FULL sums: the partial sums meet
+ *                                       in the fused all-reduce kernel over in-process peer mappings (no IPC, no NCCL),
+ *   h2b_*_batch transforms              deal polynomial j to device j mod n_dev, all devices pipelined concurrently,
+ * and every other entry point (assignment, `_dev` calls, ...) runs on dev_ids[0].  SRS handles of a group are only valid
+ * on that group.  h2b_ctx_device_count returns n_dev (1 for h2b_ctx_create). */
+int h2b_ctx_create_multi(const int* dev_ids, int n_dev, h2b_ctx** out);
+int h2b_ctx_device_count(const h2b_ctx* ctx);
 void h2b_ctx_destroy(h2b_ctx* ctx);
 /* Use a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) for all work; NULL = the
  * context's own stream. */

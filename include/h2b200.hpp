@@ -54,6 +54,12 @@ public:
         int rc = h2b_ctx_create(device, &ctx_);
         if (rc != H2B_OK) throw Error(rc, h2b_last_error(nullptr));
     }
+    // one process, several GPUs (h2b_ctx_create_multi): commitments and batched transforms use all of them
+    explicit Context(const std::vector<int>& devices) {
+        int rc = h2b_ctx_create_multi(devices.data(), (int)devices.size(), &ctx_);
+        if (rc != H2B_OK) throw Error(rc, h2b_last_error(nullptr));
+    }
+    int device_count() const { return h2b_ctx_device_count(ctx_); }
     ~Context() { h2b_ctx_destroy(ctx_); }
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;

@@ -143,6 +143,45 @@ int main() {
         CHECK(memcmp(&gl4[0], &G, sizeof(G)) == 0 && memcmp(&gl4[1], &idp, sizeof(G)) == 0 && memcmp(&gl4[3], &idp, sizeof(G)) == 0);
     }
 
+    {   // one process, all GPUs of the box (h2b_ctx_create_multi): the sharded commitments equal the single-device ones and
+        // the batched transforms dealt over the devices equal the single-device transforms
+        int ndev = 0;
+        for (int d = 0; d < 16; d++) {  // probe: a context on device d exists?
+            h2b_ctx* probe = nullptr;
+            if (h2b_ctx_create(d, &probe) != H2B_OK) break;
+            h2b_ctx_destroy(probe);
+            ndev++;
+        }
+        if (ndev >= 2) {
+            std::vector<int> devs;
+            for (int d = 0; d < (ndev > 4 ? 4 : ndev); d++) devs.push_back(d);
+            Context grp(devs);
+            CHECK(grp.device_count() == (int)devs.size());
+            ParamsKZG gp(grp, k, g, gl);
+            std::vector<G1> both = {params.commit(s), gp.commit(s), params.commit_lagrange(s), gp.commit_lagrange(s)};
+            auto gm = gp.commit_many({0, 1, 0, 1, 0}, {&s, &s, &s, &s, &s});
+            both.push_back(gm[0]);
+            both.push_back(gm[3]);
+            ctx.batch_normalize(both);
+            CHECK(memcmp(&both[0], &both[1], sizeof(G1)) == 0);
+            CHECK(memcmp(&both[2], &both[3], sizeof(G1)) == 0);
+            CHECK(memcmp(&both[0], &both[4], sizeof(G1)) == 0);
+            CHECK(memcmp(&both[2], &both[5], sizeof(G1)) == 0);
+            // five columns through lagrange_to_coeff_batch on the group vs one at a time on device 0
+            std::vector<std::vector<Fr>> cols(5, s);
+            for (size_t j = 0; j < cols.size(); j++) cols[j][1] = small_mont(ctx, 100 + j);
+            std::vector<std::vector<Fr>> want = cols;
+            for (auto& c : want) dom.lagrange_to_coeff(c);
+            std::vector<uint64_t*> ptrs;
+            for (auto& c : cols) ptrs.push_back(reinterpret_cast<uint64_t*>(c.data()));
+            grp.check(h2b_lagrange_to_coeff_batch(grp.raw(), ptrs.data(), ptrs.size(), k));
+            for (size_t j = 0; j < cols.size(); j++) CHECK(cols[j] == want[j]);
+            printf("host mirror: device group of %zu GPUs checked\n", devs.size());
+        } else {
+            printf("host mirror: single GPU, device-group checks skipped\n");
+        }
+    }
+
     printf(fails ? "host mirror: %d FAILED\n" : "host mirror: all checks passed\n", fails);
     return fails ? 1 : 0;
 }
