@@ -92,11 +92,15 @@ __device__ __forceinline__ int ba_classify_full(const Affine& p, const Affine& q
 }
 
 // One level of one tile: `kk` pairs per thread, pair index = base + i * BA_T + tid, npairs = total pairs of the level.
-template <bool LEVEL1>
+// PT = true: every thread inverts the product of its own denominators with the constant-time safegcd routine
+// (Fp::inv_safegcd: mostly add / shift work on the ALU pipe the products leave idle) — no product tree, no barrier, no
+// warp waits for one lane.  PT = false: one inversion per CTA tile (product tree in shared memory + a single-lane inv_bgcd).
+template <bool LEVEL1, bool PT>
 __device__ __forceinline__ void ba_level(const BaSrc<LEVEL1> src, Affine* __restrict__ out, Fq* __restrict__ pref,
                                          u32 base, u32 npairs, int kk, u32* node) {
     const int tid = threadIdx.x;
     const Fq zero = Fq::zero();
+    Fq inv_total;
     // ---- forward sweep: prefix products of the denominators of this thread's pairs
     {
         Fq run = Fq::one();
@@ -122,8 +126,10 @@ __device__ __forceinline__ void ba_level(const BaSrc<LEVEL1> src, Affine* __rest
             if (pair < npairs) run.store(pref + pair);
             pair = pair_n; w = wn; px = pxn; qx = qxn;
         }
-        ba_smem_store(node + BA_T + tid, 2 * BA_T, run);
+        if (PT) inv_total = run.inv_safegcd();
+        else ba_smem_store(node + BA_T + tid, 2 * BA_T, run);
     }
+    if (!PT) {
     __syncthreads();
     // ---- product tree of the thread totals, one inversion, back down to per-thread inverses
 #pragma unroll 1
@@ -150,9 +156,11 @@ __device__ __forceinline__ void ba_level(const BaSrc<LEVEL1> src, Affine* __rest
         }
         __syncthreads();
     }
+    inv_total = ba_smem_load(node + BA_T + tid, 2 * BA_T);
+    }
     // ---- backward sweep: individual inverses, the additions, coalesced stores
     {
-        Fq inv_run = ba_smem_load(node + BA_T + tid, 2 * BA_T);  // 1 / (product of all denominators of this thread)
+        Fq inv_run = inv_total;  // 1 / (product of all denominators of this thread)
         auto fetch = [&](u32 pr, uint2 ww, Affine& p, Affine& q) {
             p.x = zero; p.y = zero; q.x = zero; q.y = zero;
             if (ww.x != BA_PAD) { const char* a = src.addr(pr, ww.x, 0); p.x = src.ld(a); p.y = src.ld(a + 32); }
@@ -209,6 +217,7 @@ __device__ __forceinline__ void ba_level(const BaSrc<LEVEL1> src, Affine* __rest
 // n_entries_ptr: number of (padded) sorted entries M' on the device (a multiple of 2^R).  cursor: level-1 pair cursor,
 // zero at launch.  buf_a / buf_b / buf_c: sums of levels 1, 2, 3 (M'/2, M'/4, M'/8 points); pref: M'/2 prefix products.
 // k_nominal: level-1 pairs per thread and tile (multiple of 4).  R <= 3.
+template <bool PT>
 __global__ void __launch_bounds__(BA_T, 4) k_batch_affine(const u32* __restrict__ vals, const Affine* __restrict__ table,
                                                           Affine* __restrict__ buf_a, Affine* __restrict__ buf_b,
                                                           Affine* __restrict__ buf_c, Fq* __restrict__ pref,
@@ -239,15 +248,15 @@ __global__ void __launch_bounds__(BA_T, 4) k_batch_affine(const u32* __restrict_
         const int k = (int)sh_k;
         if (base1 >= npairs1) break;
         const BaSrc<true> s1{vals, table, nullptr};
-        ba_level<true>(s1, buf_a, pref, base1, npairs1, k, node);
+        ba_level<true, PT>(s1, buf_a, pref, base1, npairs1, k, node);
         // the prefix scratch of every level stays inside the tile's own level-1 region [base1, base1 + BA_T * k)
         if (R >= 2) {
             const BaSrc<false> s2{nullptr, nullptr, buf_a};
-            ba_level<false>(s2, buf_b, pref + (base1 - (base1 >> 1)), base1 >> 1, m_entries >> 2, k >> 1, node);
+            ba_level<false, PT>(s2, buf_b, pref + (base1 - (base1 >> 1)), base1 >> 1, m_entries >> 2, k >> 1, node);
         }
         if (R >= 3) {
             const BaSrc<false> s3{nullptr, nullptr, buf_b};
-            ba_level<false>(s3, buf_c, pref + (base1 - (base1 >> 2)), base1 >> 2, m_entries >> 3, k >> 2, node);
+            ba_level<false, PT>(s3, buf_c, pref + (base1 - (base1 >> 2)), base1 >> 2, m_entries >> 3, k >> 2, node);
         }
     }
 }

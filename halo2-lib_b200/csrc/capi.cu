@@ -271,6 +271,7 @@ int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value) {
         const std::string k(key);
         if (k == "msm.affine_levels") { H2B_REQUIRE(value >= -1 && value <= 3, "msm.affine_levels: -1 (default) .. 3"); ctx->opt_affine_levels = (int)value; }
         else if (k == "msm.affine_k") { H2B_REQUIRE(value == -1 || (value >= 8 && value <= 128 && value % 4 == 0), "msm.affine_k: multiple of 4 in [8, 128]"); ctx->opt_affine_k = (int)value; }
+        else if (k == "msm.affine_per_thread_inverse") { H2B_REQUIRE(value >= -1 && value <= 1, "msm.affine_per_thread_inverse: -1, 0 or 1"); ctx->opt_affine_pt = (int)value; }
         else if (k == "lookup.leftover_order") { H2B_REQUIRE(value == 0 || value == 1, "lookup.leftover_order: 0 (front to back) or 1 (zcash: from the back)"); ctx->opt_lookup_backward = (int)value; }
         else H2B_REQUIRE(false, "set_option: unknown key");
     });
@@ -1361,7 +1362,7 @@ int h2b_poly_lincomb(h2b_ctx* ctx, const uint64_t* const* polys, const uint64_t*
 // ------------------------------------------------------------------------------------------------ test hook
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
     return guarded(ctx, [&] {
-        H2B_REQUIRE(a && out && (b || (op > 2 && op < 7) || op == 9) && (field == 0 || field == 1) && op >= 0 && op <= 9, "field_op: bad argument");
+        H2B_REQUIRE(a && out && (b || (op > 2 && op < 7) || op == 9 || op == 10) && (field == 0 || field == 1) && op >= 0 && op <= 10, "field_op: bad argument");
         if (n == 0) return;
         char* d = (char*)ctx->get(WS_ASSIGN_IN, 3 * n * 32);
         H2B_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));

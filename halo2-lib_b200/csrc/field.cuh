@@ -569,6 +569,156 @@ struct __align__(16) Fp {
         }
         return r * (r2() * r2());  // R^2 * R^2 * R^-1 = R^3;  r * R^3 * R^-1 = r R^2 = a^-1 R
     }
+
+    // ---- a^-1 by constant-time "safegcd" (Bernstein-Yang divsteps; the 30-bit batched form of libsecp256k1's modinv32,
+    // restated): 20 rounds of 30 divsteps on the low words build a 2x2 transition matrix that is then applied to the
+    // full-width (f, g) and, modulo p, to (d, e) with f = d*A, g = e*A.  No data-dependent branch: every lane of a warp
+    // can invert its own element at once, and the work is ~10k add / shift / logic instructions plus ~1800 wide
+    // multiplies (the cost of ~15 products) — it runs mostly on the ALU pipe that the Montgomery products leave idle.
+    // Used where EVERY thread needs its own inverse (per-thread Montgomery trick in the batch-affine path); the
+    // single-lane paths keep inv_bgcd.  inv(0) = 0.  Signed 30-bit limbs: value = sum l[i] 2^(30 i), l[0..7] in [0, 2^30).
+    __host__ __device__ static constexpr u32 MOD30(int i) {  // limb i of p in base 2^30
+        u64 lo = 0;
+        // bits [30 i, 30 i + 30) of the 256-bit modulus
+        const int bit = 30 * i, w = bit >> 5, off = bit & 31;
+        lo = (u64)(w < 8 ? P::MOD(w) : 0u) | ((u64)(w + 1 < 8 ? P::MOD(w + 1) : 0u) << 32);
+        return (u32)((lo >> off) & 0x3fffffffu);
+    }
+    __host__ __device__ static constexpr u32 MODINV30() {  // p^-1 mod 2^30 (Newton iteration on the low word)
+        u32 p0 = P::MOD(0), x = p0;  // x = p^-1 mod 2^3 for odd p
+        for (int i = 0; i < 5; i++) x *= 2u - p0 * x;
+        return x & 0x3fffffffu;
+    }
+    __device__ __noinline__ Fp inv_safegcd() const {
+        constexpr int32_t M30 = 0x3fffffff;
+        int32_t d[9], e[9], f[9], g[9];
+        // A (Montgomery limbs, 8 x 32 bits) -> g; p -> f; d = 0, e = 1
+        {
+            u32 w[9];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = l[i];
+            w[8] = 0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const int bit = 30 * i, wi = bit >> 5, off = bit & 31;
+                u64 two = (u64)w[wi] | ((u64)(wi + 1 < 9 ? w[wi + 1] : 0u) << 32);
+                g[i] = (int32_t)((two >> off) & 0x3fffffffu);
+                f[i] = (int32_t)MOD30(i);
+                d[i] = 0;
+                e[i] = 0;
+            }
+            e[0] = 1;
+        }
+        int32_t zeta = -1;  // -(delta + 1/2), delta = 1/2
+#pragma unroll 1
+        for (int round = 0; round < 20; round++) {
+            // 30 divsteps on the low words
+            u32 u = 1, v = 0, q = 0, r = 1;
+            u32 ff = (u32)f[0] | ((u32)f[1] << 30), gg = (u32)g[0] | ((u32)g[1] << 30);
+#pragma unroll 6
+            for (int i = 0; i < 30; i++) {
+                u32 c1 = (u32)(zeta >> 31);
+                const u32 mask2 = 0u - (gg & 1u);
+                const u32 x = (ff ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+                gg += x & mask2;
+                q += y & mask2;
+                r += z & mask2;
+                c1 &= mask2;
+                zeta = (int32_t)(((u32)zeta ^ c1) - 1u);
+                ff += gg & c1;
+                u += q & c1;
+                v += r & c1;
+                gg >>= 1;
+                u <<= 1;
+                v <<= 1;
+            }
+            const int64_t tu = (int32_t)u, tv = (int32_t)v, tq = (int32_t)q, tr = (int32_t)r;
+            // (d, e) <- t * (d, e) / 2^30 mod p
+            {
+                const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+                int32_t md = ((int32_t)tu & sd) + ((int32_t)tv & se), me = ((int32_t)tq & sd) + ((int32_t)tr & se);
+                int64_t cd = tu * d[0] + tv * e[0], ce = tq * d[0] + tr * e[0];
+                md -= (int32_t)((MODINV30() * (u32)cd + (u32)md) & (u32)M30);
+                me -= (int32_t)((MODINV30() * (u32)ce + (u32)me) & (u32)M30);
+                cd += (int64_t)MOD30(0) * md;
+                ce += (int64_t)MOD30(0) * me;
+                cd >>= 30;
+                ce >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; i++) {
+                    cd += tu * d[i] + tv * e[i] + (int64_t)MOD30(i) * md;
+                    ce += tq * d[i] + tr * e[i] + (int64_t)MOD30(i) * me;
+                    d[i - 1] = (int32_t)cd & M30;
+                    e[i - 1] = (int32_t)ce & M30;
+                    cd >>= 30;
+                    ce >>= 30;
+                }
+                d[8] = (int32_t)cd;
+                e[8] = (int32_t)ce;
+            }
+            // (f, g) <- t * (f, g) / 2^30 (exact)
+            {
+                int64_t cf = tu * f[0] + tv * g[0], cg = tq * f[0] + tr * g[0];
+                cf >>= 30;
+                cg >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; i++) {
+                    cf += tu * f[i] + tv * g[i];
+                    cg += tq * f[i] + tr * g[i];
+                    f[i - 1] = (int32_t)cf & M30;
+                    g[i - 1] = (int32_t)cg & M30;
+                    cf >>= 30;
+                    cg >>= 30;
+                }
+                f[8] = (int32_t)cf;
+                g[8] = (int32_t)cg;
+            }
+        }
+        // g = 0, f = +-1 (f = p when A = 0, then d = 0): result = sign(f) * d, brought into [0, p)
+        // signed limbs -> 288-bit two's complement words
+        u32 w[9];
+        {
+            int64_t acc = 0;
+            int have = 0, li = 0;
+#pragma unroll
+            for (int j = 0; j < 9; j++) {
+#pragma unroll
+                for (int rep = 0; rep < 3; rep++) {
+                    if (have < 32 && li < 9) {
+                        acc += (int64_t)((u64)(li < 8 ? (int64_t)d[li] : (int64_t)d[8]) << have);
+                        have += 30;
+                        li++;
+                    }
+                }
+                w[j] = (u32)acc;
+                acc >>= 32;
+                have -= 32;
+            }
+        }
+        const u32 negf = (u32)(f[8] >> 31);  // all ones when f = -1
+        {   // w <- negf ? -w : w
+            u32 c;
+            add_cc(w[0], w[0] ^ negf, negf & 1u);
+#pragma unroll
+            for (int i = 1; i < 8; i++) addc_cc(w[i], w[i] ^ negf, 0);
+            addc(w[8], w[8] ^ negf, 0);
+            (void)c;
+        }
+        // w in (-2p, 2p): add p while negative (twice), then subtract p once if >= p
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            const u32 neg = (u32)((int32_t)w[8] >> 31);
+            add_cc(w[0], w[0], P::MOD(0) & neg);
+#pragma unroll
+            for (int i = 1; i < 8; i++) addc_cc(w[i], w[i], P::MOD(i) & neg);
+            addc(w[8], w[8], 0);
+        }
+        Fp res;
+#pragma unroll
+        for (int i = 0; i < 8; i++) res.l[i] = w[i];
+        res = reduce_once(res);  // w[8] == 0 now and the value is < 2p
+        return res * (r2() * r2());  // plain residue (aR)^-1 -> Montgomery a^-1 R
+    }
 };
 
 typedef Fp<FqParams> Fq;

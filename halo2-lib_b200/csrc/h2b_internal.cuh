@@ -90,6 +90,7 @@ struct h2b_ctx {
     bool ntt_attr_set = false;
     int opt_affine_levels = -1;  // h2b_ctx_set_option("msm.affine_levels"): -1 = default
     int opt_affine_k = -1;       // "msm.affine_k"
+    int opt_affine_pt = -1;      // "msm.affine_per_thread_inverse": 1 = every thread inverts (safegcd), 0 = one inversion per tile
     int opt_lookup_backward = 0; // "lookup.leftover_order": 0 = front to back (PSE / axiom walk), 1 = zcash (pop from the back)
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
     std::vector<h2b_ctx*> members;  // device group (h2b_ctx_create_multi): members[0] == this, the others are private

@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(128) k_field_op(int op, const uint64_t* __rest
         case 7: r = F::mul_add_mul(x, y, x + y, x - y); break;  // a*b + (a+b)(a-b)
         case 8: r = F::mul_sub_mul(x, y, y, y); break;          // a*b - b*b
         case 9: r = x.inv_bgcd(); break;
+        case 10: r = x.inv_safegcd(); break;
         default: r = x.to_mont(); break;
     }
     r.store(out + 4 * (size_t)i);
@@ -660,8 +661,17 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
         }();
         u32* ba_cursor = d_L + 1;
         H2B_CUDA(cudaMemsetAsync(ba_cursor, 0, 4, st));
-        H2B_LAUNCH(ctx, k_batch_affine, ctx->sm_count * BA_CTAS, BA_T, 0, vals, (const Affine*)d_table, red[0], red[1], red[2], red_pref,
-                   off + nb_total, ba_cursor, R, BA_K);
+        static const int BA_PT_ENV = [] {  // H2B_BA_PT=1: per-thread safegcd inversion instead of one inversion per tile
+            const char* e = getenv("H2B_BA_PT");
+            return e ? atoi(e) : 0;
+        }();
+        const bool per_thread = ctx->opt_affine_pt >= 0 ? ctx->opt_affine_pt != 0 : BA_PT_ENV != 0;
+        if (per_thread)
+            H2B_LAUNCH(ctx, k_batch_affine<true>, ctx->sm_count * BA_CTAS, BA_T, 0, vals, (const Affine*)d_table, red[0], red[1], red[2], red_pref,
+                       off + nb_total, ba_cursor, R, BA_K);
+        else
+            H2B_LAUNCH(ctx, k_batch_affine<false>, ctx->sm_count * BA_CTAS, BA_T, 0, vals, (const Affine*)d_table, red[0], red[1], red[2], red_pref,
+                       off + nb_total, ba_cursor, R, BA_K);
         H2B_LAUNCH(ctx, k_accumulate<true>, ceil_div(n_chunks, 128), 128, 0, (const u32*)nullptr, off, nb_total, d_L, (const Affine*)red[R - 1], buckets, partials, R);
     }
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, d_L, partials, buckets, big + 1, big, R);

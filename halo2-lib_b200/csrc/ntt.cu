@@ -51,7 +51,10 @@ struct NttPlan {
     int scaled = 0;
     void* block = nullptr;
     void* block2 = nullptr;
+    bool domain_root = false;  // omega is the 2^log_n domain root or its inverse (kept for the context's lifetime)
+    uint64_t seq = 0;          // creation order, for the eviction of plans built for arbitrary roots
 };
+static constexpr size_t NTT_MAX_ADHOC_PLANS = 4;  // best_fft with arbitrary roots: bounded cache (a plan can hold n x 32 B per pass)
 
 // out[i] = omega^(i * mult)
 __global__ void k_pow_table(Fr omega, uint64_t mult, u32 count, Fr* __restrict__ out) {
@@ -234,7 +237,27 @@ static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4], 
     std::array<uint64_t, 5> key = {omega[0], omega[1], omega[2], omega[3], (uint64_t)log_n | ((uint64_t)(scaled ? 1 : 0) << 32)};
     auto it = ctx->ntt_plans.find(key);
     if (it != ctx->ntt_plans.end()) return it->second;
+    const bool domain_root = log_n <= 28 && (memcmp(omega, FR_OMEGA[log_n], 32) == 0 || memcmp(omega, FR_OMEGA_INV[log_n], 32) == 0);
+    if (!domain_root) {  // evict the oldest plan of an arbitrary root once the bound is reached
+        size_t adhoc = 0;
+        auto oldest = ctx->ntt_plans.end();
+        for (auto jt = ctx->ntt_plans.begin(); jt != ctx->ntt_plans.end(); ++jt) {
+            if (jt->second->domain_root) continue;
+            adhoc++;
+            if (oldest == ctx->ntt_plans.end() || jt->second->seq < oldest->second->seq) oldest = jt;
+        }
+        if (adhoc >= NTT_MAX_ADHOC_PLANS) {
+            H2B_CUDA(cudaDeviceSynchronize());  // a transform that uses the plan may still be in flight
+            if (oldest->second->block) cudaFree(oldest->second->block);
+            if (oldest->second->block2) cudaFree(oldest->second->block2);
+            delete oldest->second;
+            ctx->ntt_plans.erase(oldest);
+        }
+    }
+    static uint64_t plan_seq = 0;
     NttPlan* p = new NttPlan();
+    p->domain_root = domain_root;
+    p->seq = ++plan_seq;
     struct Guard {  // a failed allocation / launch must not leak the half-built plan
         NttPlan* p;
         ~Guard() {
@@ -288,6 +311,9 @@ static NttPlan* get_plan(h2b_ctx* ctx, uint32_t log_n, const uint64_t omega[4], 
             consumed += p->r[t];
         }
     }
+    // the tables are built on whichever stream is current; a later use from another stream (h2b_ctx_set_stream, the side
+    // queue) must not overtake the build
+    H2B_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->ntt_plans[key] = p;
     guard.p = nullptr;
     return p;

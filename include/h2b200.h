@@ -74,6 +74,8 @@ int h2b_ctx_side_join(h2b_ctx* ctx);
 /* Tuning / experiment switches (results never depend on them).  Keys:
  *   "msm.affine_levels"  0..3 (-1 = default 0): batch-affine halving levels in front of the XYZZ bucket accumulation
  *   "msm.affine_k"       multiple of 4 in [8, 128] (-1 = default 32): pairs per thread and tile of those levels
+ *   "msm.affine_per_thread_inverse"  1: every thread inverts its own denominator product (constant-time safegcd), 0: one
+ *                        inversion per tile (product tree + single lane); -1 = default
  * and one switch that selects between two equally valid outputs (see h2b_permute_expression_pair):
  *   "lookup.leftover_order"  0 (default): left-over table values fill the repeated rows front to back; 1: from the back */
 int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value);
@@ -418,7 +420,8 @@ int h2b_eval_polynomial_batch_dev(h2b_ctx* ctx, const void* const* d_polys, cons
 /* ---- test hooks (field arithmetic of the kernels, element-wise on the device) --------------------- */
 /* field: 0 = Fq, 1 = Fr; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 from_mont(a), 5 to_mont(a), 6 sqr(a),
  * 7 a*b + (a+b)(a-b) and 8 a*b - b*b through the fused two-product Montgomery routine of the group law,
- * 9 inv(a) by the binary extended Euclidean routine the single-lane inversions use */
+ * 9 inv(a) by the binary extended Euclidean routine the single-lane inversions use, 10 inv(a) by the constant-time
+ * safegcd routine (every lane inverts its own element) */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
 
 #ifdef __cplusplus

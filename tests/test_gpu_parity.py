@@ -50,6 +50,7 @@ def test_field_ops(ctx, which, m):
     assert np.array_equal(ctx.field_op(which, 5, ints_to_limbs(a)), A)
     assert np.array_equal(ctx.field_op(which, 3, A[:300]), orc.f_inv(which, A[:300]))
     assert np.array_equal(ctx.field_op(which, 9, A[:600]), orc.f_inv(which, A[:600]))  # binary-Euclid inversion (single-lane paths)
+    assert np.array_equal(ctx.field_op(which, 10, A[:3000]), orc.f_inv(which, A[:3000]))  # constant-time safegcd (every lane inverts)
     # products of edge x edge (carry patterns)
     ea = [x for x in edge for _ in edge]
     eb = [y for _ in edge for y in edge]
@@ -221,14 +222,15 @@ def test_msm_closed_form_large(ctx, h2b):
     params.close()
 
 
-@pytest.mark.parametrize("levels", [1, 2, 3])
-def test_msm_batch_affine_levels(h2b, levels):
+@pytest.mark.parametrize("levels,per_thread", [(1, 0), (2, 0), (3, 0), (2, 1), (3, 1)])
+def test_msm_batch_affine_levels(h2b, levels, per_thread):
     """the opt-in batch-affine bucket reduction (csrc/batch_affine.cuh): groups of 2^levels sorted entries are summed in
     affine coordinates with a shared inversion before the XYZZ accumulation.  Same group element, every edge included:
     identity bases, repeated bases (tangent case), P + (-P) inside a bucket, hot buckets, witness-like columns."""
     c = h2b.Context(0)
     c.set_option("msm.affine_levels", levels)
     c.set_option("msm.affine_k", 8 if levels == 1 else 32)
+    c.set_option("msm.affine_per_thread_inverse", per_thread)  # 1: every thread inverts (constant-time safegcd), no barrier
     try:
         rng = np.random.default_rng(900 + levels)
         for k, dist in [(6, "uniform"), (10, "witness"), (13, "uniform")]:
