@@ -272,6 +272,7 @@ int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value) {
         if (k == "msm.affine_levels") { H2B_REQUIRE(value >= -1 && value <= 3, "msm.affine_levels: -1 (default) .. 3"); ctx->opt_affine_levels = (int)value; }
         else if (k == "msm.affine_k") { H2B_REQUIRE(value == -1 || (value >= 8 && value <= 128 && value % 4 == 0), "msm.affine_k: multiple of 4 in [8, 128]"); ctx->opt_affine_k = (int)value; }
         else if (k == "msm.affine_per_thread_inverse") { H2B_REQUIRE(value >= -1 && value <= 1, "msm.affine_per_thread_inverse: -1, 0 or 1"); ctx->opt_affine_pt = (int)value; }
+        else if (k == "msm.batch_group") { H2B_REQUIRE(value >= 0 && value <= 16, "msm.batch_group: 0 (default) .. 16 MSMs per pipeline"); ctx->opt_msm_group = (int)value; }
         else if (k == "lookup.leftover_order") { H2B_REQUIRE(value == 0 || value == 1, "lookup.leftover_order: 0 (front to back) or 1 (zcash: from the back)"); ctx->opt_lookup_backward = (int)value; }
         else H2B_REQUIRE(false, "set_option: unknown key");
     });
@@ -493,12 +494,17 @@ static void* msm_batch_enqueue(h2b_ctx* ctx, const h2b_srs* srs, const int* basi
         H2B_REQUIRE(scalars[j], "msm: null scalar column");
         tables[j] = srs_table(srs, basis[j], n);
     }
+    // the columns are cut into groups that share one sort / accumulate / reduce pipeline (msm_run_group); a group's columns
+    // are staged side by side in the lane's buffer
     constexpr int NL = h2b_ctx::NLANES;
-    const int nl = (int)(m < (size_t)NL ? m : (size_t)NL);
+    const size_t gsz = msm_group_size(ctx, n, m, srs->W);
+    const size_t ngroups = (m + gsz - 1) / gsz;
+    const size_t gmax = (m + ngroups - 1) / ngroups;
+    const int nl = (int)(ngroups < (size_t)NL ? ngroups : (size_t)NL);
     void* stage[NL];
     for (int l = 0; l < nl; l++) {
         ctx->cur_lane = l;
-        stage[l] = ctx->get(WS_SCALARS, n * 32);
+        stage[l] = ctx->get(WS_SCALARS, gmax * n * 32);
     }
     ctx->cur_lane = 0;
     void* d_out = ctx->get(WS_OUT, m * 96);
@@ -518,15 +524,22 @@ static void* msm_batch_enqueue(h2b_ctx* ctx, const h2b_srs* srs, const int* basi
         }
     };
     Join join{ctx, ks, nl};
-    for (size_t j = 0; j < m; j++) {
-        const int l = (int)(j % nl);
-        if (j >= (size_t)nl) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->lane_consumed[l], 0));
-        H2B_CUDA(cudaMemcpyAsync(stage[l], scalars[j] + 4 * row0, n * 32, cudaMemcpyHostToDevice, cs));
+    size_t j = 0;
+    for (size_t g = 0; g < ngroups; g++) {
+        const size_t cnt = m / ngroups + (g < m % ngroups ? 1 : 0);
+        const int l = (int)(g % nl);
+        if (g >= (size_t)nl) H2B_CUDA(cudaStreamWaitEvent(cs, ctx->lane_consumed[l], 0));
+        const void* d_cols[16];
+        for (size_t t = 0; t < cnt; t++) {
+            d_cols[t] = (char*)stage[l] + t * n * 32;
+            H2B_CUDA(cudaMemcpyAsync((void*)d_cols[t], scalars[j + t] + 4 * row0, n * 32, cudaMemcpyHostToDevice, cs));
+        }
         H2B_CUDA(cudaEventRecord(ctx->lane_ready[l], cs));
         H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_ready[l], 0));
         ctx->stream = ctx->lane_stream[l];
         ctx->cur_lane = l;
-        msm_run(ctx, tables[j], n, srs->c, srs->W, srs->W, stage[l], (char*)d_out + 96 * j, ctx->lane_consumed[l]);
+        msm_run_group(ctx, tables.data() + j, n, srs->c, srs->W, srs->W, d_cols, cnt, (char*)d_out + 96 * j, ctx->lane_consumed[l]);
+        j += cnt;
     }
     return d_out;
 }

@@ -91,6 +91,7 @@ struct h2b_ctx {
     int opt_affine_levels = -1;  // h2b_ctx_set_option("msm.affine_levels"): -1 = default
     int opt_affine_k = -1;       // "msm.affine_k"
     int opt_affine_pt = -1;      // "msm.affine_per_thread_inverse": 1 = every thread inverts (safegcd), 0 = one inversion per tile
+    int opt_msm_group = 0;       // "msm.batch_group": MSMs of a batch call that share one sort / accumulate / reduce pipeline (0 = by size)
     int opt_lookup_backward = 0; // "lookup.leftover_order": 0 = front to back (PSE / axiom walk), 1 = zcash (pop from the back)
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
     std::vector<h2b_ctx*> members;  // device group (h2b_ctx_create_multi): members[0] == this, the others are private
@@ -172,7 +173,11 @@ void msm_build_table(h2b_ctx* ctx, const void* d_bases, size_t count, int c, int
 // table mode: q = W (one bucket set), table = W x n affine; ad-hoc mode: q = 1, table = n affine
 void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out,
              cudaEvent_t after_digits = nullptr);
-// m MSMs over the same table, spread over the context's lanes; joins on ctx->stream
+// m MSMs of one size through ONE sort / accumulate / bucket-reduction pipeline (m <= 16; tabulated bases unless m == 1)
+void msm_run_group(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, int W, int q, const void* const* d_scalars, size_t m,
+                   void* d_out, cudaEvent_t after_digits = nullptr);
+size_t msm_group_size(const h2b_ctx* ctx, size_t n, size_t m, int W);  // MSMs per pipeline for a batch of m
+// m MSMs over tabulated bases: cut into groups (msm_run_group) that are dealt to the context's lanes; joins on ctx->stream
 void msm_run_batch(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, int W, const void* const* d_scalars, size_t m, void* d_out);
 void g1_sum_run(h2b_ctx* ctx, const void* d_points, size_t m, void* d_out);
 void g1_normalize_run(h2b_ctx* ctx, void* d_points, size_t m);

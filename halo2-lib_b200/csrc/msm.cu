@@ -30,6 +30,13 @@ namespace h2b {
 static constexpr u32 SIGN_BIT = 0x80000000u;
 static constexpr int ACC_L_DEFAULT = 32;  // upper bound of the sorted entries per accumulate thread (see k_accumulate)
 static constexpr int BIG_PARTIALS = 64;  // buckets spanning more chunks than this are summed by a whole CTA
+// A *group* of MSMs over the same domain size runs through ONE pipeline: the bucket sets of the g-th MSM follow those of
+// the (g-1)-th in one bucket array, so the sort, the accumulation and the latency-bound bucket reduction are launched once
+// per group (a prover phase commits 1..13 columns at once) instead of once per column.
+static constexpr int MSM_MAX_GROUP = 16;
+struct MsmScalars { const uint64_t* p[MSM_MAX_GROUP]; };
+// The MSMs of a group read at most TWO distinct tables (the SRS has two bases); bit 30 of a sorted entry selects one.
+static constexpr u32 TABLE_BIT = 0x40000000u;
 
 // ------------------------------------------------------------------------------------------------ digits + counting sort
 // Signed base-2^c recoding of one canonical scalar; calls f(w, digit_magnitude (1..2^(c-1)), negative) for every
@@ -98,19 +105,23 @@ __device__ __forceinline__ u32 warp_agg_add(u32* counters, u32 key, bool active,
 
 // MODE 0: histogram of bucket keys.  MODE 1: scatter (table index | sign) to its sorted position via the cursors.
 // One thread per scalar; window w belongs to bucket set w / q and table level w % q.  Zero digits are dropped.
+// blockIdx.y = MSM of the group; its bucket sets start at bucket blockIdx.y * spm * nbw (spm = sets per MSM).
 template <int MODE>
-__global__ void __launch_bounds__(256) k_digits(const uint64_t* __restrict__ scalars, u32 n, int c, int W, int q, u32 nbw,
-                                                u32* __restrict__ counters, u32* __restrict__ vals_sorted) {
+__global__ void __launch_bounds__(256) k_digits(const __grid_constant__ MsmScalars cols, u32 n, int c, int W, int q, u32 nbw, u32 spm,
+                                                u32 table_mask, u32* __restrict__ counters, u32* __restrict__ vals_sorted) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
+    const uint64_t* __restrict__ scalars = cols.p[blockIdx.y];
+    const u32 key0 = blockIdx.y * spm * nbw;
+    const u32 tbit = ((table_mask >> blockIdx.y) & 1u) ? TABLE_BIT : 0u;
     Fr s = Fr::zero();
     if (live) s = Fr::load_nc(scalars + 4 * (size_t)i).from_mont();  // canonical integer, as `to_repr()` gives
     for_each_digit(s, c, W, [&](int w, u32 d, bool neg) {
         const bool active = live && d != 0;
-        const u32 key = active ? (u32)(w / q) * nbw + (d - 1) : 0;
+        const u32 key = active ? key0 + (u32)(w / q) * nbw + (d - 1) : 0;
         // tiny digits and the (narrow) top window are where hot buckets come from: group them before the atomic
         const u32 slot = warp_agg_add(counters, key, active, d <= 4 || w == W - 1);
-        if (MODE == 1 && active) vals_sorted[slot] = ((u32)(w % q) * n + i) | (neg ? SIGN_BIT : 0u);
+        if (MODE == 1 && active) vals_sorted[slot] = ((u32)(w % q) * n + i) | tbit | (neg ? SIGN_BIT : 0u);
     });
 }
 
@@ -191,8 +202,8 @@ __global__ void __launch_bounds__(256) k_scan_apply(u32 nb, u32 ntiles, const u3
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
-__device__ __forceinline__ Affine load_signed(const Affine* __restrict__ table, u32 val) {
-    Affine p = Affine::load(table + (val & ~SIGN_BIT));
+__device__ __forceinline__ Affine load_signed(const Affine* __restrict__ table, const Affine* __restrict__ table_b, u32 val) {
+    Affine p = Affine::load(((val & TABLE_BIT) ? table_b : table) + (val & ~(SIGN_BIT | TABLE_BIT)));
     if (val & SIGN_BIT) p.y = p.y.neg();
     return p;
 }
@@ -220,7 +231,7 @@ __device__ __forceinline__ u32 bucket_of(const u32* __restrict__ off, u32 lo, u3
 template <bool DIRECT>
 __global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ vals, const u32* __restrict__ off,
                                                        u32 nb_total, const u32* __restrict__ d_L,
-                                                       const Affine* __restrict__ table,
+                                                       const Affine* __restrict__ table, const Affine* __restrict__ table_b,
                                                        XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials, int sh) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 L = __ldg(d_L);
@@ -229,13 +240,12 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const u32* __restrict__ v
     if (cs64 >= mv) return;
     const u32 cs = (u32)cs64;
     const u32 ce = (mv - cs < (u32)L) ? mv : cs + L;
-    auto fetch = [&](u32 i) -> Affine {
-        if (DIRECT) return Affine::load(table + i);
-        return load_signed(table, __ldg(vals + i));
-    };
-
     u32 cur = bucket_of(off, 0, nb_total, cs, sh);
     u32 run_end = offs(off, cur + 1, sh);
+    auto fetch = [&](u32 i) -> Affine {
+        if (DIRECT) return Affine::load(table + i);
+        return load_signed(table, table_b, __ldg(vals + i));
+    };
     XYZZ acc = XYZZ::identity();
     Affine p = fetch(cs);
     for (u32 i = cs; i < ce; i++) {
@@ -403,6 +413,8 @@ __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
 // the sets (`shift` doublings between consecutive sets; one set when the bases are tabulated) and stores the
 // Jacobian result.
 static constexpr int WQ = 256;  // points per CTA of k_weighted_final (64 quads x 4)
+// `nsets` = sets of ONE MSM; the grid covers gridDim.x / (nsets * cta_per_set) MSMs (a group, see MsmScalars): the last
+// CTA of every MSM to finish combines that MSM's sets and stores its result at out + 96 * msm.
 __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__ rc, int ml, int mh, u32 nsets, int shift,
                                                         XYZZ* __restrict__ parts, u32* __restrict__ done,
                                                         void* __restrict__ out) {
@@ -412,7 +424,8 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
     __shared__ u32 is_last;
     const u32 sub_lo = ((1u << ml) + WQ - 1) / WQ, sub_hi = ((1u << mh) + WQ - 1) / WQ;
     const u32 cta_per_set = sub_lo + 2 * sub_hi;
-    const u32 set = blockIdx.x / cta_per_set, c = blockIdx.x % cta_per_set;
+    const u32 set = blockIdx.x / cta_per_set, c = blockIdx.x % cta_per_set;  // set counts across the MSMs of the group
+    const u32 msm = set / nsets;
     const u32 kind = c < sub_lo ? 0 : (c < sub_lo + sub_hi ? 1 : 2);
     const u32 sub = kind == 0 ? c : (kind == 1 ? c - sub_lo : c - sub_lo - sub_hi);
     const u32 per_set = (1u << ml) + 2 * (1u << mh);
@@ -425,7 +438,7 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
     if (threadIdx.x == 0) w.store(parts + (size_t)set * cta_per_set + c);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(done, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(done + msm, 1u) == nsets * cta_per_set - 1);
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -433,7 +446,7 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
     for (u32 s0 = 0; s0 < nsets; s0++) {
         // three quads add the CTA partials of S_lo, S_hi, T of this set
         if (qid < 3) {
-            const XYZZ* p = parts + (size_t)s0 * cta_per_set + (qid == 0 ? 0 : (qid == 1 ? sub_lo : sub_lo + sub_hi));
+            const XYZZ* p = parts + (size_t)(msm * nsets + s0) * cta_per_set + (qid == 0 ? 0 : (qid == 1 ? sub_lo : sub_lo + sub_hi));
             const u32 cnt = qid == 0 ? sub_lo : sub_hi;
             XYZZ a = XYZZ::load(p);
             for (u32 i = 1; i < cnt; i++) quad_add_nl(a, XYZZ::load(p + i));
@@ -456,8 +469,8 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
             quad_add_nl(total, XYZZ::load(vsets + s2));
         }
         if (threadIdx.x == 0) {
-            store_jacobian(total, out);
-            *done = 0;
+            store_jacobian(total, (char*)out + 96 * (size_t)msm);
+            done[msm] = 0;
         }
     }
 }
@@ -589,19 +602,36 @@ static int msm_choose_levels(const h2b_ctx* ctx, int q_is_table) {
     return 0;
 }
 
-void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out,
-             cudaEvent_t after_digits) {
+// m MSMs of the same size through one pipeline (table mode: q == W, one bucket set per MSM; ad-hoc mode: m == 1).
+// The m results are stored at d_out + 96 * j.
+void msm_run_group(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, int W, int q, const void* const* d_scalars, size_t m,
+                   void* d_out, cudaEvent_t after_digits) {
     H2B_REQUIRE(n >= 1 && n <= ((size_t)1 << 27), "msm: n out of range");
     H2B_REQUIRE((size_t)W * n < ((size_t)1 << 31) - 8, "msm: n * windows exceeds the 31-bit table index");
+    H2B_REQUIRE(m >= 1 && m <= (size_t)MSM_MAX_GROUP, "msm: group size out of range");
+    H2B_REQUIRE(m == 1 || q == W, "msm: groups need tabulated bases");
     const u32 nbw = 1u << (c - 1);
-    const u32 nsets = (u32)((W + q - 1) / q);
-    const u32 nb_total = nsets * nbw;
-    const size_t M = (size_t)W * n;
+    const u32 nsets = (u32)((W + q - 1) / q);  // bucket sets of one MSM
+    const u32 nb_group = nsets * nbw;          // buckets of one MSM
+    const u32 nb_total = (u32)m * nb_group;
+    const size_t M = (size_t)W * n * m;
     cudaStream_t st = ctx->stream;
-    const int R = msm_choose_levels(ctx, q == W);  // batch-affine halving passes; groups of G = 2^R entries
+    const int R = m == 1 ? msm_choose_levels(ctx, q == W) : 0;  // batch-affine halving passes; groups of G = 2^R entries
     const size_t G = (size_t)1 << R;
     const size_t Mp = M + (G - 1) * nb_total;  // upper bound of the padded entry count
     H2B_REQUIRE(Mp < ((size_t)1 << 32), "msm: padded entry count exceeds 32 bits");
+    MsmScalars cols;
+    const Affine* tab_a = (const Affine*)d_tables[0];
+    const Affine* tab_b = tab_a;
+    u32 table_mask = 0;  // bit j: MSM j reads the second table
+    for (size_t j = 0; j < (size_t)MSM_MAX_GROUP; j++) cols.p[j] = (const uint64_t*)d_scalars[j < m ? j : 0];
+    for (size_t j = 1; j < m; j++) {
+        if (d_tables[j] == (const void*)tab_a) continue;
+        if (tab_b == tab_a) tab_b = (const Affine*)d_tables[j];
+        H2B_REQUIRE(d_tables[j] == (const void*)tab_b, "msm: a group reads at most two distinct tables");
+        table_mask |= 1u << j;
+    }
+    H2B_REQUIRE(table_mask == 0 || (size_t)W * n < ((size_t)1 << 30), "msm: two-table groups need n * windows < 2^30");
 
     u32* vals = (u32*)ctx->get(WS_VALS_A, Mp * 4 + 16);
     u32* cnt = (u32*)ctx->get(WS_KEYS_A, (2 * ((size_t)nb_total + 2) + nb_total / SCAN_TILE + 8) * 4);  // histogram, cursors, tile sums, L, tile cursor
@@ -634,18 +664,19 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
 
     // counting sort by bucket: histogram -> exclusive scan -> scatter (digits are recomputed, not stored)
     H2B_CUDA(cudaMemsetAsync(hist, 0, ((size_t)nb_total + 1) * 4, st));
-    H2B_LAUNCH(ctx, k_digits<0>, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, hist, (u32*)nullptr);
+    const dim3 dgrid(ceil_div(n, 256), (unsigned)m);
+    H2B_LAUNCH(ctx, k_digits<0>, dgrid, 256, 0, cols, (u32)n, c, W, q, nbw, nsets, table_mask, hist, (u32*)nullptr);
     const u32 ntiles = (nb_total + SCAN_TILE - 1) / SCAN_TILE;
     u32* tile_sums = cursor + nb_total + 2;
     H2B_LAUNCH(ctx, k_scan_tiles, ntiles, 256, 0, hist, nb_total, off, tile_sums, (u32)(G - 1));
     u32* d_L = tile_sums + ntiles + 1;
     H2B_LAUNCH(ctx, k_scan_apply, ntiles, 256, 0, nb_total, ntiles, tile_sums, off, cursor, slots, l_min, l_max, d_L, hist, vals, R);
-    H2B_LAUNCH(ctx, k_digits<1>, ceil_div(n, 256), 256, 0, (const uint64_t*)d_scalars, (u32)n, c, W, q, nbw, cursor, vals);
+    H2B_LAUNCH(ctx, k_digits<1>, dgrid, 256, 0, cols, (u32)n, c, W, q, nbw, nsets, table_mask, cursor, vals);
     if (after_digits) H2B_CUDA(cudaEventRecord(after_digits, st));
 
     H2B_CUDA(cudaMemsetAsync(big, 0, 4, st));
     if (R == 0) {
-        H2B_LAUNCH(ctx, k_accumulate<false>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, d_L, (const Affine*)d_table, buckets, partials, 0);
+        H2B_LAUNCH(ctx, k_accumulate<false>, ceil_div(n_chunks, 128), 128, 0, vals, off, nb_total, d_L, tab_a, tab_b, buckets, partials, 0);
     } else {
         // R halving levels in affine coordinates, one fused launch: every CTA takes its tile through all levels
         static const int BA_K_ENV = [] {  // nominal level-1 pairs per thread and tile (H2B_BA_K: experiments)
@@ -667,12 +698,12 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
         }();
         const bool per_thread = ctx->opt_affine_pt >= 0 ? ctx->opt_affine_pt != 0 : BA_PT_ENV != 0;
         if (per_thread)
-            H2B_LAUNCH(ctx, k_batch_affine<true>, ctx->sm_count * BA_CTAS, BA_T, 0, vals, (const Affine*)d_table, red[0], red[1], red[2], red_pref,
+            H2B_LAUNCH(ctx, k_batch_affine<true>, ctx->sm_count * BA_CTAS, BA_T, 0, vals, tab_a, red[0], red[1], red[2], red_pref,
                        off + nb_total, ba_cursor, R, BA_K);
         else
-            H2B_LAUNCH(ctx, k_batch_affine<false>, ctx->sm_count * BA_CTAS, BA_T, 0, vals, (const Affine*)d_table, red[0], red[1], red[2], red_pref,
+            H2B_LAUNCH(ctx, k_batch_affine<false>, ctx->sm_count * BA_CTAS, BA_T, 0, vals, tab_a, red[0], red[1], red[2], red_pref,
                        off + nb_total, ba_cursor, R, BA_K);
-        H2B_LAUNCH(ctx, k_accumulate<true>, ceil_div(n_chunks, 128), 128, 0, (const u32*)nullptr, off, nb_total, d_L, (const Affine*)red[R - 1], buckets, partials, R);
+        H2B_LAUNCH(ctx, k_accumulate<true>, ceil_div(n_chunks, 128), 128, 0, (const u32*)nullptr, off, nb_total, d_L, (const Affine*)red[R - 1], (const Affine*)nullptr, buckets, partials, R);
     }
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, d_L, partials, buckets, big + 1, big, R);
     XYZZ* seg = (XYZZ*)ctx->get(WS_POOL, (2 * (n_chunks / BIG_SEG) + 64) * sizeof(XYZZ));
@@ -680,18 +711,24 @@ void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, c
     H2B_LAUNCH(ctx, k_collect_big2, 64, 256, 0, off, d_L, seg, buckets, big + 1, big, R);
 
     // bucket reduction: row/column sums of the 2^mh x 2^ml bucket grid, small scalar multiples, final combine
-    const int m = c - 1, ml = (m + 1) / 2, mh = m - ml;
+    const int mm = c - 1, ml = (mm + 1) / 2, mh = mm - ml;
     H2B_REQUIRE(nsets <= 64, "msm: too many bucket sets");
+    const u32 all_sets = nsets * (u32)m;
     const u32 per_set = (1u << ml) + (1u << mh);  // row + column sums (one CTA each)
     const u32 sub_lo = ((1u << ml) + WQ - 1) / WQ, sub_hi = ((1u << mh) + WQ - 1) / WQ;
     const u32 cta_per_set = sub_lo + 2 * sub_hi;
-    XYZZ* rc = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)nsets * (per_set + (1u << mh)) * sizeof(XYZZ));
-    char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)nsets * cta_per_set * sizeof(XYZZ) + 256);
+    XYZZ* rc = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)all_sets * (per_set + (1u << mh)) * sizeof(XYZZ));
+    char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)all_sets * cta_per_set * sizeof(XYZZ) + 256);
     XYZZ* parts = (XYZZ*)rb;
-    u32* done = (u32*)(rb + (size_t)nsets * cta_per_set * sizeof(XYZZ));
-    H2B_CUDA(cudaMemsetAsync(done, 0, 4, st));
-    H2B_LAUNCH(ctx, k_rowcol_sums, nsets * per_set, 128, 0, buckets, ml, mh, nsets, rc);
-    H2B_LAUNCH(ctx, k_weighted_final, nsets * cta_per_set, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
+    u32* done = (u32*)(rb + (size_t)all_sets * cta_per_set * sizeof(XYZZ));  // one counter per MSM of the group
+    H2B_CUDA(cudaMemsetAsync(done, 0, 4 * MSM_MAX_GROUP, st));
+    H2B_LAUNCH(ctx, k_rowcol_sums, all_sets * per_set, 128, 0, buckets, ml, mh, all_sets, rc);
+    H2B_LAUNCH(ctx, k_weighted_final, all_sets * cta_per_set, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
+}
+
+void msm_run(h2b_ctx* ctx, const void* d_table, size_t n, int c, int W, int q, const void* d_scalars, void* d_out,
+             cudaEvent_t after_digits) {
+    msm_run_group(ctx, &d_table, n, c, W, q, &d_scalars, 1, d_out, after_digits);
 }
 
 void g1_sum_run(h2b_ctx* ctx, const void* d_points, size_t m, void* d_out) {
@@ -730,16 +767,37 @@ struct LaneScope {
     }
 };
 
+// How many MSMs of a batch share one pipeline (msm_run_group).  Large domains: the accumulation dominates and lanes of
+// single MSMs overlap one MSM's sort / tail with the next one's accumulation; small domains (k <= 17, the shards of a
+// multi-GPU run) are bound by the latency of the bucket reduction, which a group pays once.
+size_t msm_group_size(const h2b_ctx* ctx, size_t n, size_t m, int W) {
+    if (msm_choose_levels(ctx, 1) > 0) return 1;  // the batch-affine passes are built for one MSM at a time
+    static const int forced = [] {
+        const char* e = getenv("H2B_MSM_GROUP");
+        return e ? atoi(e) : 0;
+    }();
+    size_t g = ctx->opt_msm_group > 0 ? (size_t)ctx->opt_msm_group : (forced > 0 ? (size_t)forced : 0);
+    if (g == 0) {
+        const int lg = ceil_log2(n);
+        g = lg <= 17 ? MSM_MAX_GROUP : (lg <= 19 ? (m + 1) / 2 : (m + 2) / 3);
+    }
+    if (g > (size_t)MSM_MAX_GROUP) g = MSM_MAX_GROUP;
+    while (g > 1 && g * (size_t)W * n >= ((size_t)1 << 32)) g--;  // sorted positions are 32-bit
+    return g < 1 ? 1 : g;
+}
+
 void msm_run_batch(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, int W, const void* const* d_scalars, size_t m,
                    void* d_out) {
     if (m == 0) return;
-    if (m == 1) {  // nothing to overlap: stay on the caller's stream
-        msm_run(ctx, d_tables[0], n, c, W, W, d_scalars[0], d_out);
+    const size_t gsz = msm_group_size(ctx, n, m, W);
+    const size_t ngroups = (m + gsz - 1) / gsz;
+    if (ngroups == 1) {  // nothing to overlap: stay on the caller's stream
+        msm_run_group(ctx, d_tables, n, c, W, W, d_scalars, m, d_out, nullptr);
         return;
     }
     cudaStream_t main = ctx->stream;
     H2B_CUDA(cudaEventRecord(ctx->fork_ev, main));
-    const int nl = (int)(m < (size_t)h2b_ctx::NLANES ? m : (size_t)h2b_ctx::NLANES);
+    const int nl = (int)(ngroups < (size_t)h2b_ctx::NLANES ? ngroups : (size_t)h2b_ctx::NLANES);
     for (int l = 0; l < nl; l++) H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork_ev, 0));
     struct Join {  // the lanes are joined back onto the caller's stream on every exit path (a throw included)
         h2b_ctx* c; cudaStream_t main; int nl;
@@ -750,9 +808,13 @@ void msm_run_batch(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, i
             }
         }
     } join{ctx, main, nl};
-    for (size_t j = 0; j < m; j++) {
-        LaneScope scope(ctx, (int)(j % nl));
-        msm_run(ctx, d_tables[j], n, c, W, W, d_scalars[j], (char*)d_out + 96 * j);
+    // balanced groups (sizes differ by at most one), dealt to the lanes round-robin
+    size_t j = 0;
+    for (size_t g = 0; g < ngroups; g++) {
+        const size_t cnt = m / ngroups + (g < m % ngroups ? 1 : 0);
+        LaneScope scope(ctx, (int)(g % nl));
+        msm_run_group(ctx, d_tables + j, n, c, W, W, d_scalars + j, cnt, (char*)d_out + 96 * j, nullptr);
+        j += cnt;
     }
 }
 

@@ -76,6 +76,8 @@ int h2b_ctx_side_join(h2b_ctx* ctx);
  *   "msm.affine_k"       multiple of 4 in [8, 128] (-1 = default 32): pairs per thread and tile of those levels
  *   "msm.affine_per_thread_inverse"  1: every thread inverts its own denominator product (constant-time safegcd), 0: one
  *                        inversion per tile (product tree + single lane); -1 = default
+ *   "msm.batch_group"    1..16 (0 = default, chosen from the domain size): how many MSMs of one batch call share a single
+ *                        sort / accumulate / bucket-reduction pipeline (1 = every MSM runs its own, on one of three lanes)
  * and one switch that selects between two equally valid outputs (see h2b_permute_expression_pair):
  *   "lookup.leftover_order"  0 (default): left-over table values fill the repeated rows front to back; 1: from the back */
 int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value);

@@ -105,7 +105,12 @@ int main() {
             return c;
         };
         auto pr = permute_expression_pair(ctx, col({9, 2, 9, 9, 4}), col({4, 9, 9, 2, 7}), 3, 2);
+        // left-over table values (7, 9) fill the repeated rows front to back by default, from the back with the zcash option
+        CHECK(pr.first == col({2, 4, 9, 9, 9}) && pr.second == col({2, 4, 9, 7, 9}));
+        ctx.check(h2b_ctx_set_option(ctx.raw(), "lookup.leftover_order", 1));
+        pr = permute_expression_pair(ctx, col({9, 2, 9, 9, 4}), col({4, 9, 9, 2, 7}), 3, 2);
         CHECK(pr.first == col({2, 4, 9, 9, 9}) && pr.second == col({2, 4, 9, 9, 7}));
+        ctx.check(h2b_ctx_set_option(ctx.raw(), "lookup.leftover_order", 0));
         threw = false;
         try { permute_expression_pair(ctx, col({9, 2, 9, 9, 5}), col({4, 9, 9, 2, 7}), 3, 2); } catch (const Error& e) { threw = e.code == H2B_ERR_UNSATISFIED; }
         CHECK(threw);

@@ -222,6 +222,53 @@ def test_msm_closed_form_large(ctx, h2b):
     params.close()
 
 
+@pytest.mark.parametrize("group", [0, 1, 2, 3, 5, 16])
+def test_msm_group_pipeline(h2b, group):
+    """option "msm.batch_group": the MSMs of one batch call share ONE sort / accumulate / bucket-reduction pipeline (bucket
+    sets side by side, sorted entries carry the table bit).  Whatever the grouping, every commitment is the oracle's: two
+    distinct bases mixed inside a group, an all-zero column, a hot-bucket column, witness-like and uniform columns, batches
+    longer than a group and longer than groups x lanes — through the device-pointer and the host-pointer batch calls."""
+    import torch
+    c = h2b.Context(0)
+    c.set_option("msm.batch_group", group)
+    try:
+        rng = np.random.default_rng(4242 + group)
+        for k, m in [(9, 13), (12, 7), (6, 35)]:
+            n = 1 << k
+            Bm = _bases(c, n, a0=3 + k, delta=5)
+            Bl = _bases(c, n, a0=1000 + k, delta=7)
+            Bl[2] = 0  # identity base in one of the two tables
+            cols = []
+            for j in range(m):
+                if j == 1:
+                    sc = [0] * n
+                elif j == 2:
+                    sc = [1] * (n - 9) + rand_ints(rng, 9, R)
+                elif j % 3 == 0:
+                    sc = witness_like_ints(rng, n)
+                else:
+                    sc = rand_ints(rng, n, R)
+                cols.append(mont(sc, R))
+            basis = [(j * 7 // 3) % 2 for j in range(m)]
+            want = [orc.msm_pippenger(cols[j], Bl if basis[j] else Bm) for j in range(m)]
+            params = h2b.ParamsKZG(c, k, g=Bm, g_lagrange=Bl)
+            outs = params.commit_batch(basis, cols)  # host pointers
+            for j in range(m):
+                assert np.array_equal(norm(c, outs[j]), want[j]), (k, j, "host")
+            d_cols = [torch.from_numpy(x.view(np.int64)).cuda() for x in cols]
+            d_out = torch.zeros((m, 12), dtype=torch.int64, device="cuda")
+            params.commit_batch_dev(basis, [t.data_ptr() for t in d_cols], n, d_out.data_ptr())
+            torch.cuda.synchronize()
+            outs = d_out.cpu().numpy().view(np.uint64)
+            for j in range(m):
+                assert np.array_equal(norm(c, outs[j]), want[j]), (k, j, "dev")
+            params.close()
+        with pytest.raises(h2b.H2BError):
+            c.set_option("msm.batch_group", 17)
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("levels,per_thread", [(1, 0), (2, 0), (3, 0), (2, 1), (3, 1)])
 def test_msm_batch_affine_levels(h2b, levels, per_thread):
     """the opt-in batch-affine bucket reduction (csrc/batch_affine.cuh): groups of 2^levels sorted entries are summed in
