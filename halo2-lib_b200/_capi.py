@@ -116,6 +116,7 @@ SIGNATURES = {
     "h2b_params_raw_view": (_int, [_vp, _sz, C.POINTER(_u32), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "h2b_permute_expression_pair": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "h2b_permute_expression_pair_dev": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "h2b_permute_expression_pair_async_dev": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "h2b_quotient_graph": (_int, [_vp, _gp, _u32, _u32, _vp]),
     "h2b_quotient_graph_dev": (_int, [_vp, _gp, _u32, _u32, _vp]),
     "h2b_permutation_fold": (_int, [_vp, _vpp, _sz, _vpp, _vpp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),

@@ -1158,6 +1158,16 @@ int h2b_permute_expression_pair_dev(h2b_ctx* ctx, const void* d_input, const voi
             throw StatusError{H2B_ERR_UNSATISFIED, "permute_expression_pair: an input value is not in the table (ConstraintSystemFailure)"};
     });
 }
+int h2b_permute_expression_pair_async_dev(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
+                                          void* d_permuted_input, void* d_permuted_table, uint32_t* d_status) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(d_input && d_table && d_permuted_input && d_permuted_table && d_status, "permute_expression_pair: null pointer");
+        H2B_REQUIRE(d_input != d_permuted_input && d_table != d_permuted_table && d_input != d_permuted_table && d_table != d_permuted_input,
+                    "permute_expression_pair: outputs must not alias inputs");
+        const uint32_t* v = permute_expression_pair_enqueue(ctx, d_input, d_table, k, blinding_factors, d_permuted_input, d_permuted_table);
+        H2B_CUDA(cudaMemcpyAsync(d_status, v, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    });
+}
 int h2b_permute_expression_pair(h2b_ctx* ctx, const uint64_t* input, const uint64_t* table, uint32_t k, uint32_t blinding_factors,
                                 uint64_t* permuted_input, uint64_t* permuted_table) {
     return guarded(ctx, [&] {

@@ -214,6 +214,8 @@ void permutation_fold_run(h2b_ctx* ctx, const void* const* d_z, size_t n_sets, c
                           const uint64_t beta[4], const uint64_t gamma[4], const uint64_t y[4], uint32_t blinding_factors, uint32_t k,
                           uint32_t ext_k, void* d_values);
 // ---- lookup.cu (returns true when an input value is missing from the table)
+uint32_t* permute_expression_pair_enqueue(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
+                                          void* d_permuted_input, void* d_permuted_table);  // enqueue only; returns the device verdict word
 bool permute_expression_pair_run(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
                                  void* d_permuted_input, void* d_permuted_table);
 // ---- srs.cu

@@ -23,7 +23,7 @@ import ctypes as C
 import hashlib
 import numpy as np
 from ._capi import lib, BASIS_MONOMIAL, BASIS_LAGRANGE
-from .host import Context, ParamsKZG
+from .host import Context, ParamsKZG, H2BError
 from . import evaluation as ev
 
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
@@ -297,10 +297,16 @@ class ProverSession:
         side_transforms([(self.a, self.ac, "a")])
         # ---- lookup: compressed input q_lookup * a, permuted pair
         ctx.check(lib.h2b_fr_mul_elementwise_dev(ctx.h, vp(cs.lagr["q_lookup"].ptr), vp(self.a.ptr), n, vp(self.inp.ptr)))
-        ctx.check(lib.h2b_permute_expression_pair_dev(ctx.h, vp(self.inp.ptr), vp(cs.lagr["table"].ptr), k, bf, vp(self.pa.ptr), vp(self.ps.ptr)))
+        # enqueue only: the verdict ("an input value is not in the table") lands in the last element of d_out and is read
+        # right after the commitments of this phase, whose download synchronises anyway
+        ctx.check(lib.h2b_permute_expression_pair_async_dev(ctx.h, vp(self.inp.ptr), vp(cs.lagr["table"].ptr), k, bf, vp(self.pa.ptr),
+                                                            vp(self.ps.ptr), vp(self.d_out.at(15))))
         self._blind(self.pa, u, rng)
         self._blind(self.ps, u, rng)
         cm = self._commit([(BASIS_LAGRANGE, self.pa.ptr), (BASIS_LAGRANGE, self.ps.ptr)])
+        if int(self.d_out.download(15, 1)[0, 0]) & 0xffffffff:
+            raise H2BError(-5, "permute_expression_pair: an input value is not in the table (ConstraintSystemFailure)")
+        self.d2h_bytes += 32
         res["commitments"] += list(cm); tr.absorb(cm)
         beta, gamma = tr.squeeze(), tr.squeeze()
         bl, gl = to_limbs(beta), to_limbs(gamma)

@@ -271,11 +271,15 @@ int h2b_grand_product_fr_dev(h2b_ctx* ctx, const void* d_f, const uint64_t start
  * of PSE halo2 and its forks, recalled for halo2-axiom 0.5.3) or, with option "lookup.leftover_order" = 1, from the last
  * repeated row backwards (zcash halo2's BTreeMap + pop).  Both satisfy the argument; the choice only shows in the proof
  * bytes.  Rows >= u of both outputs are NOT written (the prover puts its blinding scalars there).  Outputs must not alias inputs.  H2B_ERR_UNSATISFIED when an input value is missing from the table.
- * The `_dev` form synchronises the stream (it has to read the verdict). */
+ * The `_dev` form synchronises the stream (it has to read the verdict); `_async_dev` does not: it enqueues everything and
+ * leaves the verdict in the caller's device word *d_status (0 = satisfied; bit 0 = an input value is missing from the
+ * table), to be read whenever the caller next synchronises (the resident prover reads it with the proof's evaluations). */
 int h2b_permute_expression_pair(h2b_ctx* ctx, const uint64_t* input, const uint64_t* table, uint32_t k, uint32_t blinding_factors,
                                 uint64_t* permuted_input, uint64_t* permuted_table);
 int h2b_permute_expression_pair_dev(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
                                     void* d_permuted_input, void* d_permuted_table);
+int h2b_permute_expression_pair_async_dev(h2b_ctx* ctx, const void* d_input, const void* d_table, uint32_t k, uint32_t blinding_factors,
+                                          void* d_permuted_input, void* d_permuted_table, uint32_t* d_status);
 
 /* ---- quotient evaluation, first slice: the custom-gate term of halo2-base's vertical gate
  * `q * (a + b*c - out)` (halo2-base/src/gates/flex_gate/mod.rs:80-91) on the extended coset domain, folded as the

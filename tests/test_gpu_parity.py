@@ -546,7 +546,7 @@ def test_assign_witnesses_from_assigned_records(ctx, h2b):
         h2b.assign_witnesses_assigned(ctx, cells, bp, k, ncols)
     # many columns (> 64: the staged-span path) still match the walk
     k2, nc2 = 5, 70
-    V = mont(rand_ints(rng, 31 * 40, R), R)
+    V = mont(rand_ints(rng, 31 + 39 * 30 + 25, R), R)  # 40 full columns (a break cell is copied into the next column) + 25 cells
     bp2 = np.array([30] * 40, dtype=np.uint64)
     rc, want = orc.assign_witnesses(V, bp2, k2, nc2)
     assert rc == 0

@@ -324,7 +324,8 @@ def test_quotient_device_pointers_full_size(ctx, h2b):
 
 
 # ------------------------------------------------------------------ lookup argument: permute_expression_pair
-@pytest.mark.parametrize("kind,k", [("range", 7), ("dup_table", 9), ("wide", 10), ("all_same", 8), ("perm", 9), ("range", 16), ("wide", 15)])
+@pytest.mark.parametrize("kind,k", [("range", 4), ("range", 7), ("dup_table", 9), ("wide", 10), ("all_same", 8), ("perm", 9), ("range", 16), ("wide", 15),
+                                    ("wide", 18), ("dup_table", 17)])
 def test_permute_expression_pair(ctx, h2b, kind, k):
     from test_oracle_quotient import lookup_columns
     bf = 5
@@ -361,6 +362,35 @@ def test_permute_expression_pair_zcash_order_option(h2b):
         assert np.array_equal(pa, wa) and np.array_equal(pt, wt)
     finally:
         c.close()
+
+
+def test_permute_expression_pair_async_keeps_the_verdict_on_the_device(ctx, h2b):
+    """h2b_permute_expression_pair_async_dev: no host synchronisation, the verdict is a device word"""
+    import torch
+    from halo2_lib_b200._capi import lib
+    from test_oracle_quotient import lookup_columns
+    k, bf = 11, 5
+    rng = np.random.default_rng(2290)
+    u = (1 << k) - (bf + 1)
+    inputs, table = lookup_columns(rng, k, bf, "range")
+    pad = rand_ints(rng, bf + 1, R)
+    A, T = mont(inputs + pad, R), mont(table + pad, R)
+    rc, wa, wt = orc.permute_expression_pair(A, T, k, bf)
+    assert rc == 0
+    vp = C.c_void_p
+    dA, dT = torch.from_numpy(A.view(np.int64)).cuda(), torch.from_numpy(T.view(np.int64)).cuda()
+    dpa, dpt = torch.zeros_like(dA), torch.zeros_like(dT)
+    st = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    ctx.check(lib.h2b_permute_expression_pair_async_dev(ctx.h, vp(dA.data_ptr()), vp(dT.data_ptr()), k, bf, vp(dpa.data_ptr()), vp(dpt.data_ptr()), vp(st.data_ptr())))
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    assert np.array_equal(dpa.cpu().numpy().view(np.uint64)[:u], wa[:u]) and np.array_equal(dpt.cpu().numpy().view(np.uint64)[:u], wt[:u])
+    A2 = A.copy()
+    A2[3] = mont([(1 << 200) + 12345], R)[0]  # not in the table
+    dA2 = torch.from_numpy(A2.view(np.int64)).cuda()
+    ctx.check(lib.h2b_permute_expression_pair_async_dev(ctx.h, vp(dA2.data_ptr()), vp(dT.data_ptr()), k, bf, vp(dpa.data_ptr()), vp(dpt.data_ptr()), vp(st.data_ptr())))
+    torch.cuda.synchronize()
+    assert int(st.item()) & 1
 
 
 def test_permute_expression_pair_missing_value_and_bad_arguments(ctx, h2b):

@@ -108,6 +108,13 @@ dPA, dPT = torch.zeros_like(dA), torch.zeros_like(dT)
 timeit(f"permute_expression_pair 2^{k} rows (16-bit range table)",
        lambda: ctx.check(lib.h2b_permute_expression_pair_dev(ctx.h, vp(dA.data_ptr()), vp(dT.data_ptr()), k, bfq, vp(dPA.data_ptr()), vp(dPT.data_ptr()))),
        32 * u * 4, cpu=lambda: orc.permute_expression_pair(Am, Tm, k, bfq), reps=3)
+# the same with full-width values (a theta-compressed multi-column lookup): all 32 byte positions take part in the sort
+Tw = host[3][:n].copy()
+Aw = Tw[rng.integers(0, u, size=n)]
+dTw, dAw = torch.from_numpy(Tw.view(np.int64)).to(dev), torch.from_numpy(Aw.view(np.int64)).to(dev)
+timeit(f"permute_expression_pair 2^{k} rows (254-bit values)",
+       lambda: ctx.check(lib.h2b_permute_expression_pair_dev(ctx.h, vp(dAw.data_ptr()), vp(dTw.data_ptr()), k, bfq, vp(dPA.data_ptr()), vp(dPT.data_ptr()))),
+       32 * u * 4, reps=3)
 # keygen side: G1 FFT of 2^16 points (once per SRS; 2^19 is 8 x the points and 19/16 x the stages)
 if not QUICK:
     kk = 16
