@@ -19,8 +19,8 @@
 
 namespace h2b {
 
-static constexpr int NTT_THREADS = 256;
-static constexpr int NTT_TILE_LOG = 11;  // elements per tile (2^11 * 32 B = 64 KB of shared memory)
+static constexpr int NTT_THREADS = 256;   // upper bound; small tiles run with TILE / 4 threads (one radix-4 group each)
+static constexpr int NTT_TILE_LOG = 11;  // largest tile: 2^11 elements * 32 B = 64 KB of shared memory
 static constexpr int NTT_MAX_R = 11;  // one column of the largest digit = 2^11 * 32 B = the whole 64 KB tile
 
 // Fr::ZETA and ZETA^2 in Montgomery form (halo2curves bn256::Fr::ZETA); the same values are
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
     SmemFr sm{smem_raw, smem_raw + TILE};
     const u32 col0 = blockIdx.x << cwl;
     const int tid = threadIdx.x;
+    const u32 NT = blockDim.x;
 
     // shared index of (row, c): the last pass keeps columns contiguous (its global rows are contiguous)
     auto sidx = [&](u32 row, u32 c) -> u32 { return LAST ? (c << r) + row : (row << cwl) + c; };
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
     };
 
     // ---- load
-    for (u32 e = tid; e < TILE; e += NTT_THREADS) {
+    for (u32 e = tid; e < TILE; e += NT) {
         u32 row, c;
         if (LAST) { row = e & (R - 1); c = e >> r; } else { c = e & (CW - 1); row = e >> cwl; }
         size_t g = gaddr(row, col0 + c);
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
     int s = 0;
     for (; s + 1 < r; s += 2) {
         const u32 half = 1u << (r - 1 - s), quarter = half >> 1;
-        for (u32 q4 = tid; q4 < (NBF >> 1); q4 += NTT_THREADS) {
+        for (u32 q4 = tid; q4 < (NBF >> 1); q4 += NT) {
             u32 c, pi;
             if (LAST) { pi = q4 & ((R >> 2) - 1); c = q4 >> (r - 2); } else { c = q4 & (CW - 1); pi = q4 >> cwl; }
             const u32 j = pi & (quarter - 1), grp = pi >> (r - 2 - s);
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
     }
     for (; s < r; s++) {
         const u32 half = 1u << (r - 1 - s);
-        for (u32 q = tid; q < NBF; q += NTT_THREADS) {
+        for (u32 q = tid; q < NBF; q += NT) {
             u32 c, pi;
             if (LAST) { pi = q & ((R >> 1) - 1); c = q >> (r - 1); } else { c = q & (CW - 1); pi = q >> cwl; }
             u32 j = pi & (half - 1), grp = pi >> (r - 1 - s);
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
     }
 
     // ---- store: row i of the column is at bit-reversed shared position
-    for (u32 e = tid; e < TILE; e += NTT_THREADS) {
+    for (u32 e = tid; e < TILE; e += NT) {
         u32 c = e & (CW - 1), row = e >> cwl;
         u32 col = col0 + c;
         u32 rrow = __brev(row) >> (32 - r);
@@ -346,6 +347,17 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
     }
     Fr* scratch = nullptr;
     if (p->npass > 1) scratch = (Fr*)ctx->get(WS_NTT_B, n * sizeof(Fr));
+    // Tile size: 2^11 elements for large transforms; smaller domains take smaller tiles so that the grid still covers the
+    // GPU several times over (2^19: 512 CTAs of 2^10 instead of 256 of 2^11; 2^16: 256 CTAs instead of 32) — the passes are
+    // latency-bound there, more resident warps hide the multiplier's dependent chains.
+    static const int tile_env = [] {
+        const char* e = getenv("H2B_NTT_TILE");
+        return e ? atoi(e) : 0;
+    }();
+    int r_max = 0;
+    for (int t = 0; t < p->npass; t++) r_max = std::max(r_max, p->r[t]);
+    int tile_log = std::min(NTT_TILE_LOG, std::max(r_max, (int)log_n - 10));
+    if (tile_env >= r_max && tile_env <= NTT_TILE_LOG) tile_log = tile_env;
     int consumed = 0;
     for (int t = 0; t < p->npass; t++) {
         const bool last = (t == p->npass - 1), first = (t == 0);
@@ -357,7 +369,7 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
         a.r = p->r[t];
         a.logM = (int)log_n - consumed - a.r;
         int cols_log = (int)log_n - a.r;
-        a.cw_log = NTT_TILE_LOG - a.r;
+        a.cw_log = tile_log - a.r;
         if (a.cw_log > cols_log) a.cw_log = cols_log;
         if (a.cw_log < 0) a.cw_log = 0;
         a.first = first;
@@ -370,8 +382,9 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
         a.coset = coset_mode;
         const unsigned grid = 1u << (cols_log - a.cw_log);
         const size_t smem = sizeof(Fr) << (a.r + a.cw_log);
-        if (last) H2B_LAUNCH(ctx, k_ntt_pass<true>, grid, NTT_THREADS, smem, a);
-        else H2B_LAUNCH(ctx, k_ntt_pass<false>, grid, NTT_THREADS, smem, a);
+        const unsigned threads = (unsigned)std::min(NTT_THREADS, std::max(32, (1 << (a.r + a.cw_log)) / 4));
+        if (last) H2B_LAUNCH(ctx, k_ntt_pass<true>, grid, threads, smem, a);
+        else H2B_LAUNCH(ctx, k_ntt_pass<false>, grid, threads, smem, a);
         consumed += a.r;
     }
 }

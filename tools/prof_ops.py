@@ -49,6 +49,13 @@ def run(label, fn, reps=5):
 
 for name, col in cols.items():
     run(f"MSM 2^{k} {name}", lambda: params.commit_dev(0, col.data_ptr(), n, out.data_ptr()))
+# a prover phase of 4 commitments: every MSM on its own lane (msm.batch_group = 1) against one shared pipeline (= 4)
+four = [torch.from_numpy(bench.uniform_residues(rng, n).view(np.int64)).to(dev) for _ in range(4)]
+out4 = torch.zeros((4, 12), dtype=torch.int64, device=dev)
+for grp in (1, 4):
+    ctx.set_option("msm.batch_group", grp)
+    run(f"4 x MSM 2^{k} uniform, msm.batch_group = {grp}", lambda: params.commit_batch_dev(0, [c.data_ptr() for c in four], n, out4.data_ptr()))
+ctx.set_option("msm.batch_group", 0)
 poly = cols["uniform"].clone()
 ext = torch.empty((4 * n, 4), dtype=torch.int64, device=dev)
 run(f"iNTT 2^{k}", lambda: ctx.check(lib.h2b_lagrange_to_coeff_dev(ctx.h, C.c_void_p(poly.data_ptr()), k)))
