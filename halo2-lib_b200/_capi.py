@@ -55,6 +55,7 @@ SIGNATURES = {
     "h2b_profile_enable": (_int, [_vp, C.c_char_p]),
     "h2b_profile_reset": (_int, [_vp]),
     "h2b_profile_read": (_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "h2b_profile_dump": (_int, [_vp, _vp, C.c_char_p]),
     "h2b_srs_upload": (_int, [_vp, _vp, _vp, _u32, _sz, _sz, C.POINTER(_vp)]),
     "h2b_srs_upload_dev": (_int, [_vp, _vp, _vp, _u32, _sz, _sz, C.POINTER(_vp)]),
     "h2b_srs_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),

@@ -130,6 +130,14 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
         for (auto& ev : ctx->ev) H2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (int l = 0; l < h2b_ctx::NLANES; l++) {
             H2B_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+            {   // the bucket reduction of a lane's MSM runs on a HIGH-priority stream: its few CTAs take the SM slots that free
+                // up first instead of queueing behind the next MSM's accumulation waves (see msm_run_group)
+                int lo_prio = 0, hi_prio = 0;
+                H2B_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+                H2B_CUDA(cudaStreamCreateWithPriority(&ctx->lane_tail[l], cudaStreamNonBlocking, hi_prio));
+            }
+            H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_acc[l], cudaEventDisableTiming));
+            H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_tail_done[l], cudaEventDisableTiming));
             H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_done[l], cudaEventDisableTiming));
             H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_ready[l], cudaEventDisableTiming));
             H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_consumed[l], cudaEventDisableTiming));
@@ -210,6 +218,9 @@ void h2b_ctx_destroy(h2b_ctx* ctx) {
             if (b.p) cudaFree(b.p);
     for (int l = 0; l < h2b_ctx::NLANES; l++) {
         if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+        if (ctx->lane_tail[l]) cudaStreamDestroy(ctx->lane_tail[l]);
+        if (ctx->lane_acc[l]) cudaEventDestroy(ctx->lane_acc[l]);
+        if (ctx->lane_tail_done[l]) cudaEventDestroy(ctx->lane_tail_done[l]);
         if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
         if (ctx->lane_ready[l]) cudaEventDestroy(ctx->lane_ready[l]);
         if (ctx->lane_consumed[l]) cudaEventDestroy(ctx->lane_consumed[l]);
@@ -272,6 +283,7 @@ int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value) {
         if (k == "msm.affine_levels") { H2B_REQUIRE(value >= -1 && value <= 3, "msm.affine_levels: -1 (default) .. 3"); ctx->opt_affine_levels = (int)value; }
         else if (k == "msm.affine_k") { H2B_REQUIRE(value == -1 || (value >= 8 && value <= 128 && value % 4 == 0), "msm.affine_k: multiple of 4 in [8, 128]"); ctx->opt_affine_k = (int)value; }
         else if (k == "msm.affine_per_thread_inverse") { H2B_REQUIRE(value >= -1 && value <= 1, "msm.affine_per_thread_inverse: -1, 0 or 1"); ctx->opt_affine_pt = (int)value; }
+        else if (k == "msm.tail_priority") { H2B_REQUIRE(value >= -1 && value <= 1, "msm.tail_priority: -1 (default), 0 or 1"); ctx->opt_tail_priority = (int)value; }
         else if (k == "msm.batch_group") { H2B_REQUIRE(value >= 0 && value <= 16, "msm.batch_group: 0 (default) .. 16 MSMs per pipeline"); ctx->opt_msm_group = (int)value; }
         else if (k == "lookup.leftover_order") { H2B_REQUIRE(value == 0 || value == 1, "lookup.leftover_order: 0 (front to back) or 1 (zcash: from the back)"); ctx->opt_lookup_backward = (int)value; }
         else H2B_REQUIRE(false, "set_option: unknown key");
@@ -325,6 +337,27 @@ int h2b_profile_read(h2b_ctx* ctx, const char* kernel, double* total_ms, uint64_
         }
         *total_ms = ms;
         *launches = cnt;
+    });
+}
+
+// Timeline of the recorded launches: one CSV line per launch — kernel, stream, start and end in microseconds after
+// `origin` (an event the caller recorded; pass the same one to several contexts of a device to align their timelines).
+int h2b_profile_dump(h2b_ctx* ctx, void* origin_cuda_event, const char* path) {
+    return guarded(ctx, [&] {
+        H2B_REQUIRE(origin_cuda_event && path, "profile_dump: null pointer");
+        H2B_CUDA(cudaDeviceSynchronize());
+        FILE* f = fopen(path, "a");
+        H2B_REQUIRE(f, "profile_dump: cannot open the file");
+        for (auto& r : ctx->prof_recs) {
+            float a = 0, b = 0;
+            if (cudaEventElapsedTime(&a, (cudaEvent_t)origin_cuda_event, r.a) != cudaSuccess ||
+                cudaEventElapsedTime(&b, (cudaEvent_t)origin_cuda_event, r.b) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            fprintf(f, "%s,%p,%.1f,%.1f\n", r.name, (void*)r.stream, a * 1e3, b * 1e3);
+        }
+        fclose(f);
     });
 }
 
@@ -517,6 +550,7 @@ static void* msm_batch_enqueue(h2b_ctx* ctx, const h2b_srs* srs, const int* basi
         ~Join() {
             c->stream = ks;
             c->cur_lane = 0;
+            c->in_lane = false;
             for (int l = 0; l < nl; l++) {
                 cudaEventRecord(c->lane_done[l], c->lane_stream[l]);
                 cudaStreamWaitEvent(ks, c->lane_done[l], 0);
@@ -538,7 +572,9 @@ static void* msm_batch_enqueue(h2b_ctx* ctx, const h2b_srs* srs, const int* basi
         H2B_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_ready[l], 0));
         ctx->stream = ctx->lane_stream[l];
         ctx->cur_lane = l;
+        ctx->in_lane = true;
         msm_run_group(ctx, tables.data() + j, n, srs->c, srs->W, srs->W, d_cols, cnt, (char*)d_out + 96 * j, ctx->lane_consumed[l]);
+        ctx->in_lane = false;
         j += cnt;
     }
     return d_out;

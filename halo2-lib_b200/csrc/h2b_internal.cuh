@@ -91,6 +91,7 @@ struct h2b_ctx {
     int opt_affine_levels = -1;  // h2b_ctx_set_option("msm.affine_levels"): -1 = default
     int opt_affine_k = -1;       // "msm.affine_k"
     int opt_affine_pt = -1;      // "msm.affine_per_thread_inverse": 1 = every thread inverts (safegcd), 0 = one inversion per tile
+    int opt_tail_priority = -1;  // "msm.tail_priority": bucket reductions of lane MSMs on high-priority streams (-1 = default on)
     int opt_msm_group = 0;       // "msm.batch_group": MSMs of a batch call that share one sort / accumulate / reduce pipeline (0 = by size)
     int opt_lookup_backward = 0; // "lookup.leftover_order": 0 = front to back (PSE / axiom walk), 1 = zcash (pop from the back)
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce
@@ -105,6 +106,10 @@ struct h2b_ctx {
     // reduction: a few CTAs) overlaps the throughput-bound phases of the next MSM of the same batch
     static constexpr int NLANES = 3;
     cudaStream_t lane_stream[NLANES] = {nullptr, nullptr, nullptr};
+    cudaStream_t lane_tail[NLANES] = {nullptr, nullptr, nullptr};     // high priority: the bucket reduction of the lane's MSM
+    cudaEvent_t lane_acc[NLANES] = {nullptr, nullptr, nullptr};       // accumulation of the lane's MSM enqueued
+    cudaEvent_t lane_tail_done[NLANES] = {nullptr, nullptr, nullptr};
+    bool in_lane = false;                                             // the current stream is lane_stream[cur_lane]
     cudaEvent_t lane_done[NLANES] = {nullptr, nullptr, nullptr};
     cudaEvent_t lane_ready[NLANES] = {nullptr, nullptr, nullptr};     // staging buffer filled (host batch API)
     cudaEvent_t lane_consumed[NLANES] = {nullptr, nullptr, nullptr};  // staging buffer read by k_digits
@@ -119,6 +124,7 @@ struct h2b_ctx {
     struct ProfRec {
         const char* name;
         cudaEvent_t a, b;
+        cudaStream_t stream;
     };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
@@ -156,7 +162,7 @@ namespace h2b {
         H2B_CUDA(cudaGetLastError());                                            \
         if (_prof) {                                                             \
             H2B_CUDA(cudaEventRecord(_eb, (ctx)->stream));                       \
-            (ctx)->prof_recs.push_back({#kernel, _ea, _eb});                     \
+            (ctx)->prof_recs.push_back({#kernel, _ea, _eb, (ctx)->stream});                     \
         }                                                                        \
     } while (0)
 

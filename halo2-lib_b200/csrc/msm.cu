@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ of
 // multiplications lo * R_lo / hi * C_hi (one thread each) and ~10 for the block sums and the final doublings.
 // One CTA of 128 threads (32 lane-quads, quad.cuh) per row sum R_lo / column sum C_hi: every quad adds its
 // stride-32 share of the row (column), then the 32 quads are summed and the result is multiplied by its weight.
-// rc[set] = [ lo * R_lo (2^ml) | hi * C_hi (2^mh) | C_hi (2^mh) ].
+// rc[set] = [ lo * R_lo (2^ml) | hi * C_hi (2^mh) | C_hi (2^mh) ] after k_rowcol_weights.
 __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ buckets, int ml, int mh, u32 nsets,
                                                      XYZZ* __restrict__ rc) {
     __shared__ XYZZ sh[4];
@@ -379,16 +379,27 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ bu
         for (u32 lo = qid; lo < (1u << ml); lo += 32) quad_add(acc, XYZZ::load(base + ((size_t)hi << ml) + lo));
     }
     acc = quad_block_sum<true>(acc, sh);
-    // quad 0 of warp 0 holds the sum: store it already multiplied by its weight (lo for a row, hi for a column) so
-    // that the final kernel only has plain sums left; the plain column sums are kept too (T = sum of all buckets)
-    if (threadIdx.x < 4) {
+    // quad 0 of warp 0 holds the sum.  The weights (lo for a row, hi for a column) are applied by k_rowcol_weights: a
+    // double-and-add chain on ONE quad would keep this CTA's four warps resident for as long again, and with the bucket
+    // sets of a whole group of MSMs in one launch the CTAs no longer fit in one wave.
+    if (threadIdx.x == 0) {
         const bool is_row = idx < (1u << ml);
-        const u32 weight = is_row ? idx : idx - (1u << ml);
         XYZZ* out = rc + (size_t)set * ((1u << ml) + 2 * (1u << mh));
-        if (!is_row && threadIdx.x == 0) acc.store(out + (1u << ml) + (1u << mh) + weight);
-        XYZZ w = quad_small_mul<true>(acc, weight, is_row ? ml : mh);
-        if (threadIdx.x == 0) w.store(out + idx);
+        acc.store(is_row ? out + idx : out + (1u << mh) + idx);  // rows in place; plain column sums in the third section
     }
+}
+// rc[set] = [ R_lo | . | C_hi ]  ->  [ lo * R_lo | hi * C_hi | C_hi ]: one lane-quad per point, 4-lane double-and-add
+__global__ void __launch_bounds__(128) k_rowcol_weights(XYZZ* __restrict__ rc, int ml, int mh, u32 nsets) {
+    const u32 per_set = (1u << ml) + (1u << mh);
+    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;  // quads never straddle the bound: blockDim.x % 4 == 0
+    if (q >= nsets * per_set) return;
+    const u32 set = q / per_set, idx = q % per_set;
+    const bool is_row = idx < (1u << ml);
+    XYZZ* base = rc + (size_t)set * ((1u << ml) + 2 * (1u << mh));
+    const u32 weight = is_row ? idx : idx - (1u << ml);
+    const XYZZ p = XYZZ::load(is_row ? base + idx : base + (1u << mh) + idx);
+    const XYZZ w = quad_small_mul<true>(p, weight, is_row ? ml : mh);
+    if ((threadIdx.x & 3) == 0) w.store(base + idx);
 }
 
 __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
@@ -705,6 +716,29 @@ void msm_run_group(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, i
                        off + nb_total, ba_cursor, R, BA_K);
         H2B_LAUNCH(ctx, k_accumulate<true>, ceil_div(n_chunks, 128), 128, 0, (const u32*)nullptr, off, nb_total, d_L, (const Affine*)red[R - 1], (const Affine*)nullptr, buckets, partials, R);
     }
+    // From here on the work is a few hundred CTAs of dependent point additions.  Inside a lane (other MSMs of the batch are
+    // in flight on the other lanes) it moves to the lane's high-priority stream: the block scheduler hands freed SM slots to
+    // it before the queued accumulation waves of the next MSM, so the latency-bound tail overlaps that accumulation instead
+    // of waiting for it to drain.  The lane stream waits for the tail (same order for the caller, workspaces stay safe).
+    static const int tail_env = [] {
+        const char* e = getenv("H2B_TAIL_PRIORITY");
+        return e ? atoi(e) : 1;
+    }();
+    const bool tail_hp = ctx->in_lane && (ctx->opt_tail_priority >= 0 ? ctx->opt_tail_priority != 0 : tail_env != 0);
+    struct TailScope {  // restores the lane stream and makes it wait for the tail on every exit path
+        h2b_ctx* c; cudaStream_t lane; bool on;
+        ~TailScope() {
+            if (!on) return;
+            cudaEventRecord(c->lane_tail_done[c->cur_lane], c->stream);
+            c->stream = lane;
+            cudaStreamWaitEvent(lane, c->lane_tail_done[c->cur_lane], 0);
+        }
+    } tail_scope{ctx, st, tail_hp};
+    if (tail_hp) {
+        H2B_CUDA(cudaEventRecord(ctx->lane_acc[ctx->cur_lane], st));
+        ctx->stream = ctx->lane_tail[ctx->cur_lane];
+        H2B_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->lane_acc[ctx->cur_lane], 0));
+    }
     H2B_LAUNCH(ctx, k_collect, ceil_div(nb_total, 128), 128, 0, off, nb_total, d_L, partials, buckets, big + 1, big, R);
     XYZZ* seg = (XYZZ*)ctx->get(WS_POOL, (2 * (n_chunks / BIG_SEG) + 64) * sizeof(XYZZ));
     H2B_LAUNCH(ctx, k_collect_big1, 2 * ctx->sm_count, 256, 0, off, d_L, partials, big + 1, big, seg, R);
@@ -721,8 +755,9 @@ void msm_run_group(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, i
     char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)all_sets * cta_per_set * sizeof(XYZZ) + 256);
     XYZZ* parts = (XYZZ*)rb;
     u32* done = (u32*)(rb + (size_t)all_sets * cta_per_set * sizeof(XYZZ));  // one counter per MSM of the group
-    H2B_CUDA(cudaMemsetAsync(done, 0, 4 * MSM_MAX_GROUP, st));
+    H2B_CUDA(cudaMemsetAsync(done, 0, 4 * MSM_MAX_GROUP, ctx->stream));
     H2B_LAUNCH(ctx, k_rowcol_sums, all_sets * per_set, 128, 0, buckets, ml, mh, all_sets, rc);
+    H2B_LAUNCH(ctx, k_rowcol_weights, ceil_div((size_t)all_sets * per_set * 4, 128), 128, 0, rc, ml, mh, all_sets);
     H2B_LAUNCH(ctx, k_weighted_final, all_sets * cta_per_set, 256, 0, rc, ml, mh, nsets, c * q, parts, done, d_out);
 }
 
@@ -760,10 +795,12 @@ struct LaneScope {
     LaneScope(h2b_ctx* c, int lane) : ctx(c), saved_stream(c->stream), saved_lane(c->cur_lane) {
         c->stream = c->lane_stream[lane];
         c->cur_lane = lane;
+        c->in_lane = true;
     }
     ~LaneScope() {
         ctx->stream = saved_stream;
         ctx->cur_lane = saved_lane;
+        ctx->in_lane = false;
     }
 };
 

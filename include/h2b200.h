@@ -76,6 +76,8 @@ int h2b_ctx_side_join(h2b_ctx* ctx);
  *   "msm.affine_k"       multiple of 4 in [8, 128] (-1 = default 32): pairs per thread and tile of those levels
  *   "msm.affine_per_thread_inverse"  1: every thread inverts its own denominator product (constant-time safegcd), 0: one
  *                        inversion per tile (product tree + single lane); -1 = default
+ *   "msm.tail_priority"  1 (default): the bucket reduction of an MSM that runs on one of the batch lanes is enqueued on a
+ *                        high-priority stream, so it overlaps the next MSM's accumulation; 0: everything on the lane stream
  *   "msm.batch_group"    1..16 (0 = default, chosen from the domain size): how many MSMs of one batch call share a single
  *                        sort / accumulate / bucket-reduction pipeline (1 = every MSM runs its own, on one of three lanes)
  * and one switch that selects between two equally valid outputs (see h2b_permute_expression_pair):
@@ -93,6 +95,9 @@ const char* h2b_version(void);
 int h2b_profile_enable(h2b_ctx* ctx, const char* filter);
 int h2b_profile_reset(h2b_ctx* ctx);
 int h2b_profile_read(h2b_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches);
+/* Appends one CSV line per recorded launch to `path`: kernel, stream, start_us, end_us after the caller's CUDA event
+ * `origin` (cudaEvent_t with timing).  Synchronises the device.  A timeline tool, not a product call. */
+int h2b_profile_dump(h2b_ctx* ctx, void* origin_cuda_event, const char* path);
 
 /* ---- SRS: replaces the base arrays of ParamsKZG<Bn256> (halo2-base/src/utils/mod.rs:401-443) ------- */
 /* Uploads this device's shard [begin, begin+count) of the 2^k monomial bases `g` and Lagrange bases

@@ -38,7 +38,7 @@ def run(label, fn, reps=5):
     tot = a.elapsed_time(b) / reps
     print(f"== {label}: {tot*1e3:.1f} us per op (with event overhead)")
     acc = 0
-    for kn in ["k_digits<0>", "k_scan", "k_digits<1>", "k_accumulate", "k_collect_big", "k_collect", "k_rowcol_sums", "k_weighted_final", "k_ntt_pass"]:
+    for kn in ["k_digits<0>", "k_scan", "k_digits<1>", "k_accumulate", "k_collect_big", "k_collect", "k_rowcol_sums", "k_rowcol_weights", "k_weighted_final", "k_ntt_pass"]:
         ms, cnt = ctx.profile_read(kn)
         if kn == "k_collect":
             ms2, cnt2 = ctx.profile_read("k_collect_big"); ms -= ms2; cnt -= cnt2
