@@ -441,7 +441,8 @@ class Rig:
         self.ctx = h.Context(self.local_rank)
         # a dedicated non-default stream: the library treats a NULL stream as "use the context's own stream", and the
         # CUDA events below must be recorded on the stream the kernels are launched on
-        self.stream = torch.cuda.Stream(device=self.dev)
+        # (higher priority than the transform stream below: the transforms fill the bubbles the MSM pipeline leaves)
+        self.stream = torch.cuda.Stream(device=self.dev, priority=-1 if os.environ.get("H2B_BENCH_PRIORITY", "1") != "0" else 0)
         torch.cuda.set_stream(self.stream)
         assert self.stream.cuda_stream != 0
         self.ctx.set_stream(self.stream.cuda_stream)

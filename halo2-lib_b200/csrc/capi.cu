@@ -120,7 +120,11 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
             const int g = e ? atoi(e) : 0;  // measured: no effect on the MSM at k = 19 (profiles/), so the driver default stays
             if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
         }
-        H2B_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        {   // the context's own stream sits at the lanes' priority: above the side queue (see the lane streams below)
+            int lo_prio = 0, hi_prio = 0;
+            H2B_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            H2B_CUDA(cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, (lo_prio + hi_prio) / 2));
+        }
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
         H2B_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
@@ -129,11 +133,14 @@ int h2b_ctx_create(int device, h2b_ctx** out) {
             for (auto& e : row) H2B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& ev : ctx->ev) H2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (int l = 0; l < h2b_ctx::NLANES; l++) {
-            H2B_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
-            {   // the bucket reduction of a lane's MSM runs on a HIGH-priority stream: its few CTAs take the SM slots that free
-                // up first instead of queueing behind the next MSM's accumulation waves (see msm_run_group)
+            {   // Three priority levels.  Highest: the bucket reduction of a lane's MSM — its few CTAs take the SM slots that
+                // free up first instead of queueing behind the next MSM's accumulation waves (see msm_run_group).  Middle: the
+                // lanes themselves.  Lowest (the default of a plain stream): the side queue and whatever else the caller runs
+                // beside the commitments — the polynomial transforms fill the bubbles the MSM pipeline leaves.
                 int lo_prio = 0, hi_prio = 0;
                 H2B_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+                static const int flat = [] { const char* e = getenv("H2B_LANE_PRIORITY"); return e ? atoi(e) == 0 : 0; }();
+                H2B_CUDA(cudaStreamCreateWithPriority(&ctx->lane_stream[l], cudaStreamNonBlocking, flat ? lo_prio : (lo_prio + hi_prio) / 2));
                 H2B_CUDA(cudaStreamCreateWithPriority(&ctx->lane_tail[l], cudaStreamNonBlocking, hi_prio));
             }
             H2B_CUDA(cudaEventCreateWithFlags(&ctx->lane_acc[l], cudaEventDisableTiming));
