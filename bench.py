@@ -109,7 +109,10 @@ class Schedule:
             "ntt": f"{self.n_poly} x iNTT(2^{self.k}) + {self.n_poly} x coeff_to_extended(2^{self.ext_k}) + 1 x extended_to_coeff(2^{self.ext_k})",
             "assignment": f"{self.A} gate column(s) with break points + {self.L} lookup column(s) x 2^{self.k} rows (the commitments of phase 0 read the assigned columns)",
             "scalars": f"{sum(1 for _, c2, _ in self.msm if c2 == 'witness')} witness-like + {sum(1 for _, c2, _ in self.msm if c2 == 'uniform')} uniform columns (SURVEY.md §8d)",
-            "overlap": "MSMs of a transcript phase run on 3 lanes; the iNTT + coset NTT of a polynomial run on a side stream from the moment the polynomial exists and are joined before extended_to_coeff / the h(X) commitments",
+            "overlap": ("the MSMs of a transcript phase share grouped sort / accumulate / bucket-reduction pipelines on up to 3 lanes (bucket reductions on high-priority streams); "
+                        + ("the iNTT + coset NTT of a polynomial run on a side stream from the moment the polynomial exists and are joined before extended_to_coeff / the h(X) commitments"
+                           if (self.n // max(gpus, 1)) >= (1 << 18) else
+                           "MSM shards below 2^18 points are latency-bound chains, so the transforms run in one block before extended_to_coeff / the h(X) commitments instead of beside the phases")),
             "parallelism": (f"msm point-range sharded x{gpus} + fused NVLink peer all-reduce of the partial sums (one kernel per phase); NTT one polynomial per device" if gpus > 1 else "single GPU"),
             "l2_policy": "inputs larger than L2: distinct scalar columns + two multi-level base tables + NTT buffers per step exceed the 126 MB L2 (k >= 16); smaller configs are sweep extras, not the headline",
         }
@@ -609,8 +612,12 @@ class Workload:
         self.expect_point = [ec_mul_g(s) for s in self.expect_scalar]
 
         # ---- polynomials of the transforms (own buffers: the in-place iNTT runs beside the commitments)
-        self.my_ntt = lambda i: h.ntt_owner(i, world) == rank  # one polynomial per device, round-robin
+        # one polynomial per device: transform i in [0, n_poly) is the iNTT of column i over 2^k, n_poly + i its coset NTT over
+        # 2^ext_k, 2 * n_poly the extended_to_coeff; whole transforms are dealt by cost (longest first) so that no device
+        # gets two of the 4x larger ones while another has none
         npoly = sched.n_poly
+        owners = h.ntt_owners_balanced([1.0] * npoly + [float(1 << (ext_k - k))] * (npoly + 1), world)
+        self.my_ntt = lambda i: owners[i] == rank
         mine = [i for i in range(npoly) if self.my_ntt(i) or self.my_ntt(npoly + i)]
         self.polys_dev = {i: dev_u64(uniform_residues(rng, n)) for i in mine}
         self.ext_dev = {i: torch.empty((1 << ext_k, 4), dtype=torch.int64, device=dev) for i in mine}
@@ -645,8 +652,14 @@ class Workload:
         if s.L:
             ctx.check(lib.h2b_assign_lookups_dev(ctx.h, vp(self.lk_dev.data_ptr()), self.n_lookup, s.k, s.L, vp(self.lcols_dev.data_ptr())))
 
-    def step_resident(self, overlap=True):
+    def step_resident(self, overlap=None):
+        """overlap=None: the schedule's own rule — the transforms of a column run beside the next commitment phase when the
+        MSM shards are large enough to be throughput-bound (>= 2^18 points per GPU); with small shards the commitment phases
+        are chains of latency-bound kernels and a transform beside them only delays every link, so the transforms run in
+        one block before the h(X) phase instead."""
         rig, s, lib, vp = self.rig, self.s, self.lib, self.C.c_void_p
+        if overlap is None:
+            overlap = self.n_loc >= (1 << 18)
         ctx, stream, stream_ntt = rig.ctx, rig.stream, rig.stream_ntt
         # every rank assigns the full columns (it commits its own row range of each of them)
         self.assign_dev()
@@ -840,7 +853,12 @@ def run_config(rig: Rig, sched: Schedule, steps: int, warmup: int, headline: boo
     torch.cuda.synchronize()
     res["verified_resident"] = wl.verify_commitments(wl.outs_dev.cpu().numpy().view(np.uint64))
     if headline:
-        res["ms_per_step_seq"], _ = rig.timed(lambda: wl.step_resident(False), max(1, min(steps, 5)), 1)
+        # the other placement of the transforms, for the record (the rule in step_resident picks by shard size)
+        dflt_overlap = wl.n_loc >= (1 << 18)
+        ms_alt, _ = rig.timed(lambda: wl.step_resident(not dflt_overlap), max(1, min(steps, 5)), 1)
+        res["ms_per_step_seq"] = ms_alt if dflt_overlap else ms_step
+        res["ms_per_step_ovl"] = ms_step if dflt_overlap else ms_alt
+        res["transform_placement"] = "beside the commitment phases (side stream)" if dflt_overlap else "one block before the h(X) phase"
     return res, wl
 
 
@@ -999,6 +1017,8 @@ def run_b200(args):
         "config": res["config"],
         "create_proof_schedule_ms": ms_step,
         "create_proof_schedule_ms_no_ntt_overlap": ms_step_seq,
+        "create_proof_schedule_ms_ntt_overlap": res["ms_per_step_ovl"],
+        "transform_placement": res["transform_placement"],
         "ntt_fr_elements_per_s": (1 << ext_k) / (op_ms["coset_ntt"] / 1e3),
         "msm_only_pairs_per_s": n / (op_ms["msm_uniform"] / 1e3),
         "msm_window_bits": window_bits, "msm_windows": windows,

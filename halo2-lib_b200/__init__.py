@@ -2,7 +2,7 @@
 B200 back end implements behind the C ABI of include/h2b200.h.  The C++ mirror for a compiled host is
 include/h2b200.hpp; the Rust binding a maintainer adds is shown in INTEGRATION.md."""
 from ._capi import lib, LIB_PATH, SIGNATURES, header_symbols  # noqa: F401
-from .parallel import shard_range, ntt_owner, all_gather_points, connect_peers, allreduce_points  # noqa: F401
+from .parallel import shard_range, ntt_owner, ntt_owners_balanced, all_gather_points, connect_peers, allreduce_points  # noqa: F401
 from .host import (  # noqa: F401
     H2BError,
     LayoutError,

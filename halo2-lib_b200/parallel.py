@@ -21,6 +21,19 @@ def ntt_owner(poly_index: int, world: int) -> int:
     return poly_index % world
 
 
+def ntt_owners_balanced(costs, world: int):
+    """owner of every transform of a proof when their costs differ (an iNTT over 2^k against a coset NTT over 2^(k+2)):
+    longest-processing-time-first — transforms in decreasing cost, each to the least loaded device; deterministic, the
+    same on every rank.  NTT does not shard (one polynomial per device): this only deals whole transforms."""
+    load = [0.0] * world
+    owner = [0] * len(costs)
+    for i in sorted(range(len(costs)), key=lambda j: (-costs[j], j)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
+
+
 def all_gather_points(partials, group=None):
     """partials: int64 tensor [m, 12] (this rank's m partial commitments) -> [m, world, 12] (contiguous per point),
     ready for h2b_g1_sum(_dev) over axis 1.  Works with nccl (device tensors) and gloo (CPU tensors)."""

@@ -18,6 +18,13 @@
  *  - Host-pointer entry points own no caller memory: buffers are read/written during the call only.
  *    `_dev` entry points take device pointers (same layouts) and enqueue on the context's stream without
  *    synchronising; the caller owns those allocations (e.g. torch tensors) and the synchronisation.
+ *    Exceptions, all on the host side only (results are stream-ordered either way): a call that needs a larger scratch
+ *    workspace than any call before it on this context waits for the device once (the workspaces are grow-only);
+ *    h2b_quotient_graph_dev / h2b_permutation_fold_dev / h2b_lookup_fold_dev / h2b_poly_lincomb_dev copy a table of a few
+ *    hundred bytes from pageable host memory, which the CUDA runtime stages before returning (not capturable into a CUDA
+ *    graph); h2b_assign_columns_dev with more than 64 columns waits for its pinned span block; the first transform of a
+ *    new domain size builds its twiddle plan and waits for it; h2b_permute_expression_pair_dev and the calls that return
+ *    a value to the host (h2b_eval_polynomial*_dev, h2b_poly_download, h2b_profile_*) synchronise the stream.
  *  - A context is bound to ONE device (one process per GPU); calls on one context are serialised by an
  *    internal mutex, so the library is re-entrant from rayon worker threads
  *    (halo2-base/src/gates/flex_gate/threads/parallelize.rs:8-29 runs user code on many threads).

@@ -70,3 +70,17 @@ def test_shard_range():
     import pytest
     with pytest.raises(ValueError):
         h.shard_range(10, 0, 3)
+
+
+def test_transforms_are_dealt_by_cost():
+    """ntt_owners_balanced: whole transforms, longest first to the least loaded device; deterministic on every rank"""
+    import halo2_lib_b200 as h
+    costs = [1.0] * 5 + [4.0] * 6  # the ECDSA schedule: 5 iNTT(2^19), 5 coset NTT(2^21) + extended_to_coeff(2^21)
+    for world in (1, 2, 4, 8):
+        own = h.ntt_owners_balanced(costs, world)
+        assert own == h.ntt_owners_balanced(costs, world) and len(own) == len(costs) and set(own) <= set(range(world))
+        load = [sum(c for c, o in zip(costs, own) if o == r) for r in range(world)]
+        assert max(load) <= sum(costs) / world + max(costs)  # LPT bound
+        if world == 8:
+            assert max(load) == 5.0 or max(load) == 4.0  # never two large transforms on one device
+            assert sum(1 for r in range(8) if any(c == 4.0 and o == r for c, o in zip(costs, own))) == 6
