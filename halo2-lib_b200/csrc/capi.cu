@@ -291,6 +291,7 @@ int h2b_ctx_set_option(h2b_ctx* ctx, const char* key, int64_t value) {
         else if (k == "msm.affine_k") { H2B_REQUIRE(value == -1 || (value >= 8 && value <= 128 && value % 4 == 0), "msm.affine_k: multiple of 4 in [8, 128]"); ctx->opt_affine_k = (int)value; }
         else if (k == "msm.affine_per_thread_inverse") { H2B_REQUIRE(value >= -1 && value <= 1, "msm.affine_per_thread_inverse: -1, 0 or 1"); ctx->opt_affine_pt = (int)value; }
         else if (k == "msm.tail_priority") { H2B_REQUIRE(value >= -1 && value <= 1, "msm.tail_priority: -1 (default), 0 or 1"); ctx->opt_tail_priority = (int)value; }
+        else if (k == "ntt.max_ctas_per_sm") { H2B_REQUIRE(value >= 0 && value <= 2, "ntt.max_ctas_per_sm: 0 (no limit), 1 or 2"); ctx->opt_ntt_ctas = (int)value; }
         else if (k == "msm.batch_group") { H2B_REQUIRE(value >= 0 && value <= 16, "msm.batch_group: 0 (default) .. 16 MSMs per pipeline"); ctx->opt_msm_group = (int)value; }
         else if (k == "lookup.leftover_order") { H2B_REQUIRE(value == 0 || value == 1, "lookup.leftover_order: 0 (front to back) or 1 (zcash: from the back)"); ctx->opt_lookup_backward = (int)value; }
         else H2B_REQUIRE(false, "set_option: unknown key");

@@ -92,6 +92,7 @@ struct h2b_ctx {
     int opt_affine_k = -1;       // "msm.affine_k"
     int opt_affine_pt = -1;      // "msm.affine_per_thread_inverse": 1 = every thread inverts (safegcd), 0 = one inversion per tile
     int opt_tail_priority = -1;  // "msm.tail_priority": bucket reductions of lane MSMs on high-priority streams (-1 = default on)
+    int opt_ntt_ctas = 0;        // "ntt.max_ctas_per_sm": 0 = as many as fit, 1 or 2 = background transform (see ntt_run)
     int opt_msm_group = 0;       // "msm.batch_group": MSMs of a batch call that share one sort / accumulate / reduce pipeline (0 = by size)
     int opt_lookup_backward = 0; // "lookup.leftover_order": 0 = front to back (PSE / axiom walk), 1 = zcash (pop from the back)
     void* peer = nullptr;  // PeerState (peer.cu): NVLink mailboxes of the multi-GPU all-reduce

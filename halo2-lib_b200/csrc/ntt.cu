@@ -21,6 +21,7 @@ namespace h2b {
 
 static constexpr int NTT_THREADS = 256;   // upper bound; small tiles run with TILE / 4 threads (one radix-4 group each)
 static constexpr int NTT_TILE_LOG = 11;  // largest tile: 2^11 elements * 32 B = 64 KB of shared memory
+static constexpr int NTT_SMEM_MAX = 227 * 1024;  // opt-in limit of dynamic shared memory per CTA on sm_100
 static constexpr int NTT_MAX_R = 11;  // one column of the largest digit = 2^11 * 32 B = the whole 64 KB tile
 
 // Fr::ZETA and ZETA^2 in Montgomery form (halo2curves bn256::Fr::ZETA); the same values are
@@ -341,8 +342,10 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
     H2B_REQUIRE(n_src <= n, "ntt: more input elements than the domain size");
     NttPlan* p = get_plan(ctx, log_n, omega, inverse_scale);
     if (!ctx->ntt_attr_set) {  // per context: the attribute belongs to the device the context is bound to
-        H2B_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Fr) << NTT_TILE_LOG)));
-        H2B_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Fr) << NTT_TILE_LOG)));
+        // up to the whole 227 KB: a transform that runs in the background asks for more shared memory than it uses so that
+        // only 1 or 2 of its CTAs fit on an SM (option "ntt.max_ctas_per_sm")
+        H2B_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_MAX));
+        H2B_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_MAX));
         ctx->ntt_attr_set = true;
     }
     Fr* scratch = nullptr;
@@ -381,7 +384,10 @@ void ntt_run(h2b_ctx* ctx, const void* d_src, size_t n_src, void* d_dst, uint32_
         a.tw_full = last ? nullptr : p->tw_full[t];
         a.coset = coset_mode;
         const unsigned grid = 1u << (cols_log - a.cw_log);
-        const size_t smem = sizeof(Fr) << (a.r + a.cw_log);
+        size_t smem = sizeof(Fr) << (a.r + a.cw_log);
+        // background mode: at most opt_ntt_ctas CTAs of this transform per SM, so that the few-CTA kernels of a latency-bound
+        // MSM pipeline running beside it always find a free slot (the transform is slower, but hidden)
+        if (ctx->opt_ntt_ctas >= 1 && ctx->opt_ntt_ctas <= 2) smem = std::max(smem, (size_t)(NTT_SMEM_MAX / ctx->opt_ntt_ctas - 1024) & ~(size_t)1023);
         const unsigned threads = (unsigned)std::min(NTT_THREADS, std::max(32, (1 << (a.r + a.cw_log)) / 4));
         if (last) H2B_LAUNCH(ctx, k_ntt_pass<true>, grid, threads, smem, a);
         else H2B_LAUNCH(ctx, k_ntt_pass<false>, grid, threads, smem, a);

@@ -85,6 +85,8 @@ int h2b_ctx_side_join(h2b_ctx* ctx);
  *                        inversion per tile (product tree + single lane); -1 = default
  *   "msm.tail_priority"  1 (default): the bucket reduction of an MSM that runs on one of the batch lanes is enqueued on a
  *                        high-priority stream, so it overlaps the next MSM's accumulation; 0: everything on the lane stream
+ *   "ntt.max_ctas_per_sm" 0 (default: as many as fit), 1 or 2: the transforms of this context leave room on every SM — for a
+ *                        transform that runs in the background of a latency-bound MSM pipeline (small multi-GPU shards)
  *   "msm.batch_group"    1..16 (0 = default, chosen from the domain size): how many MSMs of one batch call share a single
  *                        sort / accumulate / bucket-reduction pipeline (1 = every MSM runs its own, on one of three lanes)
  * and one switch that selects between two equally valid outputs (see h2b_permute_expression_pair):
