@@ -991,20 +991,25 @@ def run_b200(args):
     value = sched.pairs / (ms_step / 1e3)
     peak, peak_src = measured_hbm_peak()
     # the dominant kernel: bucket accumulation = the batch-affine reduction passes + the XYZZ accumulation of what is left
+    # a launch of the grouped pipeline accumulates the columns of a whole group (1-2 at k = 19): per launch the
+    # algorithmic bytes are 96 B x pairs of ALL its columns, so the average is formed over the step's totals
+    msm_per_launch = len(sched.msm) * args.steps / max(acc_cnt, 1)
     acc_avg_ms = (acc_ms + res["bred"][0]) / max(acc_cnt, 1)
     iso_avg_ms = (iso_ms + iso_aff_ms) / max(iso_cnt, 1)
-    achieved = 96.0 * n_loc / (acc_avg_ms / 1e3) / 1e9  # algorithmic 96 B per pair (32 B scalar + 64 B base), SURVEY.md §8d
+    achieved = 96.0 * n_loc * msm_per_launch / (acc_avg_ms / 1e3) / 1e9  # algorithmic 96 B per pair (32 B scalar + 64 B base), SURVEY.md §8d
     achieved_iso = 96.0 * n_loc / (iso_avg_ms / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"k{k}_n{world}")
+            traffic = json.load(open(tpath)).get(f"k{k}_n{world}")  # per MSM column
+            traffic = traffic * msm_per_launch if traffic else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "bucket accumulation (k_batch_affine passes + k_accumulate)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt, "algorithmic_bytes_per_launch": 96 * n_loc,
+                "avg_launch_ms": acc_avg_ms, "launches_timed": acc_cnt, "msm_columns_per_launch": msm_per_launch,
+                "algorithmic_bytes_per_launch": 96 * n_loc * msm_per_launch,
                 "timed_region_note": "launches of the timed region overlap with the kernels of the other two MSM lanes, which stretches each launch",
                 "isolated": {"avg_launch_ms": iso_avg_ms, "launches": iso_cnt, "achieved": achieved_iso, "frac": achieved_iso / peak,
                              "k_accumulate_ms": iso_ms / max(iso_cnt, 1), "k_batch_affine_ms": iso_aff_ms / max(iso_cnt, 1)},
