@@ -768,24 +768,34 @@ class Workload:
 
     # -------------------------------------------------------------------------------------------- resident prover (e2e)
     def setup_prover(self):
-        """the resident prover path (halo2-lib_b200/prover.py): a SATISFIED synthetic halo2-base circuit of this shape; host
-        side = pinned witness cells + pinned random polynomial, everything else lives behind h2b_poly handles"""
+        """the resident prover path (halo2-lib_b200/prover.py): a SATISFIED synthetic halo2-base circuit of this config's
+        shape (A gate-advice / L lookup-advice columns, selector lookup or none); host side = pinned witness cells (virtual
+        column + looked-up cells) + pinned random polynomial, everything else lives behind h2b_poly handles"""
         rig, s = self.rig, self.s
         torch, h = rig.torch, rig.h
-        assert s.A == 1 and s.L == 0 and s.n_lk == 1, "the resident prover session covers the 1 advice / q_lookup / 1 fixed shape"
         rng = np.random.default_rng(0xB2002000 + s.k)
-        a, fixed, sigma, usable = h.synthetic_circuit(rig.ctx, s.k, rng)
-        self.pr_circuit = h.Circuit(rig.ctx, s.k, fixed, sigma)
+        sel = s.n_lk > 0 and s.L == 0
+        inst = h.synthetic_circuit(rig.ctx, s.k, rng, A=s.A, L=s.L, selector_lookup=sel)
+        self.pr_circuit = h.Circuit(rig.ctx, s.k, inst["fixed"], inst["sigma"], A=s.A, L=s.L, selector_lookup=sel)
+        assert self.pr_circuit.degree == s.d and self.pr_circuit.n_sets == s.n_pm and self.pr_circuit.n_lookups == s.n_lk
         self.pr_session = h.ProverSession(rig.ctx, self.params, self.pr_circuit)
         if rig.world > 1:
             self.pr_session.shard(self.begin, self.n_loc, lambda ptr, m: h.allreduce_points(rig.ctx, ptr, m))
-        self.pr_witness = torch.from_numpy(np.ascontiguousarray(a[:usable]).view(np.int64)).pin_memory()
-        self.pr_random = torch.from_numpy(uniform_residues(rng, s.n).view(np.int64)).pin_memory()
-        self.pr_usable = usable
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).pin_memory()
+        self.pr_witness = pin(inst["virtual"])
+        self.pr_lookup = pin(inst["lookup"]) if len(inst["lookup"]) else None
+        self.pr_random = pin(uniform_residues(rng, s.n))
+        self.pr_bp = inst["break_points"]
+        self.pr_sel = sel
         self.pr_last = None
 
+    def _prove(self):
+        lk = self.pr_lookup
+        return self.pr_session.prove(self.pr_witness.data_ptr(), len(self.pr_witness), self.pr_random.data_ptr(), seed=1, break_points=self.pr_bp,
+                                     lookup_ptr=lk.data_ptr() if lk is not None else 0, n_lookup=len(lk) if lk is not None else 0)
+
     def step_e2e_prover(self):
-        self.pr_last = self.pr_session.prove(self.pr_witness.data_ptr(), self.pr_usable, self.pr_random.data_ptr(), seed=1)
+        self.pr_last = self._prove()
 
     def verify_prover(self) -> dict:
         """one untimed proof with the committed polynomials kept: every commitment against the closed form of its
@@ -793,16 +803,22 @@ class Workload:
         import prover_check as pc
         s, sess = self.s, self.pr_session
         sess.keep = {}
-        res = sess.prove(self.pr_witness.data_ptr(), self.pr_usable, self.pr_random.data_ptr(), seed=1)
+        res = self._prove()
         kept, sess.keep = sess.keep["committed"], None
         ok = 0
         for cm, (basis, poly) in zip(res["commitments"], kept):
             a0, d = BASES["monomial" if basis == 0 else "lagrange"]
             scalar = progression_dot(poly, a0, d, 0) * MONT_RINV_R % R_MOD
             ok += 1 if point_matches(cm, ec_mul_g(scalar)) else 0
-        left, right = pc.quotient_identity(res, s.k, self.pr_circuit.bf)
-        return {"commitments": ok, "of": len(kept), "quotient_identity": left == right,
+        left, right = pc.quotient_identity(res, s.k, self.pr_circuit.bf, s.A, s.L, self.pr_sel)
+        return {"commitments": ok, "of": len(kept), "expected": len(s.msm), "quotient_identity": left == right,
                 "h2d_bytes": res["h2d_bytes"], "d2h_bytes": res["d2h_bytes"]}
+
+    def close_prover(self):
+        if getattr(self, "pr_session", None) is not None:
+            self.pr_session.free()
+            self.pr_circuit.free()
+            self.pr_session = None
 
     # -------------------------------------------------------------------------------------------- verification
     def verify_commitments(self, arr) -> int:
@@ -952,6 +968,17 @@ def run_b200(args):
             t_ntt = rig.time_op(lambda: ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(w2.polys_dev[p2].data_ptr()), s2.n, s2.ext_k, vp(w2.ext_dev[p2].data_ptr()))))
             t_asg = rig.time_op(w2.assign_dev)
             ok = r2["verified_resident"] == len(s2.msm) and all(v for kk, v in ntt2.items() if kk != "points_checked")
+            # the resident proof of this shape (multi-column / lookup-advice / lookup-less circuits included), verified
+            e2e2 = None
+            if s2.k <= 20:
+                w2.setup_prover()
+                ms_p, _ = rig.timed(w2.step_e2e_prover, st, 1)
+                torch.cuda.synchronize()
+                chk = w2.verify_prover()
+                e2e2 = {"ms_per_proof": ms_p, "pairs_per_s": s2.pairs / (ms_p / 1e3), "commitments_verified": chk["commitments"], "of": chk["of"],
+                        "quotient_identity": chk["quotient_identity"], "h2d_bytes": chk["h2d_bytes"], "d2h_bytes": chk["d2h_bytes"]}
+                ok = ok and chk["commitments"] == chk["of"] == len(s2.msm) and chk["quotient_identity"]
+                w2.close_prover()
             sweep[f"config{cid}"] = {
                 "workload": r2["config"]["workload"], "k": s2.k, "columns": r2["config"]["columns"], "msm": r2["config"]["msm"], "ntt": r2["config"]["ntt"],
                 "create_proof_schedule_ms": r2["ms_per_step"], "msm_pairs_per_s": s2.pairs / (r2["ms_per_step"] / 1e3),
@@ -961,7 +988,7 @@ def run_b200(args):
                 "roofline": {"msm_hbm_frac": 96.0 * w2.n_loc / (t_msm / 1e3) / 1e9 / measured_hbm_peak()[0],
                              "ntt_hbm_frac": 64.0 * (1 << s2.ext_k) / (t_ntt / 1e3) / 1e9 / measured_hbm_peak()[0],
                              "assign_hbm_frac": 64.0 * (w2.n_cells + w2.n_lookup) / (t_asg / 1e3) / 1e9 / measured_hbm_peak()[0]},
-                "steps": st, "gpu_launches": r2["gpu_launches"],
+                "steps": st, "gpu_launches": r2["gpu_launches"], "e2e_resident_proof": e2e2,
                 "verified": {"msm": r2["verified_resident"], "of": len(s2.msm), "ntt": ntt2, "ok": rig.all_true(ok)},
             }
             w2.close()

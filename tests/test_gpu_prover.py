@@ -28,49 +28,80 @@ def ctx(h2b):
     c.close()
 
 
-def _setup(ctx, h2b, k, seed):
+def _setup(ctx, h2b, k, seed, A=1, L=0, sel=True):
     rng = np.random.default_rng(seed)
     n = 1 << k
     g = affine_to_limbs([pyref.G1])[0]
     bases_m = ctx.g1_fixed_base_mul(g, mont([3 + 5 * i for i in range(n)], R))
     bases_l = ctx.g1_fixed_base_mul(g, mont([7 + 11 * i for i in range(n)], R))
     params = h2b.ParamsKZG(ctx, k, g=bases_m, g_lagrange=bases_l)
-    a, fixed, sigma, usable = h2b.synthetic_circuit(ctx, k, rng)
-    cs = h2b.Circuit(ctx, k, fixed, sigma)
+    inst = h2b.synthetic_circuit(ctx, k, rng, A=A, L=L, selector_lookup=sel)
+    cs = h2b.Circuit(ctx, k, inst["fixed"], inst["sigma"], A=A, L=L, selector_lookup=sel)
     sess = h2b.ProverSession(ctx, params, cs)
-    return rng, params, cs, sess, a, usable, (bases_m, bases_l)
+    return rng, params, cs, sess, inst, (bases_m, bases_l)
 
 
-@pytest.mark.parametrize("k", [8, 11])
-def test_resident_proof_commitments_and_quotient_identity(ctx, h2b, k):
-    rng, params, cs, sess, a, usable, bases = _setup(ctx, h2b, k, 3100 + k)
+def _prove(sess, inst, rnd, seed=5, virtual=None):
+    v = np.ascontiguousarray(inst["virtual"] if virtual is None else virtual)
+    lk = np.ascontiguousarray(inst["lookup"])
+    return sess.prove(v.ctypes.data, len(v), rnd.ctypes.data, seed=seed, break_points=inst["break_points"],
+                      lookup_ptr=lk.ctypes.data if len(lk) else 0, n_lookup=len(lk))
+
+
+@pytest.mark.parametrize("k,A,L,sel", [(8, 1, 0, True), (11, 1, 0, True), (8, 1, 0, False), (9, 2, 1, True), (10, 3, 2, True), (9, 8, 2, True)])
+def test_resident_proof_commitments_and_quotient_identity(ctx, h2b, k, A, L, sel):
+    """shapes: the ECDSA / pairing configs (1 gate column, selector lookup), the inner_product bench (no lookup at all,
+    degree 3, extended domain 2^(k+1)) and the multi-column configs of BASELINE.json (8 / 2 and 11 / 2 in the reference's
+    config files; 8 / 2 here at a small k)"""
+    rng, params, cs, sess, inst, bases = _setup(ctx, h2b, k, 3100 + k + 10 * A, A, L, sel)
+    nlk = cs.n_lookups
     n = 1 << k
-    witness = np.ascontiguousarray(a[:usable])
     rnd = mont(rand_ints(rng, n, R), R)
     sess.keep = {}
-    res = sess.prove(witness.ctypes.data, usable, rnd.ctypes.data, seed=5)
-    assert len(res["commitments"]) == 12 and len(sess.keep["committed"]) == 12
+    res = _prove(sess, inst, rnd)
+    # advice | permuted pairs | product columns + random | h pieces | two openings
+    want_cm = (A + L) + 2 * nlk + (cs.n_sets + nlk + 1) + (cs.degree - 1) + 2
+    assert len(res["commitments"]) == want_cm and len(sess.keep["committed"]) == want_cm
+    # the assignment produced the columns of the instance (rows below the blinding rows)
+    for j, nm in enumerate(cs.adv_names):
+        assert np.array_equal(sess.keep["committed"][j][1][: cs.u], inst["cols"][j][: cs.u]), nm
     for cm, (basis, poly) in zip(res["commitments"], sess.keep["committed"]):
         want = orc.msm_pippenger(poly, bases[basis])
         got = ctx.g1_normalize(np.asarray(cm).reshape(1, 12))[0]
         assert np.array_equal(got, want)
-    left, right = pc.quotient_identity(res, k, cs.bf)
+    left, right = pc.quotient_identity(res, k, cs.bf, A, L, sel)
     assert left == right
-    # the evaluations are what Horner gives on the downloaded coefficients (advice column, a product column, an h piece)
+    # the evaluations are what Horner gives on the downloaded coefficients (an advice column, a product column, an h piece)
     x = res["challenges"]["x"]
     w = pyref.omega_for(k)
-    assert pc.fr(res["evals"][("a", 2)]) == pc.horner(sess.ac.download(), x * pow(w, 2, R) % R)
-    assert pc.fr(res["evals"][("zp", -(cs.bf + 1))]) == pc.horner(sess.zpc.download(), x * pow(w, n - (cs.bf + 1), R) % R)
+    assert pc.fr(res["evals"][("a0", 2)]) == pc.horner(sess.coef["a0"].download(), x * pow(w, 2, R) % R)
+    assert pc.fr(res["evals"][("zp0", 1)]) == pc.horner(sess.coef["zp0"].download(), x * w % R)
+    if cs.n_sets > 1:
+        assert pc.fr(res["evals"][("zp0", -(cs.bf + 1))]) == pc.horner(sess.coef["zp0"].download(), x * pow(w, n - (cs.bf + 1), R) % R)
     assert pc.fr(res["evals"][("h1", 0)]) == pc.horner(sess.h.download(n, n), x)
-    # PCIe accounting: witness + random polynomial + blinding rows up, commitments + evaluations down
-    assert res["h2d_bytes"] <= (usable + n) * 32 + 64 * 32 * 5 and res["d2h_bytes"] <= 12 * 96 + 64 * 32
+    # PCIe accounting: witness + looked-up cells + random polynomial + blinding rows up, commitments + evaluations down
+    ncols = (A + L) + 2 * nlk + cs.n_sets + nlk
+    assert res["h2d_bytes"] <= (len(inst["virtual"]) + len(inst["lookup"]) + n) * 32 + 8 * 32 * ncols
+    assert res["d2h_bytes"] <= want_cm * 96 + (len(res["evals"]) + nlk) * 32
     # second proof on the same session (buffers reused) with a broken gate: the identity must fail
-    bad = witness.copy()
+    bad = np.ascontiguousarray(inst["virtual"]).copy()
     bad[3] = mont([12345], R)[0]
     sess.keep = None
-    res2 = sess.prove(bad.ctypes.data, usable, rnd.ctypes.data, seed=5)
-    l2, r2 = pc.quotient_identity(res2, k, cs.bf)
+    res2 = _prove(sess, inst, rnd, virtual=bad)
+    l2, r2 = pc.quotient_identity(res2, k, cs.bf, A, L, sel)
     assert l2 != r2
+    # a looked-up cell that is not in the table: ConstraintSystemFailure, reported with the phase's commitments
+    bad = np.ascontiguousarray(inst["virtual"]).copy()
+    bad[1] = mont([(1 << 40) + 7], R)[0]
+    if not nlk:
+        pass
+    elif L:
+        lk_bad = dict(inst); lk_bad["lookup"] = inst["lookup"].copy(); lk_bad["lookup"][0] = bad[1]
+        with pytest.raises(h2b.H2BError):
+            _prove(sess, lk_bad, rnd)
+    else:
+        with pytest.raises(h2b.H2BError):
+            _prove(sess, inst, rnd, virtual=bad)
     sess.free(); cs.free(); params.close()
 
 
