@@ -996,6 +996,8 @@ def run_b200(args):
             torch.cuda.empty_cache()
         except Exception as e:  # a sweep extra must not take the headline down; it is reported as failed
             sweep[f"config{cid}"] = {"error": f"{type(e).__name__}: {e}"}
+            import traceback
+            print(f"sweep config {cid} failed:\n" + traceback.format_exc(), file=sys.stderr)
             if not rig.all_true(False):
                 pass
 

@@ -32,6 +32,7 @@ MONT_RINV = pow(1 << 256, -1, R_MOD)
 ROOT_OF_UNITY = pow(7, (R_MOD - 1) >> 28, R_MOD)
 DELTA = pow(7, 1 << 28, R_MOD)
 BLINDING_FACTORS = 6  # max(3, queries of the gate column = 4) + 2  
+GATES_PER_PROGRAM = 5  # vertical gates per GraphEvaluator program (10 calculations each, 64 per program)
 
 
 def to_limbs(x: int) -> np.ndarray:
@@ -137,13 +138,18 @@ class Circuit:
             ctx.check(lib.h2b_coeff_to_extended_dev(ctx.h, vp(cf.ptr), n, self.ext_k, vp(ex.ptr)))
             self.lagr[name], self.coeff[name], self.ext[name] = lg, cf, ex
         ctx.synchronize()
-        # the gate program: one vertical gate per gate-advice column (fixed slot j = q{j}, advice slot j = a{j})
-        g = ev.GraphEvaluator()
-        gates = []
-        for j in range(A):
-            a = lambda r, j=j: ("advice", j, r)
-            gates.append(("product", ("fixed", j, 0), ("sum", ("sum", a(0), ("product", a(1), a(2))), ("negated", a(3)))))
-        self.gate_graph, self.gate_res = g, g.add_gates(gates)
+        # the gate programs: one vertical gate per gate-advice column, GATES_PER_PROGRAM columns per h2b_graph (a program holds
+        # at most 64 calculations; every program continues the Horner fold in y from the previous value, so a chain of
+        # programs is the one fold evaluate_h does); inside a program fixed slot i = q{j0 + i}, advice slot i = a{j0 + i}
+        self.gate_programs = []
+        for j0 in range(0, A, GATES_PER_PROGRAM):
+            g = ev.GraphEvaluator()
+            js = list(range(j0, min(A, j0 + GATES_PER_PROGRAM)))
+            gates = []
+            for i in range(len(js)):
+                a = lambda r, i=i: ("advice", i, r)
+                gates.append(("product", ("fixed", i, 0), ("sum", ("sum", a(0), ("product", a(1), a(2))), ("negated", a(3)))))
+            self.gate_programs.append((g, g.add_gates(gates), js))
         # the lookups' programs: (compressed input + beta)(compressed table + gamma)
         g2 = ev.GraphEvaluator()
         if L == 0:   # fixed slots [q_lookup, table], advice slot [a0]
@@ -467,9 +473,9 @@ class ProverSession:
         # ---- quotient: gate, permutation and lookup terms folded with y on the extended coset
         kw = dict(beta=bl, gamma=gl, theta=to_limbs(theta), y=yl)
         ctx.check(lib.h2b_poly_zero(ctx.h, self.h.h))
-        bg = ev.BoundGraph(cs.gate_graph, cs.gate_res, fixed=[cs.ext["q%d" % j].ptr for j in range(A)],
-                           advice=[self.ext["a%d" % j].ptr for j in range(A)], **kw)
-        ctx.check(lib.h2b_quotient_graph_dev(ctx.h, C.byref(bg.struct), k, ext_k, vp(self.h.ptr)))
+        for g, g_res, js in cs.gate_programs:
+            bg = ev.BoundGraph(g, g_res, fixed=[cs.ext["q%d" % j].ptr for j in js], advice=[self.ext["a%d" % j].ptr for j in js], **kw)
+            ctx.check(lib.h2b_quotient_graph_dev(ctx.h, C.byref(bg.struct), k, ext_k, vp(self.h.ptr)))
         ext_ptr = {"c": cs.ext["c"].ptr}
         ext_ptr.update({nm: self.ext[nm].ptr for nm in cs.adv_names})
         npc = len(cs.perm_cols)
