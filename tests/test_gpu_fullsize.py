@@ -71,6 +71,41 @@ def test_msm_closed_form_full_size(env, k):
     del d_pts
 
 
+def test_grouped_commitment_phase_full_size(env):
+    """the advice phase of the k = 20 MSM-circuit config (halo2-ecc/configs/bn254/bench_msm.config:5: 11 + 2 advice
+    columns => 13 commitments in one batch call) plus monomial-basis columns in the same call: the grouped pipelines
+    (bucket sets side by side, table bit in the sorted entries) at full size, every commitment against its closed form"""
+    h, ctx, torch = env
+    import bench
+    k = 20
+    n = 1 << k
+    prog = {0: (1234567, 89), 1: (7654321, 97)}  # basis -> (a0, delta) of its progression a_i * G
+    d_m = _progression_bases_dev(h, ctx, torch, n, *prog[0])
+    d_l = _progression_bases_dev(h, ctx, torch, n, *prog[1])
+    params = h.ParamsKZG(ctx, k, g=d_m.data_ptr(), g_lagrange=d_l.data_ptr(), device_ptrs=True)
+    rng = np.random.default_rng(0xB2004000)
+    basis = [1] * 13 + [0, 1, 0]
+    cols, d_cols = [], []
+    for j in range(len(basis)):
+        canon = bench.witness_like(rng, n) if j % 3 else _uniform(rng, n)
+        if j == 5:
+            canon[:] = 0  # an all-zero column inside the group
+        S = ctx.field_op(1, 5, canon)
+        cols.append(S)
+        d_cols.append(torch.from_numpy(S.view(np.int64)).cuda())
+    d_out = torch.zeros((len(basis), 12), dtype=torch.int64, device="cuda")
+    params.commit_batch_dev(basis, [t.data_ptr() for t in d_cols], n, d_out.data_ptr())
+    torch.cuda.synchronize()
+    outs = ctx.g1_normalize(d_out.cpu().numpy().view(np.uint64))
+    for j, b in enumerate(basis):
+        a0, d = prog[b]
+        kk = bench.progression_dot(cols[j], a0, d, 0) * bench.MONT_RINV_R % R
+        want = pyref.g1_mul(kk, pyref.G1) if kk else None
+        assert jac_limbs_to_affine(outs[j]) == want, j
+    params.close()
+    del d_m, d_l, d_cols
+
+
 @pytest.mark.parametrize("k", [19, 23, 25])
 def test_ntt_properties_full_size(env, k):
     h, ctx, torch = env
