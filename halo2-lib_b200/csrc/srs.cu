@@ -8,8 +8,11 @@
 // (not vendored; restated from the definitions — the outputs are unique group elements).
 //
 // The group FFT is radix-2 decimation in time on XYZZ points in HBM: n/2 butterflies per stage, each one scalar
-// multiplication by a twiddle (double-and-add over <= 254 bits, ~4.2k Montgomery products) plus two point additions —
-// integer-multiplier bound, ~ k * n/2 * 4.4k products in total (k = 19: ~2.2e10, a third of a second), run once per SRS.
+// multiplication by a twiddle plus two point additions — integer-multiplier bound, run once per SRS.  The scalar
+// multiplication uses the curve's endomorphism (GLV): phi(x, y) = (beta x, y) = lambda (x, y), so
+// tw * P = k1 * P + k2 * phi(P) with |k1|, |k2| < 2^127 (k_glv_decompose, once per distinct twiddle), evaluated jointly
+// with 2-bit windows over a 16-entry table i*P + j*phi(P): 128 doublings + <= 64 additions + 13 table additions
+// (~2.2k Montgomery products) instead of 254 + ~127 (~4.1k) for the plain double-and-add.
 #include "h2b_internal.cuh"
 #include "curve.cuh"
 #include "fr_domain_consts.inc"
@@ -83,19 +86,141 @@ __global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict
     r.store(out + i);
 }
 
-// s * p, s canonical (non-Montgomery) limbs; MSB-first double-and-add (doubling the identity is free)
-static __device__ __noinline__ XYZZ xyzz_scalar_mul(const XYZZ& p, const Fr& s) {
+// ---------------------------------------------------------------- GLV scalar multiplication
+// lambda = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd (lambda^2 + lambda + 1 = 0 mod r) acts on G1 as
+// phi(x, y) = (beta x, y), beta = 0x59e26bcea0d48bacd4f263f1acdb5c4f5763473177fffffe (checked against the oracle's
+// scalar multiplication in tests/test_oracle_srs.py).  Lattice basis of {(a, b): a + b lambda = 0 mod r} from the
+// extended Euclid on (r, lambda):  v1 = (a1, -|b1|), v2 = (a2, b2), det = r.  For a scalar k:
+//     c1 = floor(k g1 / 2^256), c2 = floor(k g2 / 2^256),  g1 = floor(2^256 b2 / r), g2 = floor(2^256 |b1| / r),
+//     k1 = k - c1 a1 - c2 a2,   k2 = c1 |b1| - c2 b2,      k = k1 + k2 lambda (mod r),  |k1|, |k2| < 2^127.
+struct GlvScalar {
+    u32 k1[4], k2[4];  // magnitudes
+    u32 neg;           // bit 0: k1 < 0, bit 1: k2 < 0
+    u32 pad[3];
+};
+template <int NA, int NB>
+__device__ __forceinline__ void mp_mul(const u32* a, const u32* b, u32* out) {  // out[NA + NB] = a * b
+#pragma unroll
+    for (int i = 0; i < NA + NB; i++) out[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        u64 carry = 0;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const u64 t = (u64)a[i] * b[j] + out[i + j] + carry;
+            out[i + j] = (u32)t;
+            carry = t >> 32;
+        }
+        out[i + NB] = (u32)carry;
+    }
+}
+template <int N>
+__device__ __forceinline__ void mp_sub(u32* a, const u32* b) {  // a -= b (mod 2^(32 N))
+    u64 borrow = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const u64 t = (u64)a[i] - b[i] - borrow;
+        a[i] = (u32)t;
+        borrow = (t >> 32) & 1;
+    }
+}
+template <int N>
+__device__ __forceinline__ bool mp_abs(u32* a) {  // two's complement -> magnitude; returns the sign
+    const bool neg = a[N - 1] >> 31;
+    if (neg) {
+        u64 carry = 1;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const u64 t = (u64)(~a[i]) + carry;
+            a[i] = (u32)t;
+            carry = t >> 32;
+        }
+    }
+    return neg;
+}
+__device__ __forceinline__ GlvScalar glv_decompose(const Fr& k) {  // k canonical
+    const u32 A1[2] = {0x94d213e3u, 0x89d32568u};
+    const u32 B1[4] = {0x7d4f1128u, 0x8211bbebu, 0xeeb859fcu, 0x6f4d8248u};  // |b1|, b1 < 0
+    const u32 A2[4] = {0x1221250bu, 0x0be4e154u, 0xeeb859fdu, 0x6f4d8248u};
+    const u32 B2[2] = {0x94d213e3u, 0x89d32568u};
+    const u32 G1[3] = {0xc7e0b3d7u, 0xd91d232eu, 0x00000002u};
+    const u32 G2[5] = {0x391eb18du, 0x7a7bd9d4u, 0xa773d2cfu, 0x4ccef014u, 0x00000002u};
+    u32 t1[11], t2[13];
+    mp_mul<8, 3>(k.l, G1, t1);
+    mp_mul<8, 5>(k.l, G2, t2);
+    const u32* c1 = t1 + 8;  // < 2^64 (k < 2^254, g1 < 2^66); 3 limbs kept, the top one is 0
+    const u32* c2 = t2 + 8;  // < 2^128; 5 limbs kept, the top one is 0
+    // k1 = k - c1 a1 - c2 a2 over 9 limbs (two's complement)
+    u32 k1[9], p1[5], p2[9];
+#pragma unroll
+    for (int i = 0; i < 8; i++) k1[i] = k.l[i];
+    k1[8] = 0;
+    mp_mul<3, 2>(c1, A1, p1);
+    mp_mul<5, 4>(c2, A2, p2);
+    u32 w[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) w[i] = i < 5 ? p1[i] : 0;
+    mp_sub<9>(k1, w);
+    mp_sub<9>(k1, p2);
+    // k2 = c1 |b1| - c2 b2
+    u32 k2[9], q1[7], q2[7];
+    mp_mul<3, 4>(c1, B1, q1);
+    mp_mul<5, 2>(c2, B2, q2);
+#pragma unroll
+    for (int i = 0; i < 9; i++) { k2[i] = i < 7 ? q1[i] : 0; w[i] = i < 7 ? q2[i] : 0; }
+    mp_sub<9>(k2, w);
+    GlvScalar r;
+    r.neg = (mp_abs<9>(k1) ? 1u : 0u) | (mp_abs<9>(k2) ? 2u : 0u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { r.k1[i] = k1[i]; r.k2[i] = k2[i]; }
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    return r;
+}
+// glv[i] = decomposition of the canonical scalar tw[i]
+__global__ void __launch_bounds__(128) k_glv_decompose(const uint64_t* __restrict__ tw, u32 count, GlvScalar* __restrict__ glv) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) glv[i] = glv_decompose(Fr::load_nc(tw + 4 * (size_t)i));
+}
+__device__ __forceinline__ Fq fq_beta() {  // beta in Montgomery form
+    Fq b;
+    b.l[0] = 0xd782e155u; b.l[1] = 0x71930c11u; b.l[2] = 0xffbe3323u; b.l[3] = 0xa6bb947cu;
+    b.l[4] = 0xd4741444u; b.l[5] = 0xaa303344u; b.l[6] = 0x26594943u; b.l[7] = 0x2c3b3f0du;
+    return b;
+}
+// s * p = k1 * p + k2 * phi(p): 2-bit joint windows over T[i + 4 j] = i * (+-p) + j * (+-phi(p))
+static __device__ __noinline__ XYZZ xyzz_glv_mul(const XYZZ& p, const GlvScalar& s) {
+    if (p.is_identity()) return p;
+    XYZZ T[16];
+    T[0] = XYZZ::identity();
+    T[1] = (s.neg & 1u) ? p.neg() : p;
+    T[4] = (s.neg & 2u) ? p.neg() : p;
+    T[4].x = T[4].x * fq_beta();
+    T[2] = xyzz_dbl(T[1]);
+    T[3] = T[2];
+    xyzz_add(T[3], T[1]);
+    T[8] = xyzz_dbl(T[4]);
+    T[12] = T[8];
+    xyzz_add(T[12], T[4]);
+#pragma unroll 1
+    for (int j = 1; j < 4; j++)
+#pragma unroll 1
+        for (int i = 1; i < 4; i++) {
+            T[4 * j + i] = T[4 * j];
+            xyzz_add(T[4 * j + i], T[i]);
+        }
     XYZZ acc = XYZZ::identity();
 #pragma unroll 1
-    for (int limb = 7; limb >= 0; limb--) {
-        u32 v = 0;
+    for (int limb = 3; limb >= 0; limb--) {
+        u32 v1 = 0, v2 = 0;
 #pragma unroll
-        for (int t = 0; t < 8; t++)
-            if (t == limb) v = s.l[t];
+        for (int t = 0; t < 4; t++)
+            if (t == limb) { v1 = s.k1[t]; v2 = s.k2[t]; }
 #pragma unroll 1
-        for (int bit = 31; bit >= 0; bit--) {
+        for (int sh = 30; sh >= 0; sh -= 2) {
             acc = xyzz_dbl(acc);
-            if ((v >> bit) & 1) xyzz_add(acc, p);
+            acc = xyzz_dbl(acc);
+            const u32 idx = ((v1 >> sh) & 3u) | (((v2 >> sh) & 3u) << 2);
+            if (idx) xyzz_add(acc, T[idx]);
         }
     }
     return acc;
@@ -133,23 +258,23 @@ __global__ void k_srs_consts(Fr x, u32 k, uint64_t* __restrict__ pw, uint64_t* _
     ((xn - Fr::one()) * n_inv).store(extra + 4);
 }
 // stage s (1-based): pairs (i0, i0 + half), twiddle tw[j << (k - s)]
-__global__ void __launch_bounds__(128) k_ecfft_stage(XYZZ* __restrict__ pts, const uint64_t* __restrict__ tw, u32 k, u32 s) {
+__global__ void __launch_bounds__(128) k_ecfft_stage(XYZZ* __restrict__ pts, const GlvScalar* __restrict__ tw, u32 k, u32 s) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >> (k - 1)) return;
     const u32 half = 1u << (s - 1), j = t & (half - 1), i0 = ((t >> (s - 1)) << s) + j, i1 = i0 + half;
     XYZZ a = XYZZ::load(pts + i0), b = XYZZ::load(pts + i1);
-    if (j) b = xyzz_scalar_mul(b, Fr::load_nc(tw + 4 * ((size_t)j << (k - s))));
+    if (j) b = xyzz_glv_mul(b, tw[(size_t)j << (k - s)]);
     XYZZ lo = a;
     xyzz_add(lo, b);
     xyzz_add(a, b.neg());
     lo.store(pts + i0);
     a.store(pts + i1);
 }
-__global__ void __launch_bounds__(128) k_scale_to_affine(const XYZZ* __restrict__ pts, const uint64_t* __restrict__ scalar_canon, u32 n,
+__global__ void __launch_bounds__(128) k_scale_to_affine(const XYZZ* __restrict__ pts, const GlvScalar* __restrict__ scalar, u32 n,
                                                          Affine* __restrict__ out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    xyzz_to_affine(xyzz_scalar_mul(XYZZ::load(pts + i), Fr::load_nc(scalar_canon))).store(out + i);
+    xyzz_to_affine(xyzz_glv_mul(XYZZ::load(pts + i), *scalar)).store(out + i);
 }
 // den[i] = tau - omega^i
 __global__ void __launch_bounds__(256) k_lagrange_den(Fr tau, const uint64_t* __restrict__ omega_pows, u32 n, uint64_t* __restrict__ den) {
@@ -180,17 +305,24 @@ static Fr fr_of(const uint64_t x[4]) {
 void g_to_lagrange_run(h2b_ctx* ctx, const void* d_g, uint32_t k, void* d_g_lagrange) {
     H2B_REQUIRE(k <= 28, "g_to_lagrange: k out of range");
     const size_t n = (size_t)1 << k;
-    // workspace: XYZZ points | twiddles (n/2 canonical) | pw (32) | extra (2)
-    char* w = (char*)ctx->get(WS_POOL, n * sizeof(XYZZ) + (n / 2 + 40) * 32);
+    // workspace: XYZZ points | twiddles (n/2 canonical) | pw (32) | extra (2) | GLV halves of the twiddles (n/2) and of 2^-k
+    const size_t tw_cnt = n / 2 + 1;
+    char* w = (char*)ctx->get(WS_POOL, n * sizeof(XYZZ) + (tw_cnt + 40) * 32 + (tw_cnt + 1) * sizeof(GlvScalar));
     XYZZ* pts = (XYZZ*)w;
     uint64_t* tw = (uint64_t*)(w + n * sizeof(XYZZ));
-    uint64_t* pw = tw + 4 * (n / 2 + 1);
+    uint64_t* pw = tw + 4 * tw_cnt;
     uint64_t* extra = pw + 4 * 32;
+    GlvScalar* glv = (GlvScalar*)(extra + 4 * 8);
+    GlvScalar* glv_ninv = glv + tw_cnt;
     H2B_LAUNCH(ctx, k_srs_consts, 1, 32, 0, fr_of(FR_OMEGA_INV[k]), k, pw, extra);
-    if (n > 1) H2B_LAUNCH(ctx, k_power_table, ceil_div(n / 2, 256), 256, 0, pw, (u32)(n / 2), 1, tw);
+    if (n > 1) {
+        H2B_LAUNCH(ctx, k_power_table, ceil_div(n / 2, 256), 256, 0, pw, (u32)(n / 2), 1, tw);
+        H2B_LAUNCH(ctx, k_glv_decompose, ceil_div(n / 2, 128), 128, 0, tw, (u32)(n / 2), glv);
+    }
+    H2B_LAUNCH(ctx, k_glv_decompose, 1, 128, 0, extra, 1u, glv_ninv);  // extra[0] = (2^k)^-1, canonical
     H2B_LAUNCH(ctx, k_affine_to_xyzz_bitrev, ceil_div(n, 256), 256, 0, (const Affine*)d_g, k, pts);
-    for (uint32_t s = 1; s <= k; s++) H2B_LAUNCH(ctx, k_ecfft_stage, ceil_div(n / 2, 128), 128, 0, pts, tw, k, s);
-    H2B_LAUNCH(ctx, k_scale_to_affine, ceil_div(n, 128), 128, 0, pts, extra, (u32)n, (Affine*)d_g_lagrange);
+    for (uint32_t s = 1; s <= k; s++) H2B_LAUNCH(ctx, k_ecfft_stage, ceil_div(n / 2, 128), 128, 0, pts, (const GlvScalar*)glv, k, s);
+    H2B_LAUNCH(ctx, k_scale_to_affine, ceil_div(n, 128), 128, 0, pts, (const GlvScalar*)glv_ninv, (u32)n, (Affine*)d_g_lagrange);
 }
 
 void batch_invert_run(h2b_ctx* ctx, void* d_a, size_t n);

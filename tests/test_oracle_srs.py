@@ -82,3 +82,29 @@ def test_compressed_point_roundtrip_python():
         assert pyref.g1_decompress(pyref.g1_compress(pyref.g1_neg(p))) == (pyref.g1_neg(p), True)
     assert pyref.g1_decompress(pyref.g1_compress(None)) == (None, True)
     assert pyref.g1_decompress(pyref.P.to_bytes(32, "little"))[1] is False
+
+
+def test_glv_constants_of_the_g1_fft():
+    """csrc/srs.cu multiplies by the twiddles through the endomorphism phi(x, y) = (beta x, y) = lambda (x, y): the
+    constants hard-coded there, re-derived with plain integers — lambda and beta are matching cube roots of unity, the
+    lattice vectors annihilate (1, lambda), the approximate division yields |k1|, |k2| < 2^127 and k = k1 + k2 lambda."""
+    import random
+    R, P = pyref.R, pyref.P
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    beta = 0x59e26bcea0d48bacd4f263f1acdb5c4f5763473177fffffe
+    assert (lam * lam + lam + 1) % R == 0 and (beta * beta + beta + 1) % P == 0
+    gx, gy = pyref.G1
+    assert pyref.g1_mul(lam, pyref.G1) == (beta * gx % P, gy)
+    a1, b1 = 0x89d3256894d213e3, -0x6f4d8248eeb859fc8211bbeb7d4f1128
+    a2, b2 = 0x6f4d8248eeb859fd0be4e1541221250b, 0x89d3256894d213e3
+    assert (a1 + b1 * lam) % R == 0 and (a2 + b2 * lam) % R == 0 and a1 * b2 - a2 * b1 == R
+    g1, g2 = (b2 << 256) // R, (-b1 << 256) // R
+    assert g1 == 0x2d91d232ec7e0b3d7 and g2 == 0x24ccef014a773d2cf7a7bd9d4391eb18d
+    rng = random.Random(5)
+    for k in [0, 1, R - 1, lam, R - lam] + [rng.randrange(R) for _ in range(2000)]:
+        c1, c2 = (k * g1) >> 256, (k * g2) >> 256
+        k1, k2 = k - c1 * a1 - c2 * a2, c1 * (-b1) - c2 * b2
+        assert (k1 + k2 * lam - k) % R == 0 and abs(k1) < 1 << 127 and abs(k2) < 1 << 127
+    # Montgomery form of beta as the kernel holds it
+    bm = beta * (1 << 256) % P
+    assert [(bm >> (32 * i)) & 0xffffffff for i in range(8)] == [0xd782e155, 0x71930c11, 0xffbe3323, 0xa6bb947c, 0xd4741444, 0xaa303344, 0x26594943, 0x2c3b3f0d]
