@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) k_collect_big2(const u32* __restrict__ of
 // multiplications lo * R_lo / hi * C_hi (one thread each) and ~10 for the block sums and the final doublings.
 // One CTA of 128 threads (32 lane-quads, quad.cuh) per row sum R_lo / column sum C_hi: every quad adds its
 // stride-32 share of the row (column), then the 32 quads are summed and the result is multiplied by its weight.
-// rc[set] = [ lo * R_lo (2^ml) | hi * C_hi (2^mh) | C_hi (2^mh) ] after k_rowcol_weights.
+// rc[set] = [ lo * R_lo (2^ml) | (2^ml hi + 1) * C_hi (2^mh) | C_hi (2^mh) ] after k_rowcol_weights.
 __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ buckets, int ml, int mh, u32 nsets,
                                                      XYZZ* __restrict__ rc) {
     __shared__ XYZZ sh[4];
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const XYZZ* __restrict__ bu
         acc.store(is_row ? out + idx : out + (1u << mh) + idx);  // rows in place; plain column sums in the third section
     }
 }
-// rc[set] = [ R_lo | . | C_hi ]  ->  [ lo * R_lo | hi * C_hi | C_hi ]: one lane-quad per point, 4-lane double-and-add
+// rc[set] = [ R_lo | . | C_hi ]  ->  [ lo * R_lo | (2^ml hi + 1) * C_hi | C_hi ]: one lane-quad per point, 4-lane double-and-add
 __global__ void __launch_bounds__(128) k_rowcol_weights(XYZZ* __restrict__ rc, int ml, int mh, u32 nsets) {
     const u32 per_set = (1u << ml) + (1u << mh);
     const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;  // quads never straddle the bound: blockDim.x % 4 == 0
@@ -396,9 +396,11 @@ __global__ void __launch_bounds__(128) k_rowcol_weights(XYZZ* __restrict__ rc, i
     const u32 set = q / per_set, idx = q % per_set;
     const bool is_row = idx < (1u << ml);
     XYZZ* base = rc + (size_t)set * ((1u << ml) + 2 * (1u << mh));
-    const u32 weight = is_row ? idx : idx - (1u << ml);
+    // a column sum carries its own share of V = sum_b (b + 1) B_b in one weight: 2^ml * hi (its index) + 1 (the plain sum
+    // of all buckets), so that the final kernel has nothing left but two sums and one addition
+    const u32 weight = is_row ? idx : (((idx - (1u << ml)) << ml) + 1u);
     const XYZZ p = XYZZ::load(is_row ? base + idx : base + (1u << mh) + idx);
-    const XYZZ w = quad_small_mul<true>(p, weight, is_row ? ml : mh);
+    const XYZZ w = quad_small_mul<true>(p, weight, is_row ? ml : ml + mh);
     if ((threadIdx.x & 3) == 0) w.store(base + idx);
 }
 
@@ -418,29 +420,28 @@ __device__ __forceinline__ void store_jacobian(const XYZZ& p, void* out) {
     z.store(o + 64);
 }
 
-// S_lo = sum of rc[0 .. 2^ml), S_hi = sum of rc[2^ml .. 2^ml + 2^mh), T = sum of the plain column sums: plain sums of
-// 64 x 4 points per CTA (one lane-quad adds 4 of them).  CTAs of a set: [0, sub_lo) -> S_lo, then sub_hi CTAs S_hi, then
-// sub_hi CTAs T.  The last CTA to finish adds the CTA partials, forms V_set = T + S_lo + 2^ml * S_hi, runs Horner over
-// the sets (`shift` doublings between consecutive sets; one set when the bases are tabulated) and stores the
-// Jacobian result.
+// S_lo = sum of rc[0 .. 2^ml) (weighted row sums), S_hi = sum of rc[2^ml .. 2^ml + 2^mh) (column sums weighted with
+// 2^ml hi + 1): plain sums of 64 x 4 points per CTA (one lane-quad adds 4 of them).  CTAs of a set: [0, sub_lo) -> S_lo, then
+// sub_hi CTAs -> S_hi.  `nsets` = sets of ONE MSM; the grid covers gridDim.x / (nsets * cta_per_set) MSMs (a group, see
+// MsmScalars): the last CTA of every MSM to finish adds the CTA partials, forms V_set = S_lo + S_hi, runs Horner over the
+// sets (`shift` doublings between consecutive sets; one set when the bases are tabulated) and stores that MSM's Jacobian
+// result at out + 96 * msm.
 static constexpr int WQ = 256;  // points per CTA of k_weighted_final (64 quads x 4)
-// `nsets` = sets of ONE MSM; the grid covers gridDim.x / (nsets * cta_per_set) MSMs (a group, see MsmScalars): the last
-// CTA of every MSM to finish combines that MSM's sets and stores its result at out + 96 * msm.
 __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__ rc, int ml, int mh, u32 nsets, int shift,
                                                         XYZZ* __restrict__ parts, u32* __restrict__ done,
                                                         void* __restrict__ out) {
     __shared__ XYZZ sh[8];
-    __shared__ XYZZ comb[3];
+    __shared__ XYZZ comb[2];
     __shared__ XYZZ vsets[64];
     __shared__ u32 is_last;
     const u32 sub_lo = ((1u << ml) + WQ - 1) / WQ, sub_hi = ((1u << mh) + WQ - 1) / WQ;
-    const u32 cta_per_set = sub_lo + 2 * sub_hi;
+    const u32 cta_per_set = sub_lo + sub_hi;
     const u32 set = blockIdx.x / cta_per_set, c = blockIdx.x % cta_per_set;  // set counts across the MSMs of the group
     const u32 msm = set / nsets;
-    const u32 kind = c < sub_lo ? 0 : (c < sub_lo + sub_hi ? 1 : 2);
-    const u32 sub = kind == 0 ? c : (kind == 1 ? c - sub_lo : c - sub_lo - sub_hi);
+    const u32 kind = c < sub_lo ? 0 : 1;
+    const u32 sub = kind == 0 ? c : c - sub_lo;
     const u32 per_set = (1u << ml) + 2 * (1u << mh);
-    const XYZZ* src = rc + (size_t)set * per_set + (kind == 0 ? 0 : (kind == 1 ? (1u << ml) : (1u << ml) + (1u << mh)));
+    const XYZZ* src = rc + (size_t)set * per_set + (kind == 0 ? 0 : (1u << ml));
     const u32 cnt = 1u << (kind ? mh : ml);
     const u32 qid = threadIdx.x >> 2;
     XYZZ w = XYZZ::identity();
@@ -455,9 +456,9 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
     __threadfence();
 
     for (u32 s0 = 0; s0 < nsets; s0++) {
-        // three quads add the CTA partials of S_lo, S_hi, T of this set
-        if (qid < 3) {
-            const XYZZ* p = parts + (size_t)(msm * nsets + s0) * cta_per_set + (qid == 0 ? 0 : (qid == 1 ? sub_lo : sub_lo + sub_hi));
+        // two quads add the CTA partials of S_lo and S_hi of this set
+        if (qid < 2) {
+            const XYZZ* p = parts + (size_t)(msm * nsets + s0) * cta_per_set + (qid == 0 ? 0 : sub_lo);
             const u32 cnt = qid == 0 ? sub_lo : sub_hi;
             XYZZ a = XYZZ::load(p);
             for (u32 i = 1; i < cnt; i++) quad_add_nl(a, XYZZ::load(p + i));
@@ -465,10 +466,8 @@ __global__ void __launch_bounds__(256) k_weighted_final(const XYZZ* __restrict__
         }
         __syncthreads();
         if (qid == 0) {
-            XYZZ v = XYZZ::load(comb + 1);  // S_hi
-            for (int d = 0; d < ml; d++) quad_dbl_nl(v);
-            quad_add_nl(v, XYZZ::load(comb + 0));  // + S_lo
-            quad_add_nl(v, XYZZ::load(comb + 2));  // + T
+            XYZZ v = XYZZ::load(comb + 0);
+            quad_add_nl(v, XYZZ::load(comb + 1));
             if (threadIdx.x == 0) v.store(vsets + s0);
         }
         __syncthreads();
@@ -750,7 +749,7 @@ void msm_run_group(h2b_ctx* ctx, const void* const* d_tables, size_t n, int c, i
     const u32 all_sets = nsets * (u32)m;
     const u32 per_set = (1u << ml) + (1u << mh);  // row + column sums (one CTA each)
     const u32 sub_lo = ((1u << ml) + WQ - 1) / WQ, sub_hi = ((1u << mh) + WQ - 1) / WQ;
-    const u32 cta_per_set = sub_lo + 2 * sub_hi;
+    const u32 cta_per_set = sub_lo + sub_hi;
     XYZZ* rc = (XYZZ*)ctx->get(WS_REDUCE_A, (size_t)all_sets * (per_set + (1u << mh)) * sizeof(XYZZ));
     char* rb = (char*)ctx->get(WS_REDUCE_B, (size_t)all_sets * cta_per_set * sizeof(XYZZ) + 256);
     XYZZ* parts = (XYZZ*)rb;
