@@ -306,6 +306,7 @@ class ProverSession:
         self.h2d_bytes = self.d2h_bytes = 0
         self.begin, self.n_loc, self.allreduce = 0, n, None
         self.keep = None  # verification runs: dict that receives the committed polynomials (downloaded, untimed)
+        self.blind_log = None
 
     def shard(self, begin: int, n_loc: int, allreduce):
         """multi-GPU: this rank commits rows [begin, begin + n_loc) of every polynomial and `allreduce(ptr, m)` combines the
@@ -349,6 +350,8 @@ class ProverSession:
         cnt = self.cs.n - first_row
         b = rng.integers(0, 1 << 62, size=(cnt, 4), dtype=np.int64).astype(np.uint64)
         b[:, 3] &= np.uint64((1 << 60) - 1)
+        if self.blind_log is not None:  # the blinding rows in the order of use (the C++ twin replays them)
+            self.blind_log.append(b)
         col.upload(b, first_row)
         self.h2d_bytes += cnt * 32
 

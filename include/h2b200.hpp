@@ -114,6 +114,7 @@ public:
     ParamsKZG(const ParamsKZG&) = delete;
     ParamsKZG& operator=(const ParamsKZG&) = delete;
     uint32_t k() const { return k_; }
+    const h2b_srs* raw() const { return srs_; }  // for the `_dev` entry points (the resident prover, h2b200_prover.hpp)
     // ParamsKZG::commit(poly in coefficient form) / commit_lagrange(poly in Lagrange form)
     G1 commit(const std::vector<Fr>& poly) const { return commit_(H2B_BASIS_MONOMIAL, poly); }
     G1 commit_lagrange(const std::vector<Fr>& poly) const { return commit_(H2B_BASIS_LAGRANGE, poly); }

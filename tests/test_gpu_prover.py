@@ -105,6 +105,50 @@ def test_resident_proof_commitments_and_quotient_identity(ctx, h2b, k, A, L, sel
     sess.free(); cs.free(); params.close()
 
 
+@pytest.mark.parametrize("k,A,L,sel", [(8, 1, 0, True), (8, 1, 0, False), (9, 7, 2, True)])
+def test_cpp_prover_matches_python(ctx, h2b, k, A, L, sel, tmp_path):
+    """the compiled host side (include/h2b200_prover.hpp: ProverCircuit + ProverSession::create_proof, Blake2b transcript,
+    host-side 254-bit arithmetic) drives the C ABI to the SAME BYTES as halo2-lib_b200/prover.py for the same instance,
+    SRS, random polynomial and blinding rows: commitments, evaluations and challenges are compared byte for byte.  The
+    Python proof is the one the protocol-level checks above run on."""
+    import os, subprocess
+    rng, params, cs, sess, inst, bases = _setup(ctx, h2b, k, 3500 + k + 10 * A, A, L, sel)
+    n = 1 << k
+    rnd = mont(rand_ints(rng, n, R), R)
+    sess.blind_log = []
+    res = _prove(sess, inst, rnd)
+    blind = np.concatenate(sess.blind_log) if sess.blind_log else np.zeros((0, 4), dtype=np.uint64)
+    sess.blind_log = None
+    left, right = pc.quotient_identity(res, k, cs.bf, A, L, sel)
+    assert left == right
+    d = str(tmp_path)
+    w = lambda name, arr: np.ascontiguousarray(arr, dtype=np.uint64).tofile(os.path.join(d, name))
+    for nm in cs.fixed_names:
+        w("fixed_%s.bin" % nm, inst["fixed"][nm])
+    for i, sg in enumerate(inst["sigma"]):
+        w("sigma_%d.bin" % i, sg)
+    w("witness.bin", inst["virtual"]); w("breaks.bin", inst["break_points"]); w("lookup.bin", inst["lookup"])
+    w("random.bin", rnd); w("blind.bin", blind); w("bases_m.bin", bases[0]); w("bases_l.bin", bases[1])
+    with open(os.path.join(d, "manifest.txt"), "w") as f:
+        f.write("%d %d %d %d %d %d %d %d\n" % (k, A, L, 1 if sel else 0, len(inst["virtual"]), len(inst["break_points"]), len(inst["lookup"]), len(blind)))
+    import test_cpp_mirror as tcm
+    exe = os.path.join(tcm.ROOT, "build", "prover_mirror_test")
+    tcm.test_cpp_prover_mirror_compiles_and_links()
+    out = subprocess.run([exe, d], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = np.fromfile(os.path.join(d, "proof.bin"), dtype=np.uint64)
+    nc = int(raw[0])
+    cms = raw[1:1 + 12 * nc].reshape(nc, 12)
+    ne = int(raw[1 + 12 * nc])
+    evs = raw[2 + 12 * nc: 2 + 12 * nc + 4 * ne].reshape(ne, 4)
+    chal = raw[2 + 12 * nc + 4 * ne:].reshape(5, 4)
+    assert nc == len(res["commitments"]) and np.array_equal(cms, np.stack(res["commitments"]))
+    assert ne == len(res["evals"]) and np.array_equal(evs, np.stack(list(res["evals"].values())))
+    want = [res["challenges"][c] for c in ("theta", "beta", "gamma", "y", "x")]
+    assert [pc.fr(c) for c in chal] == want
+    sess.free(); cs.free(); params.close()
+
+
 def test_product_columns_vs_integer_recurrence(ctx, h2b):
     from halo2_lib_b200._capi import lib
     k, bf = 7, 6
