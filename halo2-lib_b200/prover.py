@@ -46,6 +46,31 @@ def from_limbs(l) -> int:
     return sum(int(v) << (64 * i) for i, v in enumerate(np.asarray(l, dtype=np.uint64).reshape(4))) * MONT_RINV % R_MOD
 
 
+P_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+_PR, _PRINV = (1 << 256) % P_MOD, pow(1 << 256, -1, P_MOD)
+
+
+_PR2, _PR3 = pow(_PR, 2, P_MOD), pow(_PR, 3, P_MOD)
+_ONE_BYTES = _PR.to_bytes(32, "little")
+
+
+def g1_normalize_host(pt) -> np.ndarray:
+    """Jacobian (X, Y, Z), Montgomery limbs -> (X / Z^2, Y / Z^3, 1); the identity -> all zero.  The form in which a
+    commitment enters the transcript and the proof: the accumulation order inside an MSM is not deterministic (atomics in the
+    counting sort), so the Jacobian representative is not either; the affine point is.  One modular inversion per
+    commitment on the host, as the Rust prover's `to_affine`.  (Montgomery domain throughout: with Xm = X R, Zm = Z R the
+    result x R is Xm R^2 / Zm^2.)"""
+    b = np.ascontiguousarray(pt, dtype=np.uint64).tobytes()
+    xm, ym, zm = (int.from_bytes(b[32 * j:32 * j + 32], "little") for j in range(3))
+    if zm == 0:
+        return np.zeros(12, dtype=np.uint64)
+    zi = pow(zm, -1, P_MOD)
+    zi2 = zi * zi % P_MOD
+    x = xm * zi2 % P_MOD * _PR2 % P_MOD
+    y = ym * zi2 % P_MOD * zi % P_MOD * _PR3 % P_MOD
+    return np.frombuffer(x.to_bytes(32, "little") + y.to_bytes(32, "little") + _ONE_BYTES, dtype=np.uint64)
+
+
 class Poly:
     """h2b_poly: a device-resident column / polynomial"""
 
@@ -335,7 +360,7 @@ class ProverSession:
             out = np.empty((m * 3, 4), dtype=np.uint64)
             ctx.check(lib.h2b_poly_download(ctx.h, self.d_out.h, 0, C.c_void_p(out.ctypes.data), m * 3))
             self.d2h_bytes += m * 96
-            outs.append(out.reshape(m, 12))
+            outs.append(np.stack([g1_normalize_host(pt) for pt in out.reshape(m, 12)]))
         return np.concatenate(outs)
 
     def _raw_download(self, dev_ptr: int, arr: np.ndarray):

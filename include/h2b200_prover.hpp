@@ -23,32 +23,41 @@
 
 namespace h2b {
 
-// ------------------------------------------------------------------------------------------------ host-side Fr (Montgomery)
-// a few dozen multiplications per proof: challenges, rotations of the evaluation point, powers of v and mu
-struct HostFr {
+// ------------------------------------------------------------------------------------------------ host-side fields (Montgomery)
+// a few dozen multiplications per proof: challenges, rotations of the evaluation point, powers of v and mu (Fr); one
+// inversion per commitment to bring it to affine form before it enters the transcript (Fq) — what the Rust side does on the CPU
+struct FrHostParams {
     static constexpr uint64_t MOD[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
     static constexpr uint64_t R1[4] = {0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL};
     static constexpr uint64_t R2[4] = {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL};
     static constexpr uint64_t INV = 0xc2e1f593efffffffULL;  // -r^-1 mod 2^64
-    // 2^28-th root of unity 7^((r - 1) >> 28), canonical (halo2curves bn256::Fr::ROOT_OF_UNITY)
-    static constexpr uint64_t ROOT28[4] = {0xd34f1ed960c37c9cULL, 0x3215cf6dd39329c8ULL, 0x98865ea93dd31f74ULL, 0x03ddb9f5166d18b7ULL};
-
-    static Fr one() { return {R1[0], R1[1], R1[2], R1[3]}; }
+};
+struct FqHostParams {
+    static constexpr uint64_t MOD[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+    static constexpr uint64_t R1[4] = {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL};
+    static constexpr uint64_t R2[4] = {0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL};
+    static constexpr uint64_t INV = 0x87d20782e4866389ULL;  // -p^-1 mod 2^64
+};
+template <class P>
+struct HostField {
+    using E = std::array<uint64_t, 4>;
+    static E one() { return {P::R1[0], P::R1[1], P::R1[2], P::R1[3]}; }
+    static bool is_zero(const E& a) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
     static bool geq_mod(const uint64_t a[4]) {
         for (int i = 3; i >= 0; i--) {
-            if (a[i] != MOD[i]) return a[i] > MOD[i];
+            if (a[i] != P::MOD[i]) return a[i] > P::MOD[i];
         }
         return true;
     }
     static void sub_mod(uint64_t a[4]) {
         unsigned __int128 borrow = 0;
         for (int i = 0; i < 4; i++) {
-            unsigned __int128 t = (unsigned __int128)a[i] - MOD[i] - (uint64_t)borrow;
+            unsigned __int128 t = (unsigned __int128)a[i] - P::MOD[i] - (uint64_t)borrow;
             a[i] = (uint64_t)t;
             borrow = (t >> 64) & 1;
         }
     }
-    static Fr mul(const Fr& a, const Fr& b) {  // Montgomery product (CIOS)
+    static E mul(const E& a, const E& b) {  // Montgomery product (CIOS)
         uint64_t t[6] = {0, 0, 0, 0, 0, 0};
         for (int i = 0; i < 4; i++) {
             unsigned __int128 carry = 0;
@@ -60,10 +69,10 @@ struct HostFr {
             unsigned __int128 cur = (unsigned __int128)t[4] + (uint64_t)carry;
             t[4] = (uint64_t)cur;
             t[5] = (uint64_t)(cur >> 64);
-            const uint64_t m = t[0] * INV;
-            carry = ((unsigned __int128)m * MOD[0] + t[0]) >> 64;
+            const uint64_t m = t[0] * P::INV;
+            carry = ((unsigned __int128)m * P::MOD[0] + t[0]) >> 64;
             for (int j = 1; j < 4; j++) {
-                cur = (unsigned __int128)m * MOD[j] + t[j] + (uint64_t)carry;
+                cur = (unsigned __int128)m * P::MOD[j] + t[j] + (uint64_t)carry;
                 t[j - 1] = (uint64_t)cur;
                 carry = cur >> 64;
             }
@@ -75,31 +84,7 @@ struct HostFr {
         if (t[4] || geq_mod(r)) sub_mod(r);
         return {r[0], r[1], r[2], r[3]};
     }
-    static Fr from_canonical(const uint64_t c[4]) { return mul({c[0], c[1], c[2], c[3]}, {R2[0], R2[1], R2[2], R2[3]}); }
-    static Fr pow(Fr base, uint64_t e) {
-        Fr acc = one();
-        while (e) {
-            if (e & 1) acc = mul(acc, base);
-            base = mul(base, base);
-            e >>= 1;
-        }
-        return acc;
-    }
-    // 64 little-endian bytes -> the integer mod r, Montgomery form (the transcript's challenge)
-    static Fr from_wide_bytes(const uint8_t d[64]) {
-        uint64_t lo[4], hi[4];
-        std::memcpy(lo, d, 32);
-        std::memcpy(hi, d + 32, 32);
-        // value = lo + hi 2^256;  mont(lo) = lo R2 / R,  mont(hi 2^256) = hi R2 R2 / R / R ... = mul(mul(hi, R2), R2)
-        const Fr r2 = {R2[0], R2[1], R2[2], R2[3]};
-        uint64_t l[4] = {lo[0], lo[1], lo[2], lo[3]}, h[4] = {hi[0], hi[1], hi[2], hi[3]};
-        while (geq_mod(l)) sub_mod(l);  // Montgomery multiplication wants operands < r
-        while (geq_mod(h)) sub_mod(h);
-        const Fr ml = mul({l[0], l[1], l[2], l[3]}, r2);
-        const Fr mh = mul(mul({h[0], h[1], h[2], h[3]}, r2), r2);
-        return add(ml, mh);
-    }
-    static Fr add(const Fr& a, const Fr& b) {
+    static E add(const E& a, const E& b) {
         uint64_t r[4];
         unsigned __int128 carry = 0;
         for (int i = 0; i < 4; i++) {
@@ -110,12 +95,55 @@ struct HostFr {
         if (carry || geq_mod(r)) sub_mod(r);
         return {r[0], r[1], r[2], r[3]};
     }
+    static E from_canonical(const uint64_t c[4]) { return mul({c[0], c[1], c[2], c[3]}, {P::R2[0], P::R2[1], P::R2[2], P::R2[3]}); }
+    static E pow(E base, uint64_t e) {
+        E acc = one();
+        while (e) {
+            if (e & 1) acc = mul(acc, base);
+            base = mul(base, base);
+            e >>= 1;
+        }
+        return acc;
+    }
+    static E inv(const E& a) {  // a^(modulus - 2): Fermat, ~380 products (tens of microseconds on the host)
+        uint64_t e[4] = {P::MOD[0] - 2, P::MOD[1], P::MOD[2], P::MOD[3]};  // the low limbs of both moduli are >= 2
+        E acc = one();
+        for (int limb = 3; limb >= 0; limb--)
+            for (int bit = 63; bit >= 0; bit--) {
+                acc = mul(acc, acc);
+                if ((e[limb] >> bit) & 1) acc = mul(acc, a);
+            }
+        return acc;
+    }
+};
+using HostFq = HostField<FqHostParams>;
+struct HostFr : HostField<FrHostParams> {
+    // 2^28-th root of unity 7^((r - 1) >> 28), canonical (halo2curves bn256::Fr::ROOT_OF_UNITY)
+    static constexpr uint64_t ROOT28[4] = {0xd34f1ed960c37c9cULL, 0x3215cf6dd39329c8ULL, 0x98865ea93dd31f74ULL, 0x03ddb9f5166d18b7ULL};
+    // 64 little-endian bytes -> the integer mod r, Montgomery form (the transcript's challenge)
+    static Fr from_wide_bytes(const uint8_t d[64]) {
+        uint64_t l[4], h[4];
+        std::memcpy(l, d, 32);
+        std::memcpy(h, d + 32, 32);
+        // value = lo + hi 2^256:  mont(lo) = mul(lo, R2),  mont(hi 2^256) = mul(mul(hi, R2), R2)
+        const Fr r2 = {FrHostParams::R2[0], FrHostParams::R2[1], FrHostParams::R2[2], FrHostParams::R2[3]};
+        while (geq_mod(l)) sub_mod(l);  // Montgomery multiplication wants operands < r
+        while (geq_mod(h)) sub_mod(h);
+        return add(mul({l[0], l[1], l[2], l[3]}, r2), mul(mul({h[0], h[1], h[2], h[3]}, r2), r2));
+    }
     static Fr omega(uint32_t k) {  // generator of the 2^k domain
         Fr w = from_canonical(ROOT28);
         for (uint32_t i = k; i < 28; i++) w = mul(w, w);
         return w;
     }
 };
+// Jacobian (X, Y, Z) -> (X / Z^2, Y / Z^3, 1), the identity -> all zero: the form in which a commitment enters the transcript
+// and the proof (the accumulation order inside an MSM is not deterministic, the Jacobian representative therefore is not either)
+inline G1 g1_normalize_host(const G1& p) {
+    if (HostFq::is_zero(p.z)) return G1{{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    const Fq zi = HostFq::inv(p.z), zi2 = HostFq::mul(zi, zi);
+    return G1{HostFq::mul(p.x, zi2), HostFq::mul(p.y, HostFq::mul(zi2, zi)), HostFq::one()};
+}
 
 // ------------------------------------------------------------------------------------------------ Blake2b-512 (RFC 7693)
 class Blake2b {
@@ -405,6 +433,7 @@ public:
                 std::vector<G1> out(m);
                 ctx.check(h2b_poly_download(c, d_out->raw(), 0, out[0].x.data(), m * 3));
                 res.d2h_bytes += m * 96;
+                for (auto& pt : out) pt = g1_normalize_host(pt);  // affine form: what the transcript and the proof hold
                 if (absorb) tr.absorb(out.data(), m * sizeof(G1));
                 res.commitments.insert(res.commitments.end(), out.begin(), out.end());
             }

@@ -45,5 +45,8 @@ int main() {
     uint8_t wide[64];
     for (int i = 0; i < 64; i++) wide[i] = 0xff;
     hex("wide_ff", HostFr::from_wide_bytes(wide).data(), 32);
+    const G1 pt{c1, c2, c3}, nz = g1_normalize_host(pt), id = g1_normalize_host(G1{c1, c2, Fq{0, 0, 0, 0}});
+    hex("normalize", &nz, 96);
+    hex("normalize_identity", &id, 96);
     return 0;
 }

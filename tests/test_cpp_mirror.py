@@ -59,6 +59,14 @@ def test_cpp_prover_host_side_matches_python_integers():
     root = pow(7, (R - 1) >> 28, R)
     assert out["omega5"] == mont_hex(pow(root, 1 << 23, R)) and out["omega19"] == mont_hex(pow(root, 1 << 9, R))
     assert out["wide_ff"] == mont_hex(int.from_bytes(b"\xff" * 64, "little") % R)
+    # commitments enter the transcript in affine form: the host normalisation of both provers agrees
+    import numpy as np
+    from halo2_lib_b200.prover import g1_normalize_host
+    limbs = lambda h: np.frombuffer(bytes.fromhex(h), dtype=np.uint64)
+    pt = np.concatenate([limbs(out["squeeze1"]), limbs(out["squeeze2"]), limbs(out["squeeze3"])])
+    assert np.array_equal(g1_normalize_host(pt), limbs(out["normalize"]))
+    pt0 = pt.copy(); pt0[8:] = 0
+    assert not limbs(out["normalize_identity"]).any() and not g1_normalize_host(pt0).any()
 
 
 def test_cpp_prover_mirror_compiles_and_links():
