@@ -71,6 +71,32 @@ def g1_normalize_host(pt) -> np.ndarray:
     return np.frombuffer(x.to_bytes(32, "little") + y.to_bytes(32, "little") + _ONE_BYTES, dtype=np.uint64)
 
 
+def g1_normalize_host_batch(pts: np.ndarray) -> np.ndarray:
+    """g1_normalize_host over the m commitments of a phase with ONE modular inversion (Montgomery's trick)"""
+    pts = np.ascontiguousarray(pts, dtype=np.uint64).reshape(-1, 12)
+    b = pts.tobytes()
+    val = [int.from_bytes(b[32 * j:32 * j + 32], "little") for j in range(3 * len(pts))]
+    zs = [val[3 * i + 2] for i in range(len(pts))]
+    pref, acc = [], 1
+    for z in zs:  # prefix products over the non-zero z
+        pref.append(acc)
+        if z:
+            acc = acc * z % P_MOD
+    inv = pow(acc, -1, P_MOD)
+    out = bytearray(96 * len(pts))
+    for i in range(len(pts) - 1, -1, -1):
+        z = zs[i]
+        if not z:
+            continue
+        zi = inv * pref[i] % P_MOD
+        inv = inv * z % P_MOD
+        zi2 = zi * zi % P_MOD
+        x = val[3 * i] * zi2 % P_MOD * _PR2 % P_MOD
+        y = val[3 * i + 1] * zi2 % P_MOD * zi % P_MOD * _PR3 % P_MOD
+        out[96 * i:96 * i + 96] = x.to_bytes(32, "little") + y.to_bytes(32, "little") + _ONE_BYTES
+    return np.frombuffer(bytes(out), dtype=np.uint64).reshape(-1, 12)
+
+
 class Poly:
     """h2b_poly: a device-resident column / polynomial"""
 
@@ -360,7 +386,7 @@ class ProverSession:
             out = np.empty((m * 3, 4), dtype=np.uint64)
             ctx.check(lib.h2b_poly_download(ctx.h, self.d_out.h, 0, C.c_void_p(out.ctypes.data), m * 3))
             self.d2h_bytes += m * 96
-            outs.append(np.stack([g1_normalize_host(pt) for pt in out.reshape(m, 12)]))
+            outs.append(g1_normalize_host_batch(out))
         return np.concatenate(outs)
 
     def _raw_download(self, dev_ptr: int, arr: np.ndarray):
