@@ -9,7 +9,9 @@
 //   witness.bin, breaks.bin (u64 each), lookup.bin, random.bin (2^k), blind.bin (the blinding rows in the order of use)
 //   bases_m.bin, bases_l.bin   2^k affine points (64 bytes each): the SRS
 // Output: proof.bin = [n_commitments u64][commitments 96 B each][n_evals u64][evals 32 B each][theta beta gamma y x]
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -72,6 +74,18 @@ int main(int argc, char** argv) {
         for (int rep = 0; rep < 2; rep++) {  // twice on one session: the working set is reused
             pos = 0;
             pr = sess.create_proof(witness, breaks, lookup, rnd, source);
+        }
+        if (argc >= 4 && std::string(argv[2]) == "--time") {  // wall clock of N proofs end to end (host buffers in, proof out)
+            const int reps = std::atoi(argv[3]);
+            ctx.synchronize();
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int rep = 0; rep < reps; rep++) {
+                pos = 0;
+                pr = sess.create_proof(witness, breaks, lookup, rnd, source);
+            }
+            ctx.synchronize();
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+            std::printf("prover mirror timing: %.3f ms per proof over %d proofs (k = %u, A = %zu, L = %zu)\n", ms, reps, k, A, L);
         }
         if (pos != blind.size()) throw std::runtime_error("blinding rows consumed: " + std::to_string(pos) + " of " + std::to_string(blind.size()));
         std::ofstream out(dir + "/proof.bin", std::ios::binary);
