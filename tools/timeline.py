@@ -11,21 +11,26 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=3)
 ap.add_argument("--k", type=int, default=None)
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.csv"))
+ap.add_argument("--prover", action="store_true", help="one resident PROOF (ProverSession.prove) instead of the schedule step")
 a = ap.parse_args()
 args = argparse.Namespace(gpus=1, inject_fault=None)
 rig = bench.Rig(args)
 torch = rig.torch
 from halo2_lib_b200._capi import lib
 wl = bench.Workload(rig, bench.Schedule(a.config, a.k), want_e2e=False)
+step = wl.step_resident
+if a.prover:
+    wl.setup_prover()
+    step = wl.step_e2e_prover
 for _ in range(3):
-    wl.step_resident()
+    step()
 torch.cuda.synchronize()
 for c in (rig.ctx, rig.ctx_ntt):
     c.profile_reset(); c.profile_enable("*")
 origin = torch.cuda.Event(enable_timing=True)
 end = torch.cuda.Event(enable_timing=True)
 origin.record(rig.stream)
-wl.step_resident()
+step()
 end.record(rig.stream)
 torch.cuda.synchronize()
 if os.path.exists(a.out):
