@@ -4,11 +4,12 @@
 // ParamsKZG::commit / commit_lagrange inside create_proof (sole halo2-lib call site of create_proof:
 // halo2-base/src/utils/testing.rs:40-48).  The result is the same group element.
 //
-// Pipeline (all on the context's stream, no host synchronisation):
+// Pipeline (no host synchronisation; up to 16 MSMs of one size — the columns a prover phase commits — share ONE pipeline,
+// their bucket sets side by side, msm_run_group; the bucket reduction of a lane's group runs on a high-priority stream):
 //   k_digits<0>       scalars (Montgomery) -> canonical -> signed base-2^c digits -> histogram of bucket keys
 //   k_scan_tiles/apply exclusive scan: first sorted position of every bucket
-//   k_digits<1>       same recoding, scatters (table index | sign) to its sorted position (counting sort;
-//                     warp-aggregated atomics so that hot buckets cost one atomic per warp)
+//   k_digits<1>       same recoding, scatters (table index | table bit | sign) to its sorted position (counting
+//                     sort; warp-aggregated atomics so that hot buckets cost one atomic per warp)
 //   k_accumulate      every thread owns EXACTLY L consecutive sorted entries (perfect balance under any
 //                     scalar distribution, witness columns are dominated by 0/1/88-bit limbs), gathers the
 //                     64-byte affine points with 128-bit loads, XYZZ mixed adds; buckets that end inside
@@ -16,7 +17,9 @@
 //   k_collect         per bucket: add the partials of the chunks it spans; buckets spanning > 64 chunks are
 //   k_collect_big1/2  cut into segments summed by whole CTAs
 //   k_rowcol_sums     bucket grid 2^mh x 2^ml: one CTA of 32 lane-quads per row sum / column sum (quad.cuh)
-//   k_weighted_final  lo * R_lo and hi * C_hi by 4-lane double-and-add, block sums, Horner over bucket sets
+//   k_rowcol_weights  lo * R_lo and (2^ml hi + 1) * C_hi by 4-lane double-and-add, one quad per point
+//   k_weighted_final  the two sums of the weighted points; the last CTA of every MSM adds them (Horner over bucket
+//                     sets for ad-hoc bases) and stores that MSM's Jacobian result
 //
 // Fixed bases (the SRS): `table[w*n + i] = 2^(c*w) * P_i` is built once per SRS (k_precompute_level), so all
 // windows of a scalar fall into ONE bucket set: no per-window reduction and no final doublings.
