@@ -625,6 +625,8 @@ class Workload:
         owners = h.ntt_owners_balanced([1.0] * npoly + [float(1 << (ext_k - k))] * (npoly + 1), world)
         self.my_ntt = lambda i: owners[i] == rank
         mine = [i for i in range(npoly) if self.my_ntt(i) or self.my_ntt(npoly + i)]
+        if not mine:  # a rank that owns no column transform (8 GPUs: six own one large transform each) still times the ops
+            mine = [0]
         self.polys_dev = {i: dev_u64(uniform_residues(rng, n)) for i in mine}
         self.ext_dev = {i: torch.empty((1 << ext_k, 4), dtype=torch.int64, device=dev) for i in mine}
         if 0 not in self.ext_dev:
