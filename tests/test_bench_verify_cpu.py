@@ -46,3 +46,18 @@ def test_horner_mont():
     x = 0xabcdef123
     assert bench.horner_mont(mont(c, pyref.R), x) == sum(ci * pow(x, i, pyref.R) for i, ci in enumerate(c)) % pyref.R
     assert bench.ZETA == pyref.ZETA and bench.ROOT_OF_UNITY == pyref.ROOT_OF_UNITY
+
+
+def test_every_transform_has_one_owner_at_every_world_size():
+    """bench.py deals whole transforms to the ranks by cost; at 8 GPUs some ranks own only a coset transform or none at
+    all (the k = 14 config has 7 transforms) — every transform must still have exactly one owner"""
+    import bench
+    import halo2_lib_b200 as h
+    for cfg in (1, 2, 3, 4, 5):
+        s = bench.Schedule(cfg)
+        costs = [1.0] * s.n_poly + [float(1 << (s.ext_k - s.k))] * (s.n_poly + 1)
+        for world in (1, 2, 4, 8):
+            owners = h.ntt_owners_balanced(costs, world)
+            assert len(owners) == 2 * s.n_poly + 1 and all(0 <= o < world for o in owners)
+            load = [sum(c for c, o in zip(costs, owners) if o == r) for r in range(world)]
+            assert max(load) - min(load) <= max(costs)
