@@ -48,6 +48,27 @@ int main() {
     CHECK(memcmp(&pts[0], &pts[4], sizeof(G1)) == 0);
     CHECK(memcmp(&pts[2], &pts[5], sizeof(G1)) == 0);
     CHECK(memcmp(&pts[0], &pts[2], sizeof(G1)) != 0);
+    {   // a phase of 7 commitments over both bases: grouped pipelines (any group size) == one commitment at a time
+        std::vector<std::vector<Fr>> colsv(7, s);
+        for (size_t j = 0; j < colsv.size(); j++)
+            for (size_t i = j; i < n; i += 3 + j) colsv[j][i] = small_mont(ctx, 1 + (i * (j + 1)) % 5);  // witness-like stretches
+        std::fill(colsv[3].begin(), colsv[3].end(), Fr{0, 0, 0, 0});                                      // an all-zero column
+        std::vector<int> basis = {0, 1, 1, 0, 1, 0, 1};
+        std::vector<const std::vector<Fr>*> refs;
+        for (auto& cv : colsv) refs.push_back(&cv);
+        std::vector<G1> single;
+        for (size_t j = 0; j < colsv.size(); j++) single.push_back(basis[j] ? params.commit_lagrange(colsv[j]) : params.commit(colsv[j]));
+        ctx.batch_normalize(single);
+        for (int64_t grp : {1, 3, 16, 0}) {
+            ctx.set_option("msm.batch_group", grp);
+            auto got = params.commit_many(basis, refs);
+            ctx.batch_normalize(got);
+            CHECK(memcmp(got.data(), single.data(), single.size() * sizeof(G1)) == 0);
+        }
+        bool rejected = false;
+        try { ctx.set_option("msm.batch_group", 99); } catch (const Error& e) { rejected = (e.code == H2B_ERR_ARG); }
+        CHECK(rejected);
+    }
 
     EvaluationDomain dom(ctx, 5, k);
     CHECK(dom.extended_k() == k + 2);
