@@ -354,6 +354,7 @@ class ProverSession:
         self.tmp_side = [P(n) for _ in range(3)]
         self.d_out = P(48)                              # commitments of a phase: up to 16 x 12 limbs (3 elements each)
         self.d_status = P(max(1, cs.n_lookups))         # verdict word of every lookup permutation
+        self.zero = P(1)                                # one zero element (never written)
         self.h2d_bytes = self.d2h_bytes = 0
         self.begin, self.n_loc, self.allreduce = 0, n, None
         self.keep = None  # verification runs: dict that receives the committed polynomials (downloaded, untimed)
@@ -599,6 +600,9 @@ class ProverSession:
                 for r in rots:  # successive divisions by (X - point): the quotient by the set's vanishing polynomial
                     z = to_limbs(rot(r))
                     ctx.check(lib.h2b_kate_division_dev(ctx.h, vp(src.ptr), n, vp(z.ctypes.data), vp(dst.ptr)))
+                    # kate_division writes the n - 1 quotient coefficients; the buffer is reused as an n-coefficient
+                    # polynomial (next division, linear combination), so its top coefficient is cleared
+                    ctx.check(lib.h2b_poly_copy_dev(ctx.h, vp(dst.at(n - 1)), vp(self.zero.ptr), 1))
                     src, dst = dst, src
                 mu_s = pow(mu, si, R_MOD)
                 if first:
@@ -628,6 +632,7 @@ class ProverSession:
         # final quotient: L(X) = h_spl-weighted combination, W' = L / (X - u) (the remainder is dropped by kate_division)
         ul = to_limbs(u_ch)
         ctx.check(lib.h2b_kate_division_dev(ctx.h, vp(self.tmp[2].ptr), n, vp(ul.ctypes.data), vp(self.tmp[3].ptr)))
+        ctx.check(lib.h2b_poly_copy_dev(ctx.h, vp(self.tmp[3].at(n - 1)), vp(self.zero.ptr), 1))
         cm = self._commit([(BASIS_MONOMIAL, self.tmp[3].ptr)])
         res["commitments"] += list(cm)
         res["h2d_bytes"], res["d2h_bytes"] = self.h2d_bytes, self.d2h_bytes

@@ -412,6 +412,7 @@ public:
         for (auto& t : tmp_side) t = own(n);
         d_out = own(48);
         d_status = own(std::max<size_t>(1, cs.n_lookups));
+        zero = own(1);  // one zero element (never written)
     }
 
     // witness: the virtual column of the gate cells (Montgomery), break_points as keygen pinned them, lookup_cells in
@@ -665,6 +666,9 @@ public:
                 for (int r : rots) {  // successive divisions by (X - point): the quotient by the set's vanishing polynomial
                     const Fr z = rot(r);
                     ctx.check(h2b_kate_division_dev(c, src->at(), n, z.data(), dst->at()));
+                    // kate_division writes the n - 1 quotient coefficients; the buffer is reused as an n-coefficient
+                    // polynomial (next division, linear combination), so its top coefficient is cleared
+                    ctx.check(h2b_poly_copy_dev(c, dst->at(n - 1), zero->at(), 1));
                     std::swap(src, dst);
                 }
                 const Fr mu_s = HostFr::pow(mu, si);
@@ -692,6 +696,7 @@ public:
         const Fr u_ch = tr.squeeze();
         // final quotient: W' = L / (X - u) (the remainder is dropped by kate_division)
         ctx.check(h2b_kate_division_dev(c, tmp[2]->at(), n, u_ch.data(), tmp[3]->at()));
+        ctx.check(h2b_poly_copy_dev(c, tmp[3]->at(n - 1), zero->at(), 1));
         commit({{H2B_BASIS_MONOMIAL, tmp[3]->at()}}, false);
         return res;
     }
@@ -734,7 +739,7 @@ private:
     PolyPtr v, lkv, adv_block;
     std::map<std::string, ColRef> lagr;
     std::map<std::string, Poly*> coef, ext;
-    Poly *inp = nullptr, *rnd = nullptr, *h = nullptr, *d_out = nullptr, *d_status = nullptr;
+    Poly *inp = nullptr, *rnd = nullptr, *h = nullptr, *d_out = nullptr, *d_status = nullptr, *zero = nullptr;
     std::array<Poly*, 4> tmp{};
     std::array<Poly*, 3> tmp_side{};
     std::vector<uint32_t> hold_prog;

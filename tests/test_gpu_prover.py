@@ -105,6 +105,38 @@ def test_resident_proof_commitments_and_quotient_identity(ctx, h2b, k, A, L, sel
     sess.free(); cs.free(); params.close()
 
 
+@pytest.mark.parametrize("k,A,L,sel", [(5, 1, 0, True), (5, 1, 0, False), (5, 2, 1, True), (6, 3, 2, True)])
+def test_resident_prover_matches_the_oracle_prover(ctx, h2b, k, A, L, sel):
+    """the parity test proper of row a1: the resident prover (every phase on the device, through the C ABI) against the
+    oracle's restatement of the whole create_proof flow on plain Python integers (oracle/prover_ref.py: recursive NTTs,
+    naive MSMs, row-by-row quotient, schoolbook divisions) — same instance, SRS, random polynomial and blinding rows:
+    every commitment (affine form) and every evaluation must be the same bytes, every challenge the same integer."""
+    from oracle import prover_ref
+    rng, params, cs, sess, inst, bases = _setup(ctx, h2b, k, 3700 + k + 10 * A, A, L, sel)
+    n = 1 << k
+    rnd = mont(rand_ints(rng, n, R), R)
+    sess.blind_log = []
+    res = _prove(sess, inst, rnd)
+    blinds = [unmont(b, R) for b in sess.blind_log]
+    sess.blind_log = None
+    it = iter(blinds)
+
+    def blind(rows):
+        b = next(it)
+        assert len(b) == rows
+        return b
+    aff = lambda B: [None if (x == 0 and y == 0) else (x, y) for x, y in zip(unmont(B[:, :4], pyref.P), unmont(B[:, 4:], pyref.P))]
+    want = prover_ref.create_proof(k, A, L, sel, {nm: unmont(inst["fixed"][nm], R) for nm in cs.fixed_names},
+                                   [unmont(sg, R) for sg in inst["sigma"]], unmont(inst["virtual"], R), [int(b) for b in inst["break_points"]],
+                                   unmont(inst["lookup"], R) if len(inst["lookup"]) else [], unmont(rnd, R), blind, aff(bases[0]), aff(bases[1]))
+    assert next(it, None) is None  # every blinding draw of the device prover was consumed, in the same order
+    assert res["challenges"] == want["challenges"]
+    assert [np.asarray(c, dtype=np.uint64).tobytes() for c in res["commitments"]] == want["commitments"]
+    assert [(nm, r) for nm, r in res["evals"]] == [(nm, r) for nm, r, _ in want["evals"]]
+    assert [np.asarray(v, dtype=np.uint64).tobytes() for v in res["evals"].values()] == [prover_ref.fr_bytes(v) for _, _, v in want["evals"]]
+    sess.free(); cs.free(); params.close()
+
+
 @pytest.mark.parametrize("k,A,L,sel", [(8, 1, 0, True), (8, 1, 0, False), (9, 7, 2, True)])
 def test_cpp_prover_matches_python(ctx, h2b, k, A, L, sel, tmp_path):
     """the compiled host side (include/h2b200_prover.hpp: ProverCircuit + ProverSession::create_proof, Blake2b transcript,
