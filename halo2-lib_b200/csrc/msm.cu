@@ -811,6 +811,7 @@ struct LaneScope {
 // multi-GPU run) are bound by the latency of the bucket reduction, which a group pays once.
 size_t msm_group_size(const h2b_ctx* ctx, size_t n, size_t m, int W) {
     if (msm_choose_levels(ctx, 1) > 0) return 1;  // the batch-affine passes are built for one MSM at a time
+    if ((size_t)W * n >= ((size_t)1 << 30)) return 1;  // no room for the table bit in a sorted entry: one MSM per pipeline
     static const int forced = [] {
         const char* e = getenv("H2B_MSM_GROUP");
         return e ? atoi(e) : 0;
