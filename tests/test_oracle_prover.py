@@ -75,7 +75,7 @@ def run(k, A, L, sel, seed, inst=None):
     return {"evals": {(nm, r): as_limbs(v) for nm, r, v in res["evals"]}, "challenges": res["challenges"], "commitments": res["commitments"]}
 
 
-@pytest.mark.parametrize("A,L,sel", [(1, 0, True), (1, 0, False), (2, 1, True)])
+@pytest.mark.parametrize("A,L,sel", [(1, 0, True), (1, 0, False), (2, 1, True), (3, 2, True)])
 def test_oracle_prover_satisfies_the_quotient_identity(A, L, sel):
     k = 5
     res = run(k, A, L, sel, 900 + 10 * A + L)
