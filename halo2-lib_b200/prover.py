@@ -359,6 +359,7 @@ class ProverSession:
         self.begin, self.n_loc, self.allreduce = 0, n, None
         self.keep = None  # verification runs: dict that receives the committed polynomials (downloaded, untimed)
         self.blind_log = None
+        self.blind_source = None  # optional callable rows -> (rows, 4) Montgomery limbs (tests: replay a fixed proof)
 
     def shard(self, begin: int, n_loc: int, allreduce):
         """multi-GPU: this rank commits rows [begin, begin + n_loc) of every polynomial and `allreduce(ptr, m)` combines the
@@ -400,8 +401,11 @@ class ProverSession:
 
     def _blind(self, col, first_row: int, rng: np.random.Generator):
         cnt = self.cs.n - first_row
-        b = rng.integers(0, 1 << 62, size=(cnt, 4), dtype=np.int64).astype(np.uint64)
-        b[:, 3] &= np.uint64((1 << 60) - 1)
+        if self.blind_source is not None:  # the caller's blinding scalars (Montgomery limbs), in the order of use
+            b = np.ascontiguousarray(self.blind_source(cnt), dtype=np.uint64).reshape(cnt, 4)
+        else:
+            b = rng.integers(0, 1 << 62, size=(cnt, 4), dtype=np.int64).astype(np.uint64)
+            b[:, 3] &= np.uint64((1 << 60) - 1)
         if self.blind_log is not None:  # the blinding rows in the order of use (the C++ twin replays them)
             self.blind_log.append(b)
         col.upload(b, first_row)

@@ -137,6 +137,34 @@ def test_resident_prover_matches_the_oracle_prover(ctx, h2b, k, A, L, sel):
     sess.free(); cs.free(); params.close()
 
 
+def test_resident_prover_reproduces_the_committed_golden_proof(ctx, h2b):
+    """tests/golden/prover_k5.json (made by tests/golden/make_golden_prover.py from the oracle prover on an integer-built
+    circuit): the CUDA path fed with the same instance, SRS, random polynomial and blinding rows writes the same bytes"""
+    import json, os, random
+    import test_oracle_prover as top
+    from golden import make_golden_prover as g
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prover_k5.json")))
+    k, A, L, sel, seed = g.K, g.A, g.L, g.SEL, g.SEED
+    n = 1 << k
+    inst = top.int_instance(k, A, L, sel, seed)
+    rr = random.Random(seed + 1)  # the draw order of test_oracle_prover.run: random polynomial first, then the blinding rows
+    rnd = mont([rr.randrange(R) for _ in range(n)], R)
+    to_limbs_pts = lambda pts: np.stack([np.concatenate([mont([x], pyref.P)[0], mont([y], pyref.P)[0]]) for x, y in pts])
+    bases_m, bases_l = to_limbs_pts(top.small_bases(n, 3, 5)), to_limbs_pts(top.small_bases(n, 7, 11))
+    params = h2b.ParamsKZG(ctx, k, g=bases_m, g_lagrange=bases_l)
+    fixed = {nm: mont(v, R) for nm, v in inst["fixed"].items()}
+    cs = h2b.Circuit(ctx, k, fixed, [mont(sg, R) for sg in inst["sigma"]], A=A, L=L, selector_lookup=sel)
+    sess = h2b.ProverSession(ctx, params, cs)
+    sess.blind_source = lambda rows: mont([rr.randrange(R) for _ in range(rows)], R)
+    v, lk = mont(inst["virtual"], R), mont(inst["lookup"], R)
+    res = sess.prove(v.ctypes.data, len(v), rnd.ctypes.data, break_points=np.array(inst["break_points"], dtype=np.uint64),
+                     lookup_ptr=lk.ctypes.data, n_lookup=len(lk))
+    assert {c: hex(x) for c, x in res["challenges"].items()} == want["challenges"]
+    assert [np.asarray(c, dtype=np.uint64).tobytes().hex() for c in res["commitments"]] == want["commitments_affine_montgomery"]
+    assert [[nm, r, np.asarray(x, dtype=np.uint64).tobytes().hex()] for (nm, r), x in res["evals"].items()] == want["evals_montgomery"]
+    sess.free(); cs.free(); params.close()
+
+
 @pytest.mark.parametrize("k,A,L,sel", [(8, 1, 0, True), (8, 1, 0, False), (9, 7, 2, True)])
 def test_cpp_prover_matches_python(ctx, h2b, k, A, L, sel, tmp_path):
     """the compiled host side (include/h2b200_prover.hpp: ProverCircuit + ProverSession::create_proof, Blake2b transcript,

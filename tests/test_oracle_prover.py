@@ -105,3 +105,11 @@ def test_oracle_prover_rejects_a_value_outside_the_table():
     inst["virtual"][3] = (inst["virtual"][0] + inst["virtual"][1] * inst["virtual"][2]) % R  # the gate still holds
     with pytest.raises(ValueError):
         run(5, 1, 0, True, 77, inst)
+
+
+def test_oracle_prover_reproduces_the_committed_golden_proof():
+    """tests/golden/prover_k5.json (tests/golden/make_golden_prover.py): the frozen answer of the oracle prover"""
+    import json, os
+    from golden import make_golden_prover as g
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prover_k5.json")))
+    assert g.proof() == json.loads(json.dumps(want))
